@@ -1,0 +1,148 @@
+// (a7) All-pairs consistency loss: forward + gradient in ONE streaming pass over the two
+// [B,L,N,N] head-mean stacks.  Reference: train_acr.py:143-161 (slices, 3*p in-place flips,
+// two F.l1_loss).  The flips are the index permutation pi(1+r*p+c) = 1+r*p+(p-1-c), pi(0)=0,
+// applied to rows and columns of view 2; it is done in index math here, so
+// neither input is modified and nothing is copied.
+//
+// HBM-bound: compulsory traffic = read A1, A2 once + write G1, G2 once = 16*B*L*N*N bytes.
+// One CTA per (b,l,i) row: row i of A1 is paired with row pi(i) of A2; column j with pi(j).
+// Per-row partial |d| sums go to a scratch array and are folded by a second, single-CTA kernel in a
+// fixed order (deterministic; no float atomics).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxPerThread = 16;  // supports N <= 4096
+
+__device__ __forceinline__ int flip_token(int t, int p) {
+  if (t == 0) return 0;
+  const int q = t - 1;
+  const int r = q / p;
+  const int c = q - r * p;
+  return 1 + r * p + (p - 1 - c);
+}
+
+template <bool kGrad>
+__global__ void __launch_bounds__(kThreads)
+consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ a2,
+                        int N, int p, float w_cls, float w_aff,
+                        float* __restrict__ g1, float* __restrict__ g2,
+                        float* __restrict__ partials) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;            // (b*L + l)*N + i
+  const int i = (int)(row % N);
+  const long long img = row / N;               // b*L + l
+  const int pi_i = flip_token(i, p);
+  const float* r1 = a1 + (img * N + i) * (long long)N;
+  const float* r2 = a2 + (img * N + pi_i) * (long long)N;
+  const float w = (i == 0) ? w_cls : w_aff;
+
+  float v1[kMaxPerThread], v2[kMaxPerThread];
+  int pj[kMaxPerThread];
+  const int per = (N + kThreads - 1) / kThreads;
+#pragma unroll
+  for (int k = 0; k < kMaxPerThread; ++k) {
+    if (k < per) {
+      const int j = threadIdx.x + k * kThreads;
+      if (j < N) {
+        pj[k] = flip_token(j, p);
+        v1[k] = __ldg(r1 + j);
+        v2[k] = __ldg(r2 + pj[k]);
+      }
+    }
+  }
+  float acc = 0.f;
+  float* o1 = kGrad ? g1 + (img * N + i) * (long long)N : nullptr;
+  float* o2 = kGrad ? g2 + (img * N + pi_i) * (long long)N : nullptr;
+#pragma unroll
+  for (int k = 0; k < kMaxPerThread; ++k) {
+    if (k < per) {
+      const int j = threadIdx.x + k * kThreads;
+      if (j < N) {
+        float s = 0.f;
+        if (j > 0) {
+          const float d = v1[k] - v2[k];
+          acc += fabsf(d);
+          s = (d > 0.f) ? w : ((d < 0.f) ? -w : 0.f);
+        }
+        if (kGrad) {
+          o1[j] = s;
+          o2[pj[k]] = -s;
+        }
+      }
+    }
+  }
+  const float tot = acr::block_sum(acc, red);
+  if (threadIdx.x == 0) partials[row] = tot;
+}
+
+// Folds the per-row partials: rows with i==0 feed cls_align, the rest aff_align.
+__global__ void __launch_bounds__(1024)
+consistency_finish_kernel(const float* __restrict__ partials, long long rows, int N,
+                          double inv_cls, double inv_aff, float* __restrict__ loss2) {
+  __shared__ double s_cls[32], s_aff[32];
+  double c = 0.0, a = 0.0;
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+    const float v = partials[r];
+    if (r % N == 0) c += (double)v; else a += (double)v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { s_cls[w] = c; s_aff[w] = a; }
+  __syncthreads();
+  if (w == 0) {
+    c = (lane < (int)(blockDim.x >> 5)) ? s_cls[lane] : 0.0;
+    a = (lane < (int)(blockDim.x >> 5)) ? s_aff[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+    }
+    if (lane == 0) {
+      loss2[0] = (float)(c * inv_cls);
+      loss2[1] = (float)(a * inv_aff);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" size_t acr_consistency_workspace(int B, int L, int N) {
+  if (B <= 0 || L <= 0 || N <= 0) return 0;
+  return acr::align_up((size_t)B * L * N * sizeof(float), 256);
+}
+
+extern "C" int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, int B, int L, int N, int p,
+                                       float alpha_cls, float alpha_aff,
+                                       float* loss2, float* g1, float* g2,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
+  ACR_REQUIRE(attn1 && attn2 && loss2 && workspace, ACR_E_INVAL, "acr_consistency_fwd_bwd: null pointer");
+  ACR_REQUIRE(B > 0 && L > 0 && p > 0, ACR_E_INVAL, "acr_consistency_fwd_bwd: bad B/L/p");
+  ACR_REQUIRE(N == p * p + 1, ACR_E_INVAL, "acr_consistency_fwd_bwd: N=%d is not p*p+1 (p=%d)", N, p);
+  ACR_REQUIRE(N <= kThreads * kMaxPerThread, ACR_E_INVAL, "acr_consistency_fwd_bwd: N=%d > %d unsupported", N,
+              kThreads * kMaxPerThread);
+  ACR_REQUIRE((g1 == nullptr) == (g2 == nullptr), ACR_E_INVAL, "acr_consistency_fwd_bwd: g1/g2 must both be set or null");
+  ACR_REQUIRE(workspace_bytes >= acr_consistency_workspace(B, L, N), ACR_E_NOMEM,
+              "acr_consistency_fwd_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)B * L * N;
+  ACR_REQUIRE(rows < (1ll << 31), ACR_E_INVAL, "acr_consistency_fwd_bwd: too many rows");
+  const double cnt_cls = (double)B * L * (N - 1);
+  const double cnt_aff = (double)B * L * (double)(N - 1) * (double)(N - 1);
+  const float w_cls = (float)((double)alpha_cls / cnt_cls);
+  const float w_aff = (float)((double)alpha_aff / cnt_aff);
+  float* partials = (float*)workspace;
+  if (g1) {
+    consistency_rows_kernel<true><<<(unsigned)rows, kThreads, 0, st>>>(attn1, attn2, N, p, w_cls, w_aff, g1, g2, partials);
+  } else {
+    consistency_rows_kernel<false><<<(unsigned)rows, kThreads, 0, st>>>(attn1, attn2, N, p, w_cls, w_aff, nullptr, nullptr, partials);
+  }
+  if (int e = acr::check_launch("consistency_rows_kernel")) return e;
+  consistency_finish_kernel<<<1, 1024, 0, st>>>(partials, rows, N, 1.0 / cnt_cls, 1.0 / cnt_aff, loss2);
+  return acr::check_launch("consistency_finish_kernel");
+}

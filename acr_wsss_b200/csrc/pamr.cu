@@ -1,0 +1,206 @@
+// (a10) PAMR -- pixel-adaptive mask refinement.  Reference: pamr.py:10-144.
+//
+// The reference builds [B,K,9D,H,W] / [B,K,8D,H,W] / [B,C,8D,H,W] intermediates with one-hot dilated
+// conv2d calls (pamr.py:51-52) -- 810 MB per iteration at C=21, D=6, 448x448.  Here:
+//   1. pamr_upsample_kernel   : bilinear, align_corners=True (pamr.py:126) into a ping buffer;
+//   2. pamr_affinity_kernel   : per pixel, the 8D softmax weights w[b,n,y,x] (std over the 9D samples,
+//                               -|xc-xn|/(1e-8+0.1 std), mean over the K image channels, softmax over n);
+//   3. pamr_iter_kernel x num_iter : mask[b,c,y,x] <- sum_n w[b,n,y,x] * mask[b,c,clamp(y+dy),clamp(x+dx)].
+// Neighbour order per dilation is row-major over the 3x3 window without its centre (pamr.py:24-33);
+// dilations are concatenated in list order (pamr.py:55); borders replicate (pamr.py:51).
+// Bandwidth-bound: algorithmic bytes = HW(4K + 32D) for step 2 and HW(32D + 8C) per iteration.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxDil = 8;
+struct Dil { int d[kMaxDil]; int n; };
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__global__ void __launch_bounds__(256)
+pamr_upsample_kernel(const float* __restrict__ src, int planes, int h, int w, int H, int W, float* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)planes * H * W;
+  if (idx >= total) return;
+  const int x = (int)(idx % W);
+  const int y = (int)((idx / W) % H);
+  const long long pl = idx / ((long long)W * H);
+  const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
+  const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
+  const float fy = sy * (float)y, fx = sx * (float)x;
+  const int y0 = min((int)fy, h - 1), x0 = min((int)fx, w - 1);
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float* p = src + pl * h * w;
+  const float v = hy * (hx * __ldg(p + y0 * w + x0) + lx * __ldg(p + y0 * w + x1)) +
+                  ly * (hx * __ldg(p + y1 * w + x0) + lx * __ldg(p + y1 * w + x1));
+  dst[idx] = v;
+}
+
+// One thread per pixel.  wgt layout [B, 8*nd, H, W].
+__global__ void __launch_bounds__(256)
+pamr_affinity_kernel(const float* __restrict__ x, int K, int H, int W, Dil dil, float* __restrict__ wgt) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  const int py = blockIdx.y;
+  const int b = blockIdx.z;
+  if (px >= W) return;
+  const long long HW = (long long)H * W;
+  const int nn = 8 * dil.n;
+  float* wp = wgt + (long long)b * nn * HW + (long long)py * W + px;
+  const float invK = 1.f / (float)K;
+
+  for (int k = 0; k < K; ++k) {
+    const float* img = x + ((long long)b * K + k) * HW;
+    const float xc = __ldg(img + (long long)py * W + px);
+    // unbiased std over the 9*nd samples (centre counted once per dilation), two-pass like torch.std
+    float sum = 0.f;
+    for (int di = 0; di < dil.n; ++di) {
+      const int d = dil.d[di];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = clampi(py + (t / 3 - 1) * d, 0, H - 1), xx = clampi(px + (t % 3 - 1) * d, 0, W - 1);
+        sum += __ldg(img + (long long)yy * W + xx);
+      }
+    }
+    const int cnt = 9 * dil.n;
+    const float mean = sum / (float)cnt;
+    float ss = 0.f;
+    for (int di = 0; di < dil.n; ++di) {
+      const int d = dil.d[di];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = clampi(py + (t / 3 - 1) * d, 0, H - 1), xx = clampi(px + (t % 3 - 1) * d, 0, W - 1);
+        const float dv = __ldg(img + (long long)yy * W + xx) - mean;
+        ss += dv * dv;
+      }
+    }
+    const float sd = sqrtf(ss / (float)(cnt - 1));
+    const float inv = 1.f / (1e-8f + 0.1f * sd);
+    int n = 0;
+    for (int di = 0; di < dil.n; ++di) {
+      const int d = dil.d[di];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (t == 4) continue;
+        const int yy = clampi(py + (t / 3 - 1) * d, 0, H - 1), xx = clampi(px + (t % 3 - 1) * d, 0, W - 1);
+        const float a = -fabsf(xc - __ldg(img + (long long)yy * W + xx)) * inv;
+        float* o = wp + (long long)n * HW;
+        *o = (k == 0) ? a : (*o + a);
+        ++n;
+      }
+    }
+  }
+  // mean over channels + softmax over the neighbour axis
+  float m = -INFINITY;
+  for (int n = 0; n < nn; ++n) {
+    const float v = wp[(long long)n * HW] * invK;
+    wp[(long long)n * HW] = v;
+    m = fmaxf(m, v);
+  }
+  float s = 0.f;
+  for (int n = 0; n < nn; ++n) {
+    const float e = expf(wp[(long long)n * HW] - m);
+    wp[(long long)n * HW] = e;
+    s += e;
+  }
+  const float invs = 1.f / s;
+  for (int n = 0; n < nn; ++n) wp[(long long)n * HW] *= invs;
+}
+
+// One thread per pixel and channel group.  grid (ceil(W/256), H, B*groups).
+template <int CG>
+__global__ void __launch_bounds__(256)
+pamr_iter_kernel(const float* __restrict__ wgt, const float* __restrict__ min_, float* __restrict__ mout,
+                 int C, int H, int W, Dil dil, int groups) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  const int py = blockIdx.y;
+  const int b = blockIdx.z / groups, g = blockIdx.z % groups;
+  if (px >= W) return;
+  const long long HW = (long long)H * W;
+  const int nn = 8 * dil.n;
+  const float* wp = wgt + (long long)b * nn * HW + (long long)py * W + px;
+  const int c0 = g * CG;
+  float acc[CG];
+#pragma unroll
+  for (int c = 0; c < CG; ++c) acc[c] = 0.f;
+  const float* mb = min_ + ((long long)b * C + c0) * HW;
+  int n = 0;
+  for (int di = 0; di < dil.n; ++di) {
+    const int d = dil.d[di];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (t == 4) continue;
+      const int yy = clampi(py + (t / 3 - 1) * d, 0, H - 1), xx = clampi(px + (t % 3 - 1) * d, 0, W - 1);
+      const float wv = __ldg(wp + (long long)n * HW);
+      const float* mp = mb + (long long)yy * W + xx;
+#pragma unroll
+      for (int c = 0; c < CG; ++c)
+        if (c0 + c < C) acc[c] = fmaf(wv, __ldg(mp + c * HW), acc[c]);
+      ++n;
+    }
+  }
+  float* op = mout + ((long long)b * C + c0) * HW + (long long)py * W + px;
+#pragma unroll
+  for (int c = 0; c < CG; ++c)
+    if (c0 + c < C) op[c * HW] = acc[c];
+}
+
+}  // namespace
+
+extern "C" size_t acr_pamr_workspace(int B, int K, int C, int H, int W, int nd) {
+  if (B <= 0 || K <= 0 || C <= 0 || H <= 0 || W <= 0 || nd <= 0) return 0;
+  const size_t hw = (size_t)H * W;
+  return acr::align_up((size_t)B * 8 * nd * hw * sizeof(float), 256) + 2 * acr::align_up((size_t)B * C * hw * sizeof(float), 256);
+}
+
+extern "C" int acr_pamr_fwd(const float* x, const float* mask, int B, int K, int C, int H, int W, int mh, int mw,
+                            const int* dilations_host, int nd, int num_iter,
+                            float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  ACR_REQUIRE(x && mask && out && workspace && dilations_host, ACR_E_INVAL, "acr_pamr_fwd: null pointer");
+  ACR_REQUIRE(B > 0 && K > 0 && C > 0 && H > 0 && W > 0 && mh > 0 && mw > 0, ACR_E_INVAL, "acr_pamr_fwd: bad shape");
+  ACR_REQUIRE(nd >= 1 && nd <= kMaxDil, ACR_E_INVAL, "acr_pamr_fwd: 1 <= len(dilations) <= %d required", kMaxDil);
+  ACR_REQUIRE(num_iter >= 0, ACR_E_INVAL, "acr_pamr_fwd: num_iter < 0");
+  ACR_REQUIRE(workspace_bytes >= acr_pamr_workspace(B, K, C, H, W, nd), ACR_E_NOMEM, "acr_pamr_fwd: workspace too small");
+  ACR_REQUIRE(H <= 65535 && (long long)B * C <= 65535, ACR_E_INVAL, "acr_pamr_fwd: grid too large");
+  Dil dil;
+  dil.n = nd;
+  for (int i = 0; i < kMaxDil; ++i) dil.d[i] = 0;
+  for (int i = 0; i < nd; ++i) {
+    ACR_REQUIRE(dilations_host[i] >= 1, ACR_E_INVAL, "acr_pamr_fwd: dilation < 1");
+    dil.d[i] = dilations_host[i];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t hw = (size_t)H * W;
+  char* ws = (char*)workspace;
+  float* wgt = (float*)ws;
+  ws += acr::align_up((size_t)B * 8 * nd * hw * sizeof(float), 256);
+  float* ping = (float*)ws;
+  ws += acr::align_up((size_t)B * C * hw * sizeof(float), 256);
+  float* pong = (float*)ws;
+
+  float* first = (num_iter == 0) ? out : ping;
+  {
+    const long long total = (long long)B * C * hw;
+    pamr_upsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mask, B * C, mh, mw, H, W, first);
+    if (int e = acr::check_launch("pamr_upsample_kernel")) return e;
+  }
+  if (num_iter == 0) return 0;
+  {
+    dim3 grid((W + 255) / 256, H, B);
+    pamr_affinity_kernel<<<grid, 256, 0, st>>>(x, K, H, W, dil, wgt);
+    if (int e = acr::check_launch("pamr_affinity_kernel")) return e;
+  }
+  constexpr int CG = 8;
+  const int groups = (C + CG - 1) / CG;
+  const float* cur = ping;
+  for (int it = 0; it < num_iter; ++it) {
+    float* dst = (it == num_iter - 1) ? out : ((cur == ping) ? pong : ping);
+    dim3 grid((W + 255) / 256, H, B * groups);
+    pamr_iter_kernel<CG><<<grid, 256, 0, st>>>(wgt, cur, dst, C, H, W, dil, groups);
+    if (int e = acr::check_launch("pamr_iter_kernel")) return e;
+    cur = dst;
+  }
+  return 0;
+}

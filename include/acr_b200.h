@@ -1,0 +1,152 @@
+/*
+ * acr_b200.h -- C ABI of libacr_b200.so: the B200 (sm_100a) implementation of the ACR_WSSS
+ * all-pairs attention-affinity hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: 0 = ok, <0 = invalid argument (ACR_E_*), >0 = a cudaError_t value;
+ *     acr_last_error_string() describes the last failure on the calling thread;
+ *   - no exceptions, no global state besides a lazily created per-device workspace cache;
+ *   - there is no CPU fallback: with no usable sm_100 device every compute entry point fails.
+ *
+ * Each entry point cites the reference interface (file:line under the ACR_WSSS tree) it replaces.
+ */
+#ifndef ACR_B200_H_
+#define ACR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACR_B200_ABI_VERSION 1
+
+#define ACR_E_INVAL   (-1)  /* bad shape / null pointer / unsupported size          */
+#define ACR_E_ALIGN   (-2)  /* pointer alignment requirement violated               */
+#define ACR_E_NOSM100 (-3)  /* kernel needs an sm_100 device and none is current    */
+#define ACR_E_NOMEM   (-4)  /* workspace too small                                  */
+
+int acr_abi_version(void);
+const char* acr_last_error_string(void);
+/* 1 when the current device is compute capability 10.x (tcgen05/TMEM/TMA kernels usable). */
+int acr_device_is_sm100(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (a1) Attention core.  Replaces models/vision_transformer.py:198-214 (Attention.forward, the part
+ * between the qkv Linear and the proj Linear) together with the head mean of DPT/ACR.py:107-112.
+ *
+ * qkv is the output of the qkv Linear, UNPERMUTED: element (b,n,s,h,d) at ((b*N+n)*3+s)*H*D + h*D + d
+ * (s=0 q, 1 k, 2 v) -- exactly the buffer the reference reshapes at vision_transformer.py:200.
+ * out is [B,N,H*D] (the layout proj consumes, vision_transformer.py:211).
+ * attn_mean points at slot l of the [B,L,N,N] fp32 stack: image b's N x N map starts at
+ * attn_mean + b*mean_batch_stride (elements); rows are dense (stride N).  May be NULL.
+ * p_row0 (nullable) receives the per-head softmax row of the cls token, [B,H,N] fp32 (GETAM, a8).
+ * ------------------------------------------------------------------------------------------ */
+
+/* Fused sm_100a path: bf16 operands, fp32 accumulate, tcgen05/TMEM/TMA.  D must be 64.
+ * lse [B,H,N] fp32 receives log-sum-exp of the scaled scores (natural log) for the backward. */
+int acr_attn_fwd_bf16(const void* qkv_bf16, int B, int N, int H, int D, float scale,
+                      void* out_bf16, float* lse,
+                      float* attn_mean, long long mean_batch_stride,
+                      float* p_row0, void* stream);
+
+/* Backward of the above with the dense affinity-gradient term:
+ *   dP_h = dO_h V_h^T + g_mean / H ;  dS_h = P_h * (dP_h - rowsum(P_h * dP_h)) ; dQ,dK,dV as usual.
+ * g_mean (nullable) = dLoss/dA-bar for this block, image b at g_mean + b*g_batch_stride, rows dense.
+ * d_qkv_bf16 has the layout of qkv.  g_row0 (nullable, [B,H,N] fp32) receives row 0 of dP_h, which is
+ * what the reference's save_attn_gradients hook keeps and getam consumes (DPT/ACR.py:182-213).
+ * workspace: acr_attn_bwd_bf16_workspace() bytes, 256-byte aligned. */
+size_t acr_attn_bwd_bf16_workspace(int B, int N, int H, int D);
+int acr_attn_bwd_bf16(const void* qkv_bf16, const void* out_bf16, const float* lse,
+                      const void* d_out_bf16, int B, int N, int H, int D, float scale,
+                      const float* g_mean, long long g_batch_stride,
+                      void* d_qkv_bf16, float* g_row0,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Exact fp32 path (materialises P like the reference does; used for 1e-3 parity and for the
+ * get_attn()/get_attn_gradients() accessor protocol, vision_transformer.py:186-196).
+ * P [B,H,N,N] fp32 is written; out [B,N,H*D] fp32. */
+int acr_attn_fwd_f32(const float* qkv, int B, int N, int H, int D, float scale,
+                     float* P, float* out,
+                     float* attn_mean, long long mean_batch_stride, void* stream);
+/* dP [B,H,N,N] is a required output: on return it holds dP_h (= what the reference hook stores).
+ * dS [B,H,N,N] is caller-provided scratch; d_qkv has the layout of qkv. */
+int acr_attn_bwd_f32(const float* qkv, const float* P, const float* d_out,
+                     int B, int N, int H, int D, float scale,
+                     const float* g_mean, long long g_batch_stride,
+                     float* dP, float* dS, float* d_qkv, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a7) All-pairs consistency loss, forward and gradient in one pass.
+ * Replaces train_acr.py:143-161 (= train_acr_coco.py:140-158): the slicing, the 3*p in-place
+ * flips and the two F.l1_loss calls.  attn1/attn2 are the [B,L,N,N] fp32 stacks of the two views
+ * (N = p*p+1), NOT modified.  loss2[0] = cls_align, loss2[1] = aff_align (means, before alpha).
+ * g1/g2 (nullable together) receive alpha_cls*d(cls_align)/dA + alpha_aff*d(aff_align)/dA.
+ * partials: scratch of acr_consistency_workspace() bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t acr_consistency_workspace(int B, int L, int N);
+int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, int B, int L, int N, int p,
+                            float alpha_cls, float alpha_aff,
+                            float* loss2, float* g1, float* g2,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a8) GETAM from row-0 quantities.  Replaces ACR.getam, DPT/ACR.py:177-215, for the part that
+ * reaches the result (row 0 of each block's map).  p_row0/g_row0: [L,H,N] fp32 for ONE image
+ * (per-block, per-head cls-token row of P and of dP).  func: 0 'grad', 1 'grad_s', 2 'cam_grad',
+ * 3 'cam_grad_s'.  skip = 1 (2 for the distilled DeiT variant).  cam_out [N-skip] fp32.
+ * cam_rows (nullable) [L,N] receives each block's c_l row 0.
+ * ------------------------------------------------------------------------------------------ */
+int acr_getam_row0(const float* p_row0, const float* g_row0, int L, int H, int N,
+                   int start_layer, int func, int skip,
+                   float* cam_out, float* cam_rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a9) Affinity refinement.  Replaces infer_cam.py:164-165 (patch_aff = sum_l attn[:,l,1:,1:]) and
+ * infer_cam.py:184 (matmul(patch_aff, cam)), batched over classes.
+ * attn [B,L,N,N] fp32 -> A [B,Np,Np] with Np=N-1.  If normalize!=0 rows of A are divided by their sum.
+ * cam [B,Np,C] -> out [B,Np,C] = A^t cam (t>=1).  tmp is [B,Np,C] scratch (only touched when t>1).
+ * ------------------------------------------------------------------------------------------ */
+int acr_affinity_sum(const float* attn, int B, int L, int N, int normalize, float* A, void* stream);
+int acr_affinity_refine(const float* A, const float* cam, int B, int Np, int C, int t,
+                        float* out, float* tmp, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a10) PAMR.  Replaces PAMR.forward, pamr.py:125-144, including the bilinear (align_corners=True)
+ * up-sampling of the mask (pamr.py:126): x [B,K,H,W] image, mask [B,C,mh,mw], dilations_host[nd] on
+ * the HOST (1 <= nd <= 8).  out [B,C,H,W].  workspace: acr_pamr_workspace() bytes (affinity planes +
+ * ping-pong mask).
+ * ------------------------------------------------------------------------------------------ */
+size_t acr_pamr_workspace(int B, int K, int C, int H, int W, int nd);
+int acr_pamr_fwd(const float* x, const float* mask, int B, int K, int C, int H, int W, int mh, int mw,
+                 const int* dilations_host, int nd, int num_iter,
+                 float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a11) Permutohedral bilateral filter.  Replaces bilateralfilter_batch,
+ * wrapper/bilateralfilter/bilateralfilter.cpp:42-55 (and Permutohedral::init/compute,
+ * permutohedral.cpp:115-440,507-631).  Same argument meaning and order as the SWIG export
+ * (bilateralfilter.hpp:12); images [N,3,H,W] in 0..255, ins/outs [N,K,H,W], fp32.
+ *   acr_bilateral_batch       : DEVICE buffers + workspace (acr_bilateral_workspace() bytes).
+ *   bilateralfilter_batch_b200: HOST buffers, the literal drop-in for the SWIG symbol (copies
+ *                               host->device, runs the kernels, copies back; returns void like the
+ *                               reference; on failure `outs` is left untouched and the error is
+ *                               readable through acr_last_error_string()).
+ * lattice_size_host (nullable) receives M (number of lattice vertices) per image, for reporting.
+ * ------------------------------------------------------------------------------------------ */
+size_t acr_bilateral_workspace(int N, int K, int H, int W);
+int acr_bilateral_batch(const float* images, const float* ins, float* outs,
+                        int N, int K, int H, int W, float sigmargb, float sigmaxy,
+                        void* workspace, size_t workspace_bytes, int* lattice_size_host, void* stream);
+void bilateralfilter_batch_b200(const float* images_host, int len_images, const float* ins_host, int len_ins,
+                                float* outs_host, int len_outs,
+                                int N, int K, int H, int W, float sigmargb, float sigmaxy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACR_B200_H_ */
