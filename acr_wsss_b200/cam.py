@@ -1,0 +1,100 @@
+"""CAM inference with affinity refinement: the inline block infer_cam.py:145-215, lifted into functions.
+
+`infer_cam_image` reproduces the per-image loop body (scales x flips x present classes) with the hot pieces
+on this repo's kernels: head-mean stack (fused attention), GETAM from row-0 quantities, A = sum_l attn[:,l,1:,1:]
+and ONE [Np x Np]x[Np x C'] contraction for all present classes instead of C' matrix-vector products.
+Bilinear resizes are library calls (F.interpolate), exactly the ones the reference makes.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+
+
+def affinity_refine(attn, cam, t=1, normalize=False):
+    """infer_cam.py:164-165,184.  attn [B,L,N,N]; cam [B,N-1,C] or [B,N-1] -> same shape as cam.
+
+    t=1, normalize=False is the reference (A is the plain sum over blocks, applied once);
+    t>1 / normalize=True is the generalisation named by the north star (row-normalised affinity power).
+    """
+    A = ops.affinity_sum(attn, normalize)
+    squeeze = cam.dim() == 2
+    c3 = cam.unsqueeze(-1) if squeeze else cam
+    out = ops.affinity_apply(A, c3, t)
+    return out.squeeze(-1) if squeeze else out
+
+
+def normalize_cam(sum_cam, eps):
+    """Per-class min-max normalisation, infer_cam.py:202,209 (eps 1e-5 patch CAM / 1e-6 GETAM).  [C,H,W]."""
+    mn = sum_cam.amin(dim=(1, 2), keepdim=True)
+    mx = sum_cam.amax(dim=(1, 2), keepdim=True)
+    return (sum_cam - mn) / (mx - mn + eps)
+
+
+def pseudo_label(cam_dict, num_classes, threshold):
+    """evaluation.py:30-36: argmax over [threshold, cam_1..cam_C] -> uint8 label map."""
+    h, w = next(iter(cam_dict.values())).shape
+    tensor = np.zeros((num_classes + 1, h, w), np.float32)
+    for key, v in cam_dict.items():
+        tensor[key + 1] = v
+    tensor[0, :, :] = threshold
+    return np.argmax(tensor, axis=0).astype(np.uint8)
+
+
+def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, getam_func="cam_grad_s",
+                    aff=True, t=1, normalize=False):
+    """One image of the infer_cam.py loop body (:145-215).
+
+    img [1,3,h,w] (normalised), label [1,C] multi-hot, out_size = (rows, cols) of the original image (the
+    reference calls these W,H at infer_cam.py:136).  Returns (cam_dict, patch_cam_dict, norm_cam [C,rows,cols])
+    with {class_index: float32 [rows,cols]} dicts as saved by np.save at :227-228.
+    """
+    assert img.shape[0] == 1, "the reference infers one image at a time (infer_cam.py:122)"
+    C = label.shape[1]
+    b, c, h, w = img.shape
+    rows, cols = out_size
+    present = [ci for ci in range(C) if float(label[0, ci]) > 1e-5]
+    cam_list, patch_cam_list = [], []
+    for scale in scales:
+        for hflip in (1, 2):
+            model.zero_grad()
+            inp = F.interpolate(img, size=(int(h * scale), int(w * scale)), mode="bilinear", align_corners=False)
+            if hflip % 2 == 1:
+                inp = inp.flip(-1)
+            ph, pw = int((h * scale) // 16), int((w * scale) // 16)
+            cls_pred, _, attn, patch_cam = model.forward_cam(inp)
+            patch_cam = patch_cam.permute(0, 2, 1).reshape(1, C, ph, pw)
+            patch_cam = F.interpolate(patch_cam, [rows, cols], mode="bilinear", align_corners=False)[0]
+            patch_cam = patch_cam.detach() * label[0, :].view(C, 1, 1)
+            if hflip % 2 == 1:
+                patch_cam = patch_cam.flip(-1)
+            patch_cam_list.append(patch_cam)
+
+            output = cls_pred[0, :]
+            rows0 = []
+            for ci in present:
+                model.zero_grad()
+                output[ci].backward(retain_graph=True)          # one_hot * output, infer_cam.py:173-179
+                cam, _, _ = model.getam(0, start_layer=start_layer, func=getam_func)
+                rows0.append(cam[0])
+            cam_matrix = torch.zeros(C, rows, cols, device=img.device)
+            if present:
+                cams = torch.stack(rows0, dim=1).unsqueeze(0)        # [1,Np,C']
+                if aff:
+                    cams = affinity_refine(attn.detach(), cams, t=t, normalize=normalize)
+                cams = cams[0].t().reshape(len(present), 1, ph, pw)
+                cams = F.interpolate(cams, (rows, cols), mode="bilinear", align_corners=True)[:, 0]
+                cam_matrix[present] = cams
+            if hflip % 2 == 1:
+                cam_matrix = cam_matrix.flip(-1)
+            cam_list.append(cam_matrix)
+    patch_sum = torch.stack(patch_cam_list).sum(0)
+    patch_norm = normalize_cam(patch_sum, 1e-5)
+    sum_cam = torch.stack(cam_list).sum(0)
+    norm_cam = normalize_cam(sum_cam, 1e-6)
+    norm_np = norm_cam.cpu().numpy()
+    patch_np = patch_norm.cpu().numpy()
+    cam_dict = {ci: norm_np[ci] for ci in present}
+    patch_cam_dict = {ci: patch_np[ci] for ci in present}
+    return cam_dict, patch_cam_dict, norm_cam

@@ -1,0 +1,328 @@
+"""Host-side mirror of the reference's model interface for the hot path.
+
+Mirrors (same class / method names, argument meaning, return structures and state_dict keys):
+  * models/vision_transformer.py:167-214  Attention  (forward, get_attn, get_attn_gradients, qkv/proj/num_heads/scale)
+  * models/vision_transformer.py:216-233  Block, :148-164 Mlp, :449-504 forward_flex / _resize_pos_embed
+  * DPT/ACR.py:40-143  DPT.forward_cls / forward_cam,  :147-215  ACR.forward_mirror / getam / load
+
+Only the attention core, the head mean / stack and GETAM run in this repo's kernels; LayerNorm, the Linear
+layers, GELU and the patch convolution are library calls ("GEMMs stay library").
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+_BACKBONES = {
+    # name -> (embed_dim, depth, heads, hooks, scratch in-features)
+    "vitb16_384": (768, 12, 12, [2, 5, 8, 11], [96, 192, 384, 768]),
+    "deitb16_384": (768, 12, 12, [2, 5, 8, 11], [96, 192, 384, 768]),
+    "vitl16_384": (1024, 24, 16, [5, 11, 17, 23], [256, 512, 1024, 1024]),
+}
+_BACKBONE_ALIASES = {"vitb": "vitb16_384", "deit": "deitb16_384", "vitl": "vitl16_384"}
+
+
+class Attention(nn.Module):
+    """Drop-in for models/vision_transformer.py:167-214.
+
+    precision 'fp32': exact path, P and dP are materialised, so get_attn()/get_attn_gradients() return the
+    same [B,H,N,N] tensors as the reference.  precision 'bf16': fused tcgen05 kernel; P never reaches HBM,
+    get_attn() recomputes it on demand from the saved qkv, and only row 0 of dP is kept (all GETAM needs).
+    """
+
+    def __init__(self, dim, num_heads=8, qkv_bias=False, qk_scale=None, attn_drop=0., proj_drop=0., precision="fp32"):
+        super().__init__()
+        if attn_drop != 0. or proj_drop != 0.:
+            raise NotImplementedError("the ACR path runs with attn_drop = proj_drop = 0 (vision_transformer.py:205)")
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.proj = nn.Linear(dim, dim)
+        self.precision = precision
+        self.capture_grad = True       # keep dP (fp32) / its row 0 (bf16) in backward, like the reference hook
+        self._state = {}
+        self._slot = None              # [B,N,N] view of this block's slot in the [B,L,N,N] stack
+        self.attn_mean = None          # head-mean map of the last recorded forward
+
+    # -- accessor protocol (vision_transformer.py:186-196) --
+    def get_attn(self):
+        st = self._state
+        if st.get("attn") is not None:
+            return st["attn"]
+        if st.get("qkv") is not None:          # fused path: recompute on demand through the exact kernels
+            qkv = st["qkv"].float()
+            with torch.no_grad():
+                tmp = {}
+                ops.attention_core(qkv, self.num_heads, self.scale, None, tmp, "fp32")
+            return tmp["attn"]
+        return None
+
+    def get_attn_gradients(self):
+        return self._state.get("attn_grad")
+
+    def get_attn_row0(self):
+        """Per-head cls-token row of P, [B,H,N]."""
+        st = self._state
+        if st.get("row0") is not None:
+            return st["row0"]
+        return st["attn"][:, :, 0, :] if st.get("attn") is not None else None
+
+    def get_attn_gradients_row0(self):
+        st = self._state
+        if st.get("grad_row0") is not None:
+            return st["grad_row0"]
+        return st["attn_grad"][:, :, 0, :] if st.get("attn_grad") is not None else None
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = self.qkv(x)
+        # The reference refreshes its saved map only when x.requires_grad (vision_transformer.py:207-209).
+        record = x.requires_grad
+        state = None
+        if record:
+            state = {"capture_grad": self.capture_grad}
+        out, mean = ops.attention_core(qkv, self.num_heads, self.scale, self._slot if record else None, state,
+                                       self.precision)
+        if record:
+            self._state = state
+            self.attn_mean = mean
+        out = out.to(x.dtype) if out.dtype != x.dtype and not torch.is_autocast_enabled() else out
+        return self.proj(out)
+
+
+class Mlp(nn.Module):
+    def __init__(self, in_features, hidden_features=None, out_features=None):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class Block(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio=4., qkv_bias=True, precision="fp32"):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = Attention(dim, num_heads=num_heads, qkv_bias=qkv_bias, precision=precision)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        x = x + self.mlp(self.norm2(x))
+        return x
+
+
+class PatchEmbed(nn.Module):
+    def __init__(self, img_size=384, patch_size=16, in_chans=3, embed_dim=768):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+
+def _trunc_normal_(t, std=.02):
+    return nn.init.trunc_normal_(t, std=std, a=-2., b=2.)
+
+
+class VisionTransformer(nn.Module):
+    """The parts of models/vision_transformer.py:VisionTransformer the ACR path touches (forward_flex)."""
+
+    def __init__(self, img_size=384, patch_size=16, embed_dim=768, depth=12, num_heads=12, num_classes=1000,
+                 precision="fp32"):
+        super().__init__()
+        self.patch_size = [patch_size, patch_size]
+        self.start_index = 1
+        self.embed_dim = embed_dim
+        self.patch_embed = PatchEmbed(img_size, patch_size, 3, embed_dim)
+        num_patches = (img_size // patch_size) ** 2
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.bkg_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, num_patches + 1, embed_dim))
+        self.blocks = nn.ModuleList([Block(embed_dim, num_heads, 4., True, precision) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.head = nn.Linear(embed_dim, num_classes)
+        # init as vision_transformer.py:339-349,548
+        _trunc_normal_(self.pos_embed)
+        _trunc_normal_(self.cls_token)
+        _trunc_normal_(self.bkg_token)
+        self.apply(self._init_weights)
+
+    @staticmethod
+    def _init_weights(m):
+        if isinstance(m, nn.Linear):
+            _trunc_normal_(m.weight)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.zeros_(m.bias)
+            nn.init.ones_(m.weight)
+
+    def _resize_pos_embed(self, posemb, gs_h, gs_w):
+        # vision_transformer.py:490-504
+        posemb_tok, posemb_grid = posemb[:, :self.start_index], posemb[0, self.start_index:]
+        gs_old = int(math.sqrt(len(posemb_grid)))
+        posemb_grid = posemb_grid.reshape(1, gs_old, gs_old, -1).permute(0, 3, 1, 2)
+        posemb_grid = F.interpolate(posemb_grid, size=(gs_h, gs_w), mode="bilinear")
+        posemb_grid = posemb_grid.permute(0, 2, 3, 1).reshape(1, gs_h * gs_w, -1)
+        return torch.cat([posemb_tok, posemb_grid], dim=1)
+
+    def forward_flex(self, x, last_block_out=None):
+        """vision_transformer.py:449-486.  Returns (norm(x), None); `last_block_out`, if a list, receives the
+        un-normalised output of the last block (what the reference reads through its forward hook, Q4)."""
+        b, c, h, w = x.shape
+        pos_embed = self._resize_pos_embed(self.pos_embed, h // self.patch_size[1], w // self.patch_size[0])
+        x = self.patch_embed.proj(x).flatten(2).transpose(1, 2)
+        cls_tokens = self.cls_token.expand(b, -1, -1)
+        x = torch.cat((cls_tokens.to(x.dtype), x), dim=1)
+        x = x + pos_embed.to(x.dtype)
+        for blk in self.blocks:
+            x = blk(x)
+        if last_block_out is not None:
+            last_block_out.append(x)
+        return self.norm(x), None
+
+
+class _Pretrained(nn.Module):
+    def __init__(self, model):
+        super().__init__()
+        self.model = model
+        self.activations = {}
+
+
+class _Scratch(nn.Module):
+    def __init__(self, in_shape, features=256):
+        super().__init__()
+        # DPT/blocks.py _make_scratch: present in the state_dict, dead on the ACR path
+        for i, c in enumerate(in_shape):
+            setattr(self, f"layer{i + 1}_rn", nn.Conv2d(c, features, kernel_size=3, stride=1, padding=1, bias=False))
+
+
+class ACR(nn.Module):
+    """Drop-in for DPT/ACR.py:147-215 (class ACR) and :40-143 (class DPT) on the plain-ViT backbones.
+
+    ACR(num_classes, backbone_name, path=None, precision='fp32'|'bf16').  `use_pretrain` is accepted and
+    ignored (weights are random-init or come from `path` / load_state_dict; there is no network here).
+    """
+
+    def __init__(self, num_classes, backbone_name, path=None, precision="fp32", features=256, **kwargs):
+        super().__init__()
+        self.num_class = num_classes
+        cur = _BACKBONE_ALIASES.get(backbone_name, backbone_name)
+        if cur not in _BACKBONES:
+            raise NotImplementedError(f"backbone {backbone_name!r}: only the plain ViT backbones are on the hot path "
+                                      "(SURVEY section 2 rows 13-14)")
+        self.cur_backbone = cur
+        self.precision = precision
+        dim, depth, heads, hooks, scratch_in = _BACKBONES[cur]
+        self.hooks = hooks
+        self.pretrained = _Pretrained(VisionTransformer(384, 16, dim, depth, heads, 1000, precision))
+        self.scratch = _Scratch(scratch_in, features)
+        # The reference hard-codes 768 (DPT/ACR.py:88), which breaks ViT-L; use the trunk width.
+        self.cls_head = nn.Linear(dim, num_classes)
+        self.use_gap = True
+        if path is not None:
+            self.load(path)
+
+    def load(self, path):
+        parameters = torch.load(path, map_location=torch.device("cpu"))
+        if "optimizer" in parameters:
+            parameters = parameters["model"]
+        self.load_state_dict(parameters)
+
+    def set_capture_grad(self, flag):
+        for blk in self.pretrained.model.blocks:
+            blk.attn.capture_grad = flag
+
+    # ------------------------------------------------------------------ trunk
+    def _trunk(self, x):
+        vit = self.pretrained.model
+        B = x.shape[0]
+        p_h, p_w = x.shape[2] // 16, x.shape[3] // 16
+        N = p_h * p_w + 1
+        L = len(vit.blocks)
+        stack = None
+        record = torch.is_grad_enabled()
+        if record:
+            stack = torch.empty(B, L, N, N, device=x.device, dtype=torch.float32)
+        for l, blk in enumerate(vit.blocks):
+            blk.attn._slot = stack[:, l] if record else None
+        last = []
+        if self.precision == "bf16":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                vit.forward_flex(x, last)
+        else:
+            vit.forward_flex(x, last)
+        layer_4 = last[0].float()
+        self.pretrained.activations["4"] = layer_4
+        for blk in vit.blocks:
+            blk.attn._slot = None
+        if record:
+            attn = ops.stack_views(stack, [blk.attn.attn_mean for blk in vit.blocks])
+        else:
+            # no_grad: the reference returns the stale maps of the last recorded forward
+            maps = [blk.attn.attn_mean for blk in vit.blocks]
+            attn = torch.stack(maps, dim=1) if all(m is not None for m in maps) else None
+        return layer_4, attn
+
+    def forward_cls(self, x):
+        """DPT/ACR.py:92-116 -> (x_cls [B,C], x_patch_cls [B,C], attn [B,L,N,N], None)."""
+        layer_4, attn = self._trunk(x)
+        x_cls = layer_4[:, 0, :]
+        x_patch = layer_4[:, 1:, :]
+        x_patch_cls = self.cls_head(x_patch.mean(dim=1))
+        x_cls = self.cls_head(x_cls)
+        return x_cls, x_patch_cls, attn, None
+
+    def forward_cam(self, x):
+        """DPT/ACR.py:118-143 -> (x_cls, x_patch_cls, attn [B,L,N,N], x_patch_cam [B,N-1,C])."""
+        layer_4, attn = self._trunk(x)
+        x_cls = layer_4[:, 0, :]
+        x_patch = layer_4[:, 1:, :]
+        x_cls = self.cls_head(x_cls)
+        x_patch_cls = self.cls_head(x_patch.mean(dim=1))
+        x_patch_cam = F.relu(self.cls_head(x_patch))
+        return x_cls, x_patch_cls, attn, x_patch_cam
+
+    def forward_mirror(self, x1, x2):
+        """DPT/ACR.py:170-174."""
+        x_cls_1, x_p_cls_1, attn1, b1 = self.forward_cls(x1)
+        x_cls_2, x_p_cls_2, attn2, b2 = self.forward_cls(x2)
+        return [x_cls_1, x_cls_2, x_p_cls_1, x_p_cls_2, b1, b2], [attn1, attn2]
+
+    def getam(self, batch, start_layer=0, func="grad", full=False):
+        """DPT/ACR.py:177-215.  Returns (cls_cam [1,N-1], attn_list, cam_list).
+
+        attn_list[l] is the head-mean map [B,N,N] as in the reference.  cam_list[l] is c_l restricted to
+        row 0, shape [1,1,N] (the only row the reference's result and its caller use, DPT/ACR.py:213 /
+        infer_cam.py:180-184); pass full=True on the fp32 path to get the reference's full [1,N,N] maps.
+        """
+        blocks = self.pretrained.model.blocks
+        skip = 2 if self.cur_backbone == "deitb16_distil_384" else 1
+        attn_list = [blk.attn.attn_mean for blk in blocks]
+        p0 = torch.stack([blk.attn.get_attn_row0()[batch] for blk in blocks])              # [L,H,N]
+        g0 = torch.stack([blk.attn.get_attn_gradients_row0()[batch] for blk in blocks])    # [L,H,N]
+        cls_cam, rows = ops.getam_row0(p0, g0, start_layer, func, skip, want_rows=True)
+        if full:
+            cam_list = [_getam_full(blk.attn.get_attn()[batch], blk.attn.get_attn_gradients()[batch], func).unsqueeze(0)
+                        for blk in blocks]
+        else:
+            cam_list = [rows[l].view(1, 1, -1) for l in range(len(blocks))]
+        return cls_cam, attn_list, cam_list[start_layer:]
+
+
+def _getam_full(cam, grad, func):
+    # DPT/ACR.py:187-206 on full [H,N,N] maps (fp32 path only; not on the hot path)
+    pos = grad.clamp(min=0).mean(dim=0)
+    if func == "grad":
+        return pos
+    if func == "grad_s":
+        return pos * pos
+    gp = (grad * cam).clamp(min=0).mean(dim=0)
+    return gp if func == "cam_grad" else gp * pos

@@ -1,0 +1,294 @@
+"""Tensor-level wrappers and torch.autograd.Functions over the C ABI (include/acr_b200.h).
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every computation
+below is one of the hand-written sm_100a kernels in acr_wsss_b200/csrc.  No CPU fallback exists:
+CPU tensors raise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_GETAM_FUNCS = {"grad": 0, "grad_s": 1, "cam_grad": 2, "cam_grad_s": 3}
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("acr_wsss_b200 ops need CUDA tensors: there is no CPU fallback")
+
+
+def _alias(t):
+    """A fresh (non-view) tensor sharing t's memory, so autograd treats it as a new output."""
+    return torch.empty(0, device=t.device, dtype=t.dtype).set_(t.untyped_storage(), t.storage_offset(), t.shape, t.stride())
+
+
+def _dense_map(t):
+    """A [B,N,N] map whose rows are dense; returns (tensor, batch_stride_in_elements)."""
+    if t.stride(-1) != 1 or t.stride(-2) != t.shape[-1]:
+        t = t.contiguous()
+    return t, t.stride(0)
+
+
+# ----------------------------------------------------------------------------------------------
+# (a1) attention core
+# ----------------------------------------------------------------------------------------------
+class _AttnCoreF32(torch.autograd.Function):
+    """softmax(QK^T*scale) V with materialised P (reference data flow, vision_transformer.py:198-214)."""
+
+    @staticmethod
+    def forward(ctx, qkv, num_heads, scale, mean_slot, state):
+        _need_cuda(qkv)
+        B, N, E3 = qkv.shape
+        E = E3 // 3
+        D = E // num_heads
+        qkv = qkv.contiguous().float()
+        P = torch.empty(B, num_heads, N, N, device=qkv.device, dtype=torch.float32)
+        out = torch.empty(B, N, E, device=qkv.device, dtype=torch.float32)
+        if mean_slot is None:
+            mean_slot = torch.empty(B, N, N, device=qkv.device, dtype=torch.float32)
+        assert mean_slot.stride(-1) == 1 and mean_slot.stride(-2) == N
+        _lib.check(_lib.lib().acr_attn_fwd_f32(_p(qkv), B, N, num_heads, D, scale, _p(P), _p(out),
+                                               _p(mean_slot), mean_slot.stride(0), _stream()), "acr_attn_fwd_f32")
+        ctx.save_for_backward(qkv, P)
+        ctx.dims = (B, N, num_heads, D, scale)
+        ctx.state = state
+        if state is not None:
+            state["attn"] = P
+            state["row0"] = None
+        ctx.set_materialize_grads(False)
+        return out, _alias(mean_slot)
+
+    @staticmethod
+    def backward(ctx, d_out, g_mean):
+        qkv, P = ctx.saved_tensors
+        B, N, H, D, scale = ctx.dims
+        d_out = torch.zeros(B, N, H * D, device=qkv.device) if d_out is None else d_out.contiguous().float()
+        gs = 0
+        if g_mean is not None:
+            g_mean, gs = _dense_map(g_mean.float())
+        dP = torch.empty_like(P)
+        dS = torch.empty_like(P)
+        d_qkv = torch.empty_like(qkv)
+        _lib.check(_lib.lib().acr_attn_bwd_f32(_p(qkv), _p(P), _p(d_out), B, N, H, D, scale,
+                                               _p(g_mean), gs, _p(dP), _p(dS), _p(d_qkv), _stream()), "acr_attn_bwd_f32")
+        if ctx.state is not None and ctx.state.get("capture_grad", True):
+            ctx.state["attn_grad"] = dP          # what save_attn_gradients keeps (vision_transformer.py:192-193)
+        return d_qkv, None, None, None, None
+
+
+class _AttnCoreBF16(torch.autograd.Function):
+    """Fused tcgen05 path: bf16 operands, fp32 accumulate, P never written to HBM."""
+
+    @staticmethod
+    def forward(ctx, qkv, num_heads, scale, mean_slot, state):
+        _need_cuda(qkv)
+        B, N, E3 = qkv.shape
+        E = E3 // 3
+        D = E // num_heads
+        qkv = qkv.contiguous().to(torch.bfloat16)
+        out = torch.empty(B, N, E, device=qkv.device, dtype=torch.bfloat16)
+        lse = torch.empty(B, num_heads, N, device=qkv.device, dtype=torch.float32)
+        p_row0 = torch.empty(B, num_heads, N, device=qkv.device, dtype=torch.float32) if state is not None else None
+        if mean_slot is None:
+            mean_slot = torch.empty(B, N, N, device=qkv.device, dtype=torch.float32)
+        assert mean_slot.stride(-1) == 1 and mean_slot.stride(-2) == N
+        _lib.check(_lib.lib().acr_attn_fwd_bf16(_p(qkv), B, N, num_heads, D, scale, _p(out), _p(lse),
+                                                _p(mean_slot), mean_slot.stride(0), _p(p_row0), _stream()),
+                   "acr_attn_fwd_bf16")
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.dims = (B, N, num_heads, D, scale)
+        ctx.state = state
+        if state is not None:
+            state["attn"] = None
+            state["row0"] = p_row0
+            state["qkv"] = qkv
+        ctx.set_materialize_grads(False)
+        return out, _alias(mean_slot)
+
+    @staticmethod
+    def backward(ctx, d_out, g_mean):
+        qkv, out, lse = ctx.saved_tensors
+        B, N, H, D, scale = ctx.dims
+        d_out = (torch.zeros(B, N, H * D, device=qkv.device, dtype=torch.bfloat16) if d_out is None
+                 else d_out.contiguous().to(torch.bfloat16))
+        gs = 0
+        if g_mean is not None:
+            g_mean, gs = _dense_map(g_mean.float())
+        d_qkv = torch.empty_like(qkv)
+        want_row0 = ctx.state is not None and ctx.state.get("capture_grad", True)
+        g_row0 = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32) if want_row0 else None
+        wsb = _lib.lib().acr_attn_bwd_bf16_workspace(B, N, H, D)
+        ws = torch.empty(wsb, device=qkv.device, dtype=torch.uint8)
+        _lib.check(_lib.lib().acr_attn_bwd_bf16(_p(qkv), _p(out), _p(lse), _p(d_out), B, N, H, D, scale,
+                                                _p(g_mean), gs, _p(d_qkv), _p(g_row0), _p(ws), wsb, _stream()),
+                   "acr_attn_bwd_bf16")
+        if want_row0:
+            ctx.state["grad_row0"] = g_row0
+        return d_qkv, None, None, None, None
+
+
+def attention_core(qkv, num_heads, scale, mean_slot=None, state=None, precision="fp32"):
+    """qkv [B,N,3E] (output of the qkv Linear) -> (out [B,N,E], head-mean attention [B,N,N] fp32).
+
+    `mean_slot`, when given, is the [B,N,N] view of slot l of a preallocated [B,L,N,N] stack; the
+    kernel writes into it directly and the returned map aliases it (no stack copy).
+    """
+    fn = _AttnCoreBF16 if precision == "bf16" else _AttnCoreF32
+    return fn.apply(qkv, num_heads, float(scale), mean_slot, state)
+
+
+class _StackViews(torch.autograd.Function):
+    """Zero-copy replacement for torch.stack(attn_list, dim=1) (DPT/ACR.py:112): the per-block maps
+    already live in the slots of `stack`; backward hands each block its slice of the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, stack, *maps):
+        ctx.n = len(maps)
+        ctx.set_materialize_grads(False)
+        return _alias(stack)
+
+    @staticmethod
+    def backward(ctx, g):
+        if g is None:
+            return (None,) * (ctx.n + 1)
+        return (None,) + tuple(g[:, l] for l in range(ctx.n))
+
+
+def stack_views(stack, maps):
+    return _StackViews.apply(stack, *maps)
+
+
+# ----------------------------------------------------------------------------------------------
+# (a7) consistency loss
+# ----------------------------------------------------------------------------------------------
+def consistency_fwd_bwd(attn1, attn2, p, alpha_cls=1.0, alpha_aff=1.0, need_grad=True):
+    """Returns (loss2 [2] = (cls_align, aff_align), g1, g2); g = alpha_cls*dcls/dA + alpha_aff*daff/dA."""
+    _need_cuda(attn1, attn2)
+    assert attn1.shape == attn2.shape and attn1.dim() == 4
+    B, L, N, _ = attn1.shape
+    a1 = attn1.contiguous().float()
+    a2 = attn2.contiguous().float()
+    loss2 = torch.empty(2, device=a1.device, dtype=torch.float32)
+    g1 = torch.empty_like(a1) if need_grad else None
+    g2 = torch.empty_like(a2) if need_grad else None
+    wsb = _lib.lib().acr_consistency_workspace(B, L, N)
+    ws = torch.empty(wsb, device=a1.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().acr_consistency_fwd_bwd(_p(a1), _p(a2), B, L, N, int(p), float(alpha_cls), float(alpha_aff),
+                                                  _p(loss2), _p(g1), _p(g2), _p(ws), wsb, _stream()),
+               "acr_consistency_fwd_bwd")
+    return loss2, g1, g2
+
+
+class _ConsistencyLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, attn1, attn2, p, alpha):
+        need = attn1.requires_grad or attn2.requires_grad
+        loss2, g1, g2 = consistency_fwd_bwd(attn1.detach(), attn2.detach(), p, alpha, alpha, need_grad=need)
+        if need:
+            ctx.save_for_backward(g1, g2)
+        ctx.need = need
+        total = alpha * (loss2[0] + loss2[1])
+        ctx.mark_non_differentiable(loss2)
+        return total, loss2
+
+    @staticmethod
+    def backward(ctx, g_total, _g_loss2):
+        if not ctx.need:
+            return None, None, None, None
+        g1, g2 = ctx.saved_tensors
+        # g1/g2 already carry alpha/count; scale by the incoming scalar (1.0 in the training step)
+        return g1.mul_(g_total), g2.mul_(g_total), None, None
+
+
+def consistency_loss(attn1, attn2, p, alpha):
+    """alpha*(cls_align + aff_align) with its gradient fused; also returns the two components (detached)."""
+    return _ConsistencyLoss.apply(attn1, attn2, int(p), float(alpha))
+
+
+# ----------------------------------------------------------------------------------------------
+# (a8) GETAM, (a9) refine
+# ----------------------------------------------------------------------------------------------
+def getam_row0(p_row0, g_row0, start_layer=0, func="grad", skip=1, want_rows=False):
+    """p_row0/g_row0 [L,H,N] -> cls_cam [1,N-skip] (and per-block rows [L,N] if want_rows)."""
+    _need_cuda(p_row0, g_row0)
+    L, H, N = p_row0.shape
+    p_row0 = p_row0.contiguous().float()
+    g_row0 = g_row0.contiguous().float()
+    cam = torch.empty(1, N - skip, device=p_row0.device, dtype=torch.float32)
+    rows = torch.empty(L, N, device=p_row0.device, dtype=torch.float32) if want_rows else None
+    _lib.check(_lib.lib().acr_getam_row0(_p(p_row0), _p(g_row0), L, H, N, int(start_layer), _GETAM_FUNCS[func], int(skip),
+                                         _p(cam), _p(rows), _stream()), "acr_getam_row0")
+    return (cam, rows) if want_rows else cam
+
+
+def affinity_sum(attn, normalize=False):
+    """attn [B,L,N,N] -> A [B,N-1,N-1] = sum_l attn[:,l,1:,1:] (infer_cam.py:164-165)."""
+    _need_cuda(attn)
+    B, L, N, _ = attn.shape
+    attn = attn.contiguous().float()
+    A = torch.empty(B, N - 1, N - 1, device=attn.device, dtype=torch.float32)
+    _lib.check(_lib.lib().acr_affinity_sum(_p(attn), B, L, N, int(bool(normalize)), _p(A), _stream()), "acr_affinity_sum")
+    return A
+
+
+def affinity_apply(A, cam, t=1):
+    """A [B,Np,Np], cam [B,Np,C] -> A^t cam (infer_cam.py:184, all classes in one contraction)."""
+    _need_cuda(A, cam)
+    B, Np, _ = A.shape
+    C = cam.shape[-1]
+    A = A.contiguous().float()
+    cam = cam.contiguous().float()
+    out = torch.empty_like(cam)
+    tmp = torch.empty_like(cam) if t > 1 else None
+    _lib.check(_lib.lib().acr_affinity_refine(_p(A), _p(cam), B, Np, C, int(t), _p(out), _p(tmp), _stream()),
+               "acr_affinity_refine")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# (a10) PAMR, (a11) bilateral
+# ----------------------------------------------------------------------------------------------
+def pamr_forward(x, mask, dilations, num_iter):
+    _need_cuda(x, mask)
+    B, K, H, W = x.shape
+    _, C, mh, mw = mask.shape
+    x = x.contiguous().float()
+    mask = mask.contiguous().float()
+    nd = len(dilations)
+    dil = (ctypes.c_int * nd)(*[int(d) for d in dilations])
+    out = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
+    wsb = _lib.lib().acr_pamr_workspace(B, K, C, H, W, nd)
+    ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().acr_pamr_fwd(_p(x), _p(mask), B, K, C, H, W, mh, mw, dil, nd, int(num_iter),
+                                       _p(out), _p(ws), wsb, _stream()), "acr_pamr_fwd")
+    return out
+
+
+def bilateral_filter(images, ins, sigmargb, sigmaxy, return_lattice_size=False):
+    """Device-tensor form of bilateralfilter_batch: images [N,3,H,W] (0..255), ins [N,K,H,W] -> outs."""
+    _need_cuda(images, ins)
+    N, K, H, W = ins.shape
+    assert images.shape == (N, 3, H, W)
+    images = images.contiguous().float()
+    ins = ins.contiguous().float()
+    outs = torch.empty_like(ins)
+    wsb = _lib.lib().acr_bilateral_workspace(N, K, H, W)
+    ws = torch.empty(wsb + 256, device=ins.device, dtype=torch.uint8)
+    off = (-ws.data_ptr()) % 256
+    msz = (ctypes.c_int * N)() if return_lattice_size else None
+    _lib.check(_lib.lib().acr_bilateral_batch(_p(images), _p(ins), _p(outs), N, K, H, W, float(sigmargb), float(sigmaxy),
+                                              ctypes.c_void_p(ws.data_ptr() + off), wsb, msz, _stream()),
+               "acr_bilateral_batch")
+    if return_lattice_size:
+        return outs, list(msz)
+    return outs

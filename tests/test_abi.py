@@ -1,0 +1,57 @@
+"""CPU tier: the C-ABI library builds, loads and exports every symbol include/acr_b200.h declares.
+No compute calls here (no GPU in the build container)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "acr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:acr_|bilateralfilter_)\w+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    from acr_wsss_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in acr_b200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in acr_wsss_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == names
+    assert _lib.lib().acr_abi_version() == 1
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    from acr_wsss_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        ops.consistency_fwd_bwd(torch.zeros(1, 1, 5, 5), torch.zeros(1, 1, 5, 5), 2)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "acr_wsss_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            txt = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", txt, flags=re.S).replace("# ", ""), fn
+
+
+def test_invalid_arguments_are_rejected_before_any_launch():
+    from acr_wsss_b200 import _lib
+    L = _lib.lib()
+    assert L.acr_consistency_fwd_bwd(None, None, 1, 1, 5, 2, 1.0, 1.0, None, None, None, None, 0, None) == -1
+    assert b"null" in L.acr_last_error_string()
+    assert L.acr_consistency_workspace(8, 12, 785) >= 8 * 12 * 785 * 4
+    assert L.acr_bilateral_workspace(1, 21, 224, 224) > 0
+    assert L.acr_pamr_workspace(1, 3, 21, 448, 448, 6) > 0

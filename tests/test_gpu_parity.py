@@ -1,0 +1,341 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C ABI, against (i) the committed golden vectors
+produced by the unmodified reference and (ii) the CPU oracle on the same seeded inputs.
+
+Tolerances (north star): fp32 path 1e-3 relative (scale-normalised max error); bf16 fused path 1e-2;
+>= 99.9 % pseudo-label agreement; index/permutation work (gradient signs, lattice structure) exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, rel_err, t2n
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-3
+BF16_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _orc():
+    from oracle import acr_oracle as orc
+    return orc
+
+
+# ------------------------------------------------------------------ (a7) consistency loss
+@pytest.mark.parametrize("B,L,p", [(1, 1, 1), (2, 3, 4), (1, 2, 7), (2, 12, 14)])
+def test_consistency_matches_oracle(dev, B, L, p):
+    from acr_wsss_b200 import ops
+    orc = _orc()
+    N = p * p + 1
+    g = torch.Generator().manual_seed(B * 100 + p)
+    a1 = torch.softmax(torch.randn(B, L, N, N, generator=g) * 2, -1)
+    a2 = torch.softmax(torch.randn(B, L, N, N, generator=g) * 2, -1)
+    a2[0, 0, 0, 1:] = a1[0, 0, 0, orc.flip_perm(p)[1:]]        # exact ties -> sign(0) = 0 must survive
+    c, f, g1, g2 = orc.consistency_loss_closed_form(a1, a2, p, 100.0, 100.0)
+    loss2, d1, d2 = ops.consistency_fwd_bwd(a1.to(dev), a2.to(dev), p, 100.0, 100.0)
+    assert abs(float(loss2[0]) - float(c)) <= 1e-5 * float(c) + 1e-12
+    assert abs(float(loss2[1]) - float(f)) <= 1e-5 * float(f) + 1e-12
+    assert torch.equal(torch.sign(d1.cpu()), torch.sign(g1)) and torch.equal(torch.sign(d2.cpu()), torch.sign(g2))
+    assert torch.allclose(d1.cpu(), g1, rtol=1e-6, atol=0) and torch.allclose(d2.cpu(), g2, rtol=1e-6, atol=0)
+    assert float(d1[..., 0].abs().max()) == 0.0 and float(d2[..., 0].abs().max()) == 0.0   # column 0: no gradient
+
+
+def test_consistency_full_size_properties(dev):
+    """cfg2 size (B=8, L=12, N=785): identical views -> zero loss/grad; swapping the views negates the gradient;
+    the gradient of view 2 is the permuted negative of view 1's."""
+    from acr_wsss_b200 import ops
+    orc = _orc()
+    B, L, p = 8, 12, 28
+    N = p * p + 1
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a1 = torch.softmax(torch.randn(B, L, N, N, device=dev, generator=g), -1)
+    a2 = torch.softmax(torch.randn(B, L, N, N, device=dev, generator=g), -1)
+    pi = orc.flip_perm(p).to(dev)
+    a1f = a1[:, :, pi, :][:, :, :, pi].contiguous()
+    l0, z1, z2 = ops.consistency_fwd_bwd(a1, a1f, p, 1.0, 1.0)
+    assert float(l0.abs().max()) == 0.0 and float(z1.abs().max()) == 0.0 and float(z2.abs().max()) == 0.0
+    l12, g1, g2 = ops.consistency_fwd_bwd(a1, a2, p, 100.0, 100.0)
+    assert torch.equal(g2, (-g1)[:, :, pi, :][:, :, :, pi])
+    # against a straightforward device-side evaluation of the same formula (fp64 accumulate)
+    d = a1 - a2[:, :, pi, :][:, :, :, pi]
+    assert abs(float(l12[0]) - float(d[:, :, 0, 1:].abs().double().mean())) < 1e-6 * float(l12[0])
+    assert abs(float(l12[1]) - float(d[:, :, 1:, 1:].abs().double().mean())) < 1e-6 * float(l12[1])
+
+
+# ------------------------------------------------------------------ (a1/a2) attention, exact path
+def test_attention_f32_matches_reference_module(dev):
+    from acr_wsss_b200 import Attention
+    g = load_golden("attention_small.npz")
+    att = Attention(128, num_heads=2, qkv_bias=True, precision="fp32").to(dev)
+    with torch.no_grad():
+        att.qkv.weight.copy_(torch.tensor(g["qkv_w"])); att.qkv.bias.copy_(torch.tensor(g["qkv_b"]))
+        att.proj.weight.copy_(torch.tensor(g["proj_w"])); att.proj.bias.copy_(torch.tensor(g["proj_b"]))
+    x = torch.tensor(g["x"], device=dev, requires_grad=True)
+    y = att(x)
+    P = att.get_attn()
+    assert rel_err(t2n(y), g["y"]) < FP32_TOL and rel_err(t2n(P), g["P"]) < FP32_TOL
+    loss = (y * torch.tensor(g["wy"], device=dev)).sum() + (att.attn_mean * torch.tensor(g["G"], device=dev)).sum()
+    loss.backward()
+    assert rel_err(t2n(att.get_attn_gradients()), g["dP"]) < FP32_TOL
+    assert rel_err(t2n(x.grad), g["dx"]) < FP32_TOL
+    assert rel_err(t2n(att.qkv.weight.grad), g["d_qkv_w"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("B,N,H,D", [(1, 1, 1, 64), (2, 17, 3, 64), (1, 197, 12, 64), (2, 65, 2, 32)])
+def test_attention_f32_core_vs_oracle(dev, B, N, H, D):
+    from acr_wsss_b200 import ops
+    orc = _orc()
+    g = torch.Generator().manual_seed(N)
+    qkv = torch.randn(B, N, 3 * H * D, generator=g)
+    d_out = torch.randn(B, N, H * D, generator=g)
+    G = torch.randn(B, N, N, generator=g) * 0.05
+    out_r, P_r = orc.attention_core(qkv, H, D ** -0.5)
+    dqkv_r, dP_r = orc.attention_core_backward(qkv, H, D ** -0.5, d_out, G)
+    q = qkv.to(dev).requires_grad_(True)
+    st = {}
+    out, mean = ops.attention_core(q, H, D ** -0.5, None, st, "fp32")
+    assert rel_err(t2n(out), t2n(out_r)) < FP32_TOL
+    assert rel_err(t2n(mean), t2n(P_r.mean(1))) < FP32_TOL
+    ((out * d_out.to(dev)).sum() + (mean * G.to(dev)).sum()).backward()
+    assert rel_err(t2n(q.grad), t2n(dqkv_r)) < FP32_TOL
+    assert rel_err(t2n(st["attn_grad"]), t2n(dP_r)) < FP32_TOL
+
+
+# ------------------------------------------------------------------ (a3-a7) model + training step
+def _build(dev, C, backbone, precision):
+    from acr_wsss_b200 import ACR
+    orc = _orc()
+    dim, depth, scratch = (768, 12, (96, 192, 384, 768)) if backbone == "vitb" else (1024, 24, (256, 512, 1024, 1024))
+    sd = orc.synth_state_dict(orc.vit_shapes(dim, depth, C, scratch_in=scratch))
+    m = ACR(C, backbone, precision=precision).to(dev)
+    missing = m.load_state_dict(sd, strict=True)       # reference key layout must load unchanged
+    return m, sd
+
+
+def _reference_inline_loss(attn1, attn2, x1, x2, label, h, alpha):
+    """train_acr.py:143-168 verbatim in behaviour: slices of the returned tensors, IN-PLACE flips on attn2."""
+    import torch.nn.functional as F
+    attn1_cls = attn1[:, :, 0, 1:].unsqueeze(2)
+    attn2_cls = attn2[:, :, 0, 1:].unsqueeze(2)
+    attn1_aff = attn1[:, :, 1:, 1:]
+    attn2_aff = attn2[:, :, 1:, 1:]
+    p = h // 16
+    for i in range(p):
+        attn2_cls[:, :, :, i * p:i * p + p] = attn2_cls[:, :, :, i * p:i * p + p].flip(3)
+    for i in range(p):
+        attn2_aff[:, :, i * p:i * p + p, :] = attn2_aff[:, :, i * p:i * p + p, :].flip(2)
+    for i in range(p):
+        attn2_aff[:, :, :, i * p:i * p + p] = attn2_aff[:, :, :, i * p:i * p + p].flip(3)
+    parts = (F.multilabel_soft_margin_loss(x1, label), F.multilabel_soft_margin_loss(x2, label),
+             F.l1_loss(attn1_cls, attn2_cls, reduction="mean"), F.l1_loss(attn1_aff, attn2_aff, reduction="mean"))
+    return parts[0] + parts[1] + parts[2] * alpha + parts[3] * alpha, parts
+
+
+def _train_step_check(dev, name, backbone, precision, tol, inline_loss=False):
+    from acr_wsss_b200 import acr_total_loss, synth
+    orc = _orc()
+    g = load_golden(name)
+    S, B, C, alpha = int(g["S"]), int(g["B"]), int(g["C"]), float(g["alpha"])
+    m, _ = _build(dev, C, backbone, precision)
+    m.train()
+    m.set_capture_grad(False)
+    img, label = synth.images(B, S).to(dev), synth.labels(B, C).to(dev)
+    cls_list, (attn1, attn2) = m.forward_mirror(img, img.flip(-1))
+    assert cls_list[4] is None and cls_list[5] is None and attn1.shape == (B, len(m.pretrained.model.blocks), (S // 16) ** 2 + 1, (S // 16) ** 2 + 1)
+    assert rel_err(t2n(cls_list[0]), g["x_cls_1"]) < tol and rel_err(t2n(cls_list[1]), g["x_cls_2"]) < tol
+    assert rel_err(t2n(cls_list[2]), g["x_patch_cls_1"]) < tol
+    if "attn1" in g:
+        assert rel_err(t2n(attn1), g["attn1"]) < tol and rel_err(t2n(attn2), g["attn2"]) < tol
+    else:
+        assert rel_err(t2n(attn1[:, ::5, ::97, ::7]), g["attn1_sub"]) < tol
+        assert rel_err(t2n(attn2[:, ::5, ::97, ::7]), g["attn2_sub"]) < tol
+        assert rel_err(t2n(attn1.sum(-1)[:, :, ::97]), g["attn1_rowsum"]) < tol
+    if inline_loss:
+        # the reference's own inline block (in-place flips on the returned tensor) must work on our outputs
+        loss, parts = _reference_inline_loss(attn1, attn2, cls_list[0], cls_list[1], label, S, alpha)
+        named = dict(zip(("cls_loss_1", "cls_loss_2", "cls_align_loss", "aff_align_loss"), parts))
+    else:
+        loss, named = acr_total_loss(cls_list[0], cls_list[1], label, attn1, attn2, S // 16, alpha)
+    for k in ("cls_loss_1", "cls_loss_2", "cls_align_loss", "aff_align_loss"):
+        assert abs(float(named[k]) - float(g[k])) <= tol * abs(float(g[k])), (k, float(named[k]), float(g[k]))
+    assert abs(float(loss) - float(g["loss"])) <= tol * abs(float(g["loss"]))
+    loss.backward()
+    params = dict(m.named_parameters())
+    gtol = 5 * tol
+    for k in [k[len("grad_norm/"):] for k in g if k.startswith("grad_norm/")]:
+        gr = params[k].grad
+        assert gr is not None, k
+        assert abs(float(gr.norm()) - float(g["grad_norm/" + k])) <= gtol * float(g["grad_norm/" + k]), k
+        sl = gr.reshape(gr.shape[0] if gr.dim() > 1 else 1, -1)[:8, :16] if gr.dim() <= 2 else gr.reshape(-1, gr.shape[-1])[:8, :16]
+        assert rel_err(t2n(sl), g["grad_slice/" + k]) < gtol, k
+    # parameters the reference leaves without gradient
+    assert params["pretrained.model.norm.weight"].grad is None and params["pretrained.model.bkg_token"].grad is None
+
+
+def test_train_step_fp32_vitb_64(dev):
+    _train_step_check(dev, "train_vitb_64.npz", "vitb", "fp32", FP32_TOL)
+
+
+def test_train_step_fp32_vitb_64_reference_inline_loss(dev):
+    _train_step_check(dev, "train_vitb_64.npz", "vitb", "fp32", FP32_TOL, inline_loss=True)
+
+
+def test_train_step_fp32_vitb_448(dev):
+    _train_step_check(dev, "train_vitb_448.npz", "vitb", "fp32", FP32_TOL)
+
+
+def test_train_step_fp32_vitl_96(dev):
+    _train_step_check(dev, "train_vitl_96.npz", "vitl", "fp32", FP32_TOL)
+
+
+# ------------------------------------------------------------------ (a8/a9) GETAM + CAM
+@pytest.mark.parametrize("func", ["grad", "grad_s", "cam_grad", "cam_grad_s"])
+def test_getam_row0_matches_oracle(dev, func):
+    from acr_wsss_b200 import ops
+    orc = _orc()
+    L, H, N = 4, 3, 26
+    g = torch.Generator().manual_seed(5)
+    maps = [torch.softmax(torch.randn(1, H, N, N, generator=g), -1) for _ in range(L)]
+    grads = [torch.randn(1, H, N, N, generator=g) for _ in range(L)]
+    ref, _, cl = orc.getam(maps, grads, 0, 1, func)
+    p0 = torch.stack([m[0, :, 0, :] for m in maps]).to(dev)
+    g0 = torch.stack([m[0, :, 0, :] for m in grads]).to(dev)
+    cam, rows = ops.getam_row0(p0, g0, 1, func, 1, want_rows=True)
+    assert rel_err(t2n(cam), t2n(ref)) < 1e-5
+    assert rel_err(t2n(rows[1:]), t2n(torch.stack([c[0, 0] for c in cl]))) < 1e-5
+
+
+@pytest.mark.parametrize("t,normalize", [(1, False), (2, False), (2, True), (3, True)])
+def test_affinity_refine_matches_oracle(dev, t, normalize):
+    from acr_wsss_b200 import affinity_refine
+    orc = _orc()
+    g = torch.Generator().manual_seed(t)
+    attn = torch.softmax(torch.randn(2, 5, 50, 50, generator=g), -1)
+    cam = torch.rand(2, 49, 7, generator=g)
+    ref = orc.affinity_refine(attn, cam, t, normalize)
+    got = affinity_refine(attn.to(dev), cam.to(dev), t, normalize)
+    assert rel_err(t2n(got), t2n(ref)) < 1e-4
+    got1 = affinity_refine(attn.to(dev), cam[..., 0].to(dev), t, normalize)
+    assert rel_err(t2n(got1), t2n(ref[..., 0])) < 1e-4
+
+
+def _infer_check(dev, name, precision, tol):
+    from acr_wsss_b200 import infer_cam_image, pseudo_label, synth
+    g = load_golden(name)
+    C, S = int(g["C"]), int(g["S"])
+    present = [int(c) for c in g["present"]]
+    m, _ = _build(dev, C, "vitb", precision)
+    m.eval()
+    img = synth.images(1, S, seed=3).to(dev)
+    label = synth.labels(1, C, present=present).to(dev)
+    cam_dict, patch_dict, norm_cam = infer_cam_image(m, img, label, tuple(int(v) for v in g["out_size"]),
+                                                     scales=tuple(float(s) for s in g["scales"]),
+                                                     start_layer=int(g["start_layer"]), getam_func=str(g["func"]))
+    assert sorted(cam_dict) == present and cam_dict[present[0]].dtype == np.float32
+    assert rel_err(np.stack([cam_dict[c] for c in present]), g["norm_cam"]) < tol
+    assert rel_err(np.stack([patch_dict[c] for c in present]), g["patch_norm_cam"]) < tol
+    for t in (25, 40):
+        agree = (pseudo_label(cam_dict, C, t / 100.0) == g[f"label_t{t}"]).mean()
+        assert agree >= 0.999, (t, agree)
+    return m
+
+
+def test_infer_cam_fp32_448(dev):
+    from acr_wsss_b200 import synth
+    m = _infer_check(dev, "infer_vitb_448.npz", "fp32", FP32_TOL)
+    # intermediate quantities of the un-flipped pass (the last one run)
+    g = load_golden("infer_vitb_448.npz")
+    img = synth.images(1, 448, seed=3).to(dev)
+    cls_pred, _, attn, patch_cam = m.forward_cam(img)
+    assert rel_err(t2n(cls_pred), g["cls_pred"]) < FP32_TOL
+    assert rel_err(t2n(patch_cam), g["patch_cam_tokens"]) < FP32_TOL
+    assert rel_err(t2n(attn[:, ::11, ::97, ::7]), g["attn_sub"]) < FP32_TOL
+    for ci in (3, 7, 14):
+        m.zero_grad()
+        cls_pred[0, ci].backward(retain_graph=True)
+        cam, attn_list, cam_list = m.getam(0, start_layer=10, func="grad")
+        assert cam.shape == (1, 784) and len(attn_list) == 12 and len(cam_list) == 2
+        assert rel_err(t2n(cam), g[f"getam_{ci}"]) < FP32_TOL
+
+
+def test_infer_cam_fp32_multiscale(dev):
+    _infer_check(dev, "infer_vitb_128_ms.npz", "fp32", FP32_TOL)
+
+
+# ------------------------------------------------------------------ (a10) PAMR
+def test_pamr_matches_reference(dev):
+    from acr_wsss_b200 import PAMR, synth
+    g = load_golden("pamr.npz")
+    x = (synth.smooth_rgb(2, 40, 48, seed=1) / 255.0).to(dev)
+    mask = synth.probabilities(2, 5, 10, 12, seed=1).to(dev)
+    assert rel_err(t2n(PAMR(3, [1, 2, 4])(x, mask)), g["out_a"]) < FP32_TOL
+    assert rel_err(t2n(PAMR()(x, mask)), g["out_b"]) < FP32_TOL
+    xn = ((synth.smooth_rgb(1, 112, 96, seed=2) - 120.0) / 58.0).to(dev)
+    mask2 = synth.probabilities(1, 21, 7, 6, seed=2).to(dev)
+    out = PAMR(10, [1, 2, 4, 8, 12, 24])(xn, mask2)
+    assert rel_err(t2n(out), g["out_c"]) < FP32_TOL
+    assert sorted(dict(PAMR().named_buffers())) == ["aff_m.kernel", "aff_std.kernel", "aff_x.kernel"]
+
+
+def test_pamr_full_size_vs_oracle_and_properties(dev):
+    from acr_wsss_b200 import PAMR, synth
+    orc = _orc()
+    x = ((synth.smooth_rgb(1, 448, 448, seed=4) - 120.0) / 58.0)
+    mask = synth.probabilities(1, 21, 28, 28, seed=4)
+    out = PAMR(10, [1, 2, 4, 8, 12, 24])(x.to(dev), mask.to(dev))
+    ref = orc.pamr(x[:, :, :, :], mask, 2, [1, 2, 4, 8, 12, 24])
+    out2 = PAMR(2, [1, 2, 4, 8, 12, 24])(x.to(dev), mask.to(dev))
+    assert rel_err(t2n(out2), t2n(ref)) < FP32_TOL
+    # the update is a convex combination: a probability mask stays a probability mask, constants are fixed points
+    assert float((out.sum(1) - 1).abs().max()) < 1e-4 and float(out.min()) >= 0.0
+    const = torch.full((1, 2, 28, 28), 0.37)
+    assert float((PAMR(4, [1, 3])(x.to(dev), const.to(dev)) - 0.37).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------ (a11) bilateral filter
+def test_bilateral_matches_reference_outputs(dev):
+    from acr_wsss_b200 import ops, synth, bilateralfilter_batch
+    g = load_golden("bilateral.npz")
+    for k in "abc":
+        N, K, H, W, srgb, sxy, seed = g[f"{k}_cfg"]
+        N, K, H, W, seed = int(N), int(K), int(H), int(W), int(seed)
+        img, ins = synth.smooth_rgb(N, H, W, seed=seed), synth.probabilities(N, K, H, W, seed=seed)
+        out = t2n(ops.bilateral_filter(img.to(dev), ins.to(dev), srgb, sxy))
+        # host-buffer drop-in with the SWIG calling convention (1-D float32 arrays, outs in place)
+        o2 = np.zeros(ins.numel(), np.float32)
+        bilateralfilter_batch(img.numpy().reshape(-1), ins.numpy().reshape(-1), o2, N, K, H, W, srgb, sxy)
+        o2 = o2.reshape(N, K, H, W)
+        if out.size >= 60000:
+            out, o2 = out[:, :, ::3, ::3], o2[:, :, ::3, ::3]
+        assert rel_err(out, g[f"{k}_out"]) < 1e-5, k       # only the splat summation order differs
+        assert rel_err(o2, g[f"{k}_out"]) < 1e-5, k
+
+
+def test_bilateral_lattice_size_and_cfg_shape_vs_oracle(dev):
+    from acr_wsss_b200 import ops, synth
+    from oracle import bilateral_oracle as bo
+    N, K, H, W = 1, 21, 224, 224
+    img, ins = synth.smooth_rgb(N, H, W, seed=0), synth.probabilities(N, K, H, W, seed=0)
+    out, msz = ops.bilateral_filter(img.to(dev), ins.to(dev), 15.0, 50.0, return_lattice_size=True)
+    ref = bo.oracle_bilateral(img.numpy(), ins.numpy(), 15.0, 50.0)
+    assert rel_err(t2n(out), ref) < 1e-5
+    assert 0 < msz[0] <= 6 * H * W
+    # white noise (worst-case lattice) and an odd-sized image (the reference's phantom pad pixels)
+    noise = torch.rand(1, 3, 33, 31, generator=torch.Generator().manual_seed(1)) * 255
+    ins2 = synth.probabilities(1, 3, 33, 31, seed=7)
+    out2 = ops.bilateral_filter(noise.to(dev), ins2.to(dev), 5.0, 3.0)
+    assert rel_err(t2n(out2), bo.oracle_bilateral(noise.numpy(), ins2.numpy(), 5.0, 3.0)) < 1e-5
+
+
+def test_bilateral_rejects_bad_buffers(dev):
+    from acr_wsss_b200 import bilateralfilter_batch
+    with pytest.raises(RuntimeError):
+        bilateralfilter_batch(np.zeros(10, np.float32), np.zeros(10, np.float32), np.zeros(10, np.float32), 1, 2, 4, 4, 1.0, 1.0)
+    with pytest.raises(TypeError):
+        bilateralfilter_batch(np.zeros((1, 3, 4, 4), np.float32), np.zeros(32, np.float32), np.zeros(32, np.float32), 1, 2, 4, 4, 1.0, 1.0)
