@@ -1,9 +1,366 @@
-// placeholder until the tcgen05 kernels land (next commit)
+// (a1) Fused attention for sm_100a: tcgen05 MMAs with TMEM accumulators, operands staged by TMA (SWIZZLE_128B),
+// bf16 in / fp32 accumulate.  Replaces models/vision_transformer.py:203-211 + the head mean of DPT/ACR.py:107-112
+// without ever writing the [B,H,N,N] softmax to HBM.
+//
+// Forward = two kernels per block of the ViT:
+//   attn_fwd_kernel  (grid q-tiles x H x B): flash-style S = QK^T -> online softmax -> O = PV, emits O (bf16) and the
+//                    per-row log-sum-exp.  P goes registers -> TMEM (bf16) and is the A operand of the PV MMA.
+//   attn_mean_kernel (grid kv-tiles x q-tiles x B): loops over the H heads of one 128x128 tile, recomputes S on the
+//                    tensor cores, normalises with the LSE, accumulates the head mean in registers and writes the
+//                    fp32 tile of A-bar straight into slot l of the [B,L,N,N] stack (coalesced, via smem staging).
+//                    Also emits the cls-token row of every head's P (GETAM input).
+// N = p*p+1 is never a multiple of 128: TMA zero-fills out-of-range rows, key columns >= N are masked to -inf / 0.
 #include "common.cuh"
-extern "C" int acr_attn_fwd_bf16(const void*, int, int, int, int, float, void*, float*, float*, long long, float*, void*) {
-  acr::set_error("acr_attn_fwd_bf16: not built yet");
-  return ACR_E_NOSM100;
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;               // query rows per CTA
+constexpr int BN = 128;               // key rows per tile
+constexpr int HD = 64;                // head dim (128-byte bf16 rows = one SWIZZLE_128B atom row)
+constexpr uint32_t TILE_BYTES = BM * HD * 2;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+constexpr uint32_t IDESC_S = tc::idesc_bf16_f32(128, 128, 0, 0);   // S = Q K^T : A, B K-major
+constexpr uint32_t IDESC_PV = tc::idesc_bf16_f32(128, 64, 0, 1);   // O = P V   : A (TMEM) K-major, B = V MN-major
+
+// ---------------------------------------------------------------------------------------------
+struct FwdSmem {
+  uint8_t q[TILE_BYTES];
+  uint8_t k[2][TILE_BYTES];
+  uint8_t v[2][TILE_BYTES];
+  uint64_t q_full, kv_full[2], kv_empty[2], s_full, p_full, o_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(256)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
+                int N, int H, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  FwdSmem& s = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (N + BN - 1) / BN;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_qkv);
+    tc::mbar_init(&s.q_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.kv_full[i], 1); tc::mbar_init(&s.kv_empty[i], 1); }
+    tc::mbar_init(&s.s_full, 1);
+    tc::mbar_init(&s.p_full, 128);
+    tc::mbar_init(&s.o_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<256>(&s.tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t tS = tmem, tP = tmem + 128, tO = tmem + 192;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(&s.q_full, TILE_BYTES);
+      tc::tma_load_4d(s.q, &tmap_qkv, &s.q_full, 0, h, q0, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        tc::mbar_wait(&s.kv_empty[st], ((j >> 1) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&s.kv_full[st], 2 * TILE_BYTES);
+        tc::tma_load_4d(s.k[st], &tmap_qkv, &s.kv_full[st], 0, H + h, j * BN, b);
+        tc::tma_load_4d(s.v[st], &tmap_qkv, &s.kv_full[st], 0, 2 * H + h, j * BN, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      tc::mbar_wait(&s.q_full, 0);
+      const uint32_t q_addr = tc::smem_u32(s.q);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        tc::mbar_wait(&s.kv_full[st], (j >> 1) & 1);
+        tc::tc_fence_after();
+        const uint32_t k_addr = tc::smem_u32(s.k[st]), v_addr = tc::smem_u32(s.v[st]);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          tc::mma_ss(tS, tc::smem_desc_sw128(q_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(k_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
+        tc::tc_commit(&s.s_full);
+        tc::mbar_wait(&s.p_full, j & 1);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks)
+          tc::mma_ts(tO, tP + ks * 8, tc::smem_desc_sw128(v_addr + ks * 2048, 1024, 1024), IDESC_PV, ks > 0);
+        tc::tc_commit(&s.o_full);
+        tc::tc_commit(&s.kv_empty[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    uint32_t r[32];
+    for (int j = 0; j < ntiles; ++j) {
+      tc::mbar_wait(&s.s_full, j & 1);
+      tc::tc_fence_after();
+      const int col0 = j * BN;
+      const bool tail = (col0 + BN > N);
+      float mx = m;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tc::tmem_ld32(tS + lane_off + c * 32, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float t = __uint_as_float(r[i]) * scale_log2;
+          if (tail && col0 + c * 32 + i >= N) t = -INFINITY;
+          mx = fmaxf(mx, t);
+        }
+      }
+      const float alpha = exp2f(m - mx);
+      float rowsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tc::tmem_ld32(tS + lane_off + c * 32, r);
+        tc::tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float t0 = __uint_as_float(r[2 * i]) * scale_log2 - mx;
+          float t1 = __uint_as_float(r[2 * i + 1]) * scale_log2 - mx;
+          if (tail && col0 + c * 32 + 2 * i >= N) t0 = -INFINITY;
+          if (tail && col0 + c * 32 + 2 * i + 1 >= N) t1 = -INFINITY;
+          const float p0 = exp2f(t0), p1 = exp2f(t1);
+          rowsum += p0 + p1;
+          pk[i] = tc::pack_bf16(p0, p1);
+        }
+        tc::tmem_st16(tP + lane_off + c * 16, pk);
+      }
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&s.p_full);
+      l = l * alpha + rowsum;
+      m = mx;
+      tc::mbar_wait(&s.o_full, j & 1);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tc::tmem_ld32(tO + lane_off + c * 32, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
+      }
+    }
+    if (q0 + row < N) {
+      const float inv = 1.f / l;
+      __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * ((size_t)H * HD) + (size_t)h * HD;
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        uint4 v;
+        v.x = tc::pack_bf16(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
+        v.y = tc::pack_bf16(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+        v.z = tc::pack_bf16(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
+        v.w = tc::pack_bf16(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+        reinterpret_cast<uint4*>(dst)[c] = v;
+      }
+      lse[((size_t)b * H + h) * N + q0 + row] = (m + log2f(l)) * kLn2;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<256>(tmem);
+  }
 }
+
+// ---------------------------------------------------------------------------------------------
+constexpr int MEAN_STAGES = 3;
+struct MeanSmem {
+  uint8_t qk[MEAN_STAGES][2][TILE_BYTES];      // [stage][0=Q,1=K]; reused as the fp32 staging tile at the end
+  uint64_t full[MEAN_STAGES], empty[MEAN_STAGES], t_full[2], t_empty[2];
+  uint32_t tmem_base;
+};
+constexpr int STAGE_LD = 129;                  // fp32 staging row stride (conflict-free)
+static_assert(sizeof(float) * BM * STAGE_LD <= sizeof(uint8_t) * MEAN_STAGES * 2 * TILE_BYTES, "staging tile must fit");
+
+__global__ void __launch_bounds__(384)
+attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __restrict__ lse, float* __restrict__ mean,
+                 long long mean_bs, float* __restrict__ p_row0, int N, int H, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  MeanSmem& s = *reinterpret_cast<MeanSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * BN, q0 = blockIdx.y * BM, b = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_qkv);
+    for (int i = 0; i < MEAN_STAGES; ++i) { tc::mbar_init(&s.full[i], 1); tc::mbar_init(&s.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.t_full[i], 1); tc::mbar_init(&s.t_empty[i], 256); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<256>(&s.tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int h = 0; h < H; ++h) {
+        const int st = h % MEAN_STAGES;
+        tc::mbar_wait(&s.empty[st], ((h / MEAN_STAGES) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&s.full[st], 2 * TILE_BYTES);
+        tc::tma_load_4d(s.qk[st][0], &tmap_qkv, &s.full[st], 0, h, q0, b);
+        tc::tma_load_4d(s.qk[st][1], &tmap_qkv, &s.full[st], 0, H + h, kv0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int h = 0; h < H; ++h) {
+        const int st = h % MEAN_STAGES, ab = h & 1;
+        tc::mbar_wait(&s.full[st], (h / MEAN_STAGES) & 1);
+        tc::mbar_wait(&s.t_empty[ab], ((h >> 1) & 1) ^ 1);
+        tc::tc_fence_after();
+        const uint32_t q_addr = tc::smem_u32(s.qk[st][0]), k_addr = tc::smem_u32(s.qk[st][1]);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          tc::mma_ss(tmem + ab * 128, tc::smem_desc_sw128(q_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(k_addr + ks * 32, 16, 1024),
+                     IDESC_S, ks > 0);
+        tc::tc_commit(&s.empty[st]);
+        tc::tc_commit(&s.t_full[ab]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int we = warp - 4;                       // 0..7
+    const int row = (warp & 3) * 32 + lane;
+    const int half = we >> 2;                      // which 64-column half of the tile
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const bool row_ok = (q0 + row) < N;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    uint32_t r[32];
+    for (int h = 0; h < H; ++h) {
+      const int ab = h & 1;
+      const float lse2 = row_ok ? __ldg(lse + ((size_t)b * H + h) * N + q0 + row) * kLog2e : 0.f;
+      tc::mbar_wait(&s.t_full[ab], (h >> 1) & 1);
+      tc::tc_fence_after();
+      const bool want_row0 = (p_row0 != nullptr) && (q0 + row == 0);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tc::tmem_ld32(tmem + ab * 128 + lane_off + half * 64 + c * 32, r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = kv0 + half * 64 + c * 32 + i;
+          float p = exp2f(__uint_as_float(r[i]) * scale_log2 - lse2);
+          if (col >= N) p = 0.f;
+          acc[c * 32 + i] += p;
+          if (want_row0 && col < N) p_row0[((size_t)b * H + h) * N + col] = p;
+        }
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(&s.t_empty[ab]);
+    }
+    // All MMAs have completed (the last t_full was observed) and every TMA load was consumed: the pipeline
+    // buffers are free -> stage the tile so that global stores are row-contiguous.
+    float* stage = reinterpret_cast<float*>(&s.qk[0][0][0]);
+    const float invH = 1.f / (float)H;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) stage[row * STAGE_LD + half * 64 + i] = acc[i] * invH;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float* dst = mean + (size_t)b * mean_bs;
+    for (int rr = we * 16; rr < we * 16 + 16; ++rr) {
+      if (q0 + rr >= N) break;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int col = cc * 32 + lane;
+        if (kv0 + col < N) dst[(size_t)(q0 + rr) * N + kv0 + col] = stage[rr * STAGE_LD + col];
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<256>(tmem);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 tensor [B, N, S*H, D] (S = 3 for qkv, 1 for out / d_out) viewed as 4-D (d, sh, n, b); box = 128 rows x 64 d.
+int make_tmap(CUtensorMap* m, const void* base, int B, int N, int SH, int D) {
+  EncodeTiledFn fn = get_encode_fn();
+  ACR_REQUIRE(fn != nullptr, ACR_E_NOSM100, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)SH, (cuuint64_t)N, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)D * 2, (cuuint64_t)SH * D * 2, (cuuint64_t)N * SH * D * 2};
+  cuuint32_t box[4] = {(cuuint32_t)D, 1, (cuuint32_t)BM, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ACR_REQUIRE(r == CUDA_SUCCESS, ACR_E_INVAL, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, float scale,
+                                 void* out, float* lse, float* attn_mean, long long mean_batch_stride,
+                                 float* p_row0, void* stream) {
+  ACR_REQUIRE(qkv && out && lse, ACR_E_INVAL, "acr_attn_fwd_bf16: null pointer");
+  ACR_REQUIRE(B > 0 && N > 0 && H > 0, ACR_E_INVAL, "acr_attn_fwd_bf16: bad shape");
+  ACR_REQUIRE(D == HD, ACR_E_INVAL, "acr_attn_fwd_bf16: head dim %d unsupported (64 only)", D);
+  ACR_REQUIRE(B <= 65535 && H <= 65535, ACR_E_INVAL, "acr_attn_fwd_bf16: grid too large");
+  ACR_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, ACR_E_ALIGN, "acr_attn_fwd_bf16: qkv/out must be 16-byte aligned");
+  ACR_REQUIRE(p_row0 == nullptr || attn_mean != nullptr, ACR_E_INVAL, "acr_attn_fwd_bf16: p_row0 needs attn_mean");
+  ACR_REQUIRE(acr_device_is_sm100(), ACR_E_NOSM100, "acr_attn_fwd_bf16: needs an sm_100 device");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tmap;
+  if (int e = make_tmap(&tmap, qkv, B, N, 3 * H, D)) return e;
+  const float scale_log2 = scale * kLog2e;
+  const int qt = (N + BM - 1) / BM, kt = (N + BN - 1) / BN;
+  {
+    const size_t smem = sizeof(FwdSmem) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ACR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    dim3 grid(qt, H, B);
+    attn_fwd_kernel<<<grid, 256, smem, st>>>(tmap, (__nv_bfloat16*)out, lse, N, H, scale_log2);
+    if (int e = acr::check_launch("attn_fwd_kernel")) return e;
+  }
+  if (attn_mean) {
+    const size_t smem = sizeof(MeanSmem) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ACR_CUDA(cudaFuncSetAttribute(attn_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    dim3 grid(kt, qt, B);
+    attn_mean_kernel<<<grid, 384, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, p_row0, N, H, scale_log2);
+    if (int e = acr::check_launch("attn_mean_kernel")) return e;
+  }
+  return 0;
+}
+
 extern "C" size_t acr_attn_bwd_bf16_workspace(int, int, int, int) { return 256; }
 extern "C" int acr_attn_bwd_bf16(const void*, const void*, const float*, const void*, int, int, int, int, float,
                                  const float*, long long, void*, float*, void*, size_t, void*) {

@@ -178,7 +178,13 @@ class VisionTransformer(nn.Module):
         un-normalised output of the last block (what the reference reads through its forward hook, Q4)."""
         b, c, h, w = x.shape
         pos_embed = self._resize_pos_embed(self.pos_embed, h // self.patch_size[1], w // self.patch_size[0])
-        x = self.patch_embed.proj(x).flatten(2).transpose(1, 2)
+        # patch_embed.proj is a stride-16 16x16 convolution (vision_transformer.py:463-464) == one GEMM over
+        # unfolded patches; done as a Linear so fp32 stays true fp32 (cuDNN convolutions default to TF32).
+        ph, pw = h // self.patch_size[1], w // self.patch_size[0]
+        P = self.patch_size[0]
+        proj = self.patch_embed.proj
+        x = x.reshape(b, c, ph, P, pw, P).permute(0, 2, 4, 1, 3, 5).reshape(b, ph * pw, c * P * P)
+        x = F.linear(x, proj.weight.reshape(proj.weight.shape[0], -1), proj.bias)
         cls_tokens = self.cls_token.expand(b, -1, -1)
         x = torch.cat((cls_tokens.to(x.dtype), x), dim=1)
         x = x + pos_embed.to(x.dtype)

@@ -55,13 +55,13 @@ GRAD_KEYS = ["pretrained.model.blocks.0.attn.qkv.weight", "pretrained.model.bloc
              "pretrained.model.blocks.5.mlp.fc1.weight", "cls_head.weight", "pretrained.model.pos_embed"]
 
 
-def train_golden(name, backbone, S, B, C, alpha, depth_key=11):
+def train_golden(name, backbone, S, B, C, alpha, depth_key=11, qkv_gain=4.0):
     model = loader.build_acr(C, backbone)
     dim = model.pretrained.model.embed_dim
     if backbone == "vitl":   # the reference hard-codes 768 and cannot run ViT-L unpatched
         model.cls_head = torch.nn.Linear(dim, C)
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
-    model.load_state_dict(orc.synth_state_dict(shapes))
+    model.load_state_dict(orc.synth_state_dict(shapes, qkv_gain=qkv_gain))
     model.train()
     img = synth.images(B, S)
     label = synth.labels(B, C)
@@ -76,7 +76,7 @@ def train_golden(name, backbone, S, B, C, alpha, depth_key=11):
     params = dict(model.named_parameters())
     keys = [k.replace(".11.", f".{depth_key}.") for k in GRAD_KEYS]
     out = dict(loss=loss, cls_loss_1=l1, cls_loss_2=l2, cls_align_loss=lc, aff_align_loss=la,
-               x_cls_1=x1, x_cls_2=x2, x_patch_cls_1=cls_list[2], alpha=alpha, S=S, B=B, C=C)
+               x_cls_1=x1, x_cls_2=x2, x_patch_cls_1=cls_list[2], alpha=alpha, S=S, B=B, C=C, qkv_gain=qkv_gain)
     if attn1.numel() <= 200000:
         out.update(attn1=a1_keep, attn2=a2_keep)
     else:   # sub-sample: a few layers, rows and a column stride
@@ -204,6 +204,6 @@ if __name__ == "__main__":
     if "bilateral" in which: bilateral_golden()
     if "train64" in which: train_golden("train_vitb_64.npz", "vitb", 64, 2, 20, 100.0)
     if "train448" in which: train_golden("train_vitb_448.npz", "vitb", 448, 1, 20, 100.0)
-    if "vitl64" in which: train_golden("train_vitl_96.npz", "vitl", 96, 1, 20, 100.0, depth_key=23)
+    if "vitl64" in which: train_golden("train_vitl_96.npz", "vitl", 96, 1, 20, 100.0, depth_key=23, qkv_gain=2.5)
     if "infer448" in which: infer_golden("infer_vitb_448.npz", 448, 20, (3, 7, 14), (60, 80), 10, "grad")
     if "infer_ms" in which: infer_golden("infer_vitb_128_ms.npz", 128, 20, (2, 9), (40, 36), 9, "cam_grad_s", scales=(0.5, 1, 1.5))

@@ -108,11 +108,11 @@ def test_attention_f32_core_vs_oracle(dev, B, N, H, D):
 
 
 # ------------------------------------------------------------------ (a3-a7) model + training step
-def _build(dev, C, backbone, precision):
+def _build(dev, C, backbone, precision, qkv_gain=4.0):
     from acr_wsss_b200 import ACR
     orc = _orc()
     dim, depth, scratch = (768, 12, (96, 192, 384, 768)) if backbone == "vitb" else (1024, 24, (256, 512, 1024, 1024))
-    sd = orc.synth_state_dict(orc.vit_shapes(dim, depth, C, scratch_in=scratch))
+    sd = orc.synth_state_dict(orc.vit_shapes(dim, depth, C, scratch_in=scratch), qkv_gain=qkv_gain)
     m = ACR(C, backbone, precision=precision).to(dev)
     missing = m.load_state_dict(sd, strict=True)       # reference key layout must load unchanged
     return m, sd
@@ -142,7 +142,7 @@ def _train_step_check(dev, name, backbone, precision, tol, inline_loss=False):
     orc = _orc()
     g = load_golden(name)
     S, B, C, alpha = int(g["S"]), int(g["B"]), int(g["C"]), float(g["alpha"])
-    m, _ = _build(dev, C, backbone, precision)
+    m, _ = _build(dev, C, backbone, precision, float(g["qkv_gain"]))
     m.train()
     m.set_capture_grad(False)
     img, label = synth.images(B, S).to(dev), synth.labels(B, C).to(dev)
@@ -339,3 +339,28 @@ def test_bilateral_rejects_bad_buffers(dev):
         bilateralfilter_batch(np.zeros(10, np.float32), np.zeros(10, np.float32), np.zeros(10, np.float32), 1, 2, 4, 4, 1.0, 1.0)
     with pytest.raises(TypeError):
         bilateralfilter_batch(np.zeros((1, 3, 4, 4), np.float32), np.zeros(32, np.float32), np.zeros(32, np.float32), 1, 2, 4, 4, 1.0, 1.0)
+
+
+# ------------------------------------------------------------------ (a1) fused tcgen05 path (bf16 operands)
+def _sm100():
+    from acr_wsss_b200 import _lib
+    return bool(_lib.lib().acr_device_is_sm100())
+
+
+@pytest.mark.parametrize("B,N,H", [(1, 1, 1), (2, 17, 3), (1, 128, 2), (1, 197, 12), (2, 785, 12), (1, 1025, 16)])
+def test_attention_bf16_forward_vs_oracle(dev, B, N, H):
+    from acr_wsss_b200 import ops
+    orc = _orc()
+    assert _sm100(), "the fused path needs sm_100a; there is no fallback"
+    D = 64
+    g = torch.Generator().manual_seed(N + H)
+    qkv = (torch.randn(B, N, 3 * H * D, generator=g) * 1.5).to(torch.bfloat16)
+    out_r, P_r = orc.attention_core(qkv.float(), H, D ** -0.5)
+    st = {}
+    with torch.no_grad():
+        out, mean = ops.attention_core(qkv.to(dev), H, D ** -0.5, None, st, "bf16")
+    assert out.dtype == torch.bfloat16 and mean.dtype == torch.float32
+    assert rel_err(t2n(out), t2n(out_r)) < BF16_TOL
+    assert rel_err(t2n(mean), t2n(P_r.mean(1))) < 2e-3          # fp32 softmax on exact bf16 products
+    assert rel_err(t2n(st["row0"]), t2n(P_r[:, :, 0, :])) < 2e-3
+    assert float((mean.sum(-1) - 1).abs().max()) < 1e-3         # rows of a head-mean of softmaxes sum to 1

@@ -53,7 +53,7 @@ def test_train_step_matches_reference(name, heads):
     S, B, C = int(g["S"]), int(g["B"]), int(g["C"])
     dim, depth = (768, 12) if heads == 12 else (1024, 24)
     scratch = (96, 192, 384, 768) if heads == 12 else (256, 512, 1024, 1024)
-    sd = orc.synth_state_dict(orc.vit_shapes(dim, depth, C, scratch_in=scratch))
+    sd = orc.synth_state_dict(orc.vit_shapes(dim, depth, C, scratch_in=scratch), qkv_gain=float(g["qkv_gain"]))
     sd = {k: v.requires_grad_(True) for k, v in sd.items()}
     img, label = synth.images(B, S), synth.labels(B, C)
     loss, parts, (attn1, attn2, x1, x2) = orc.train_step_loss(sd, img, label, float(g["alpha"]), heads)
