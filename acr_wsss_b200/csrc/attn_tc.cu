@@ -185,6 +185,9 @@ struct MeanSmem {
 constexpr int STAGE_LD = 129;                  // fp32 staging row stride (conflict-free)
 static_assert(sizeof(float) * BM * STAGE_LD <= sizeof(uint8_t) * MEAN_STAGES * 2 * TILE_BYTES, "staging tile must fit");
 
+// MODE 0: mean[b,q,kv] = (1/H) sum_h P_h ; MODE 1 (backward pre-pass): delta[b,h,q] += (1/H) sum_kv P_h[q,kv] * G[b,q,kv]
+// (`mean` is then the read-only G, `p_row0` the delta accumulator).
+template <int MODE>
 __global__ void __launch_bounds__(384)
 attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __restrict__ lse, float* __restrict__ mean,
                  long long mean_bs, float* __restrict__ p_row0, int N, int H, float scale_log2) {
@@ -238,15 +241,24 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const bool row_ok = (q0 + row) < N;
     float acc[64];
+    const float invH = 1.f / (float)H;
+    if (MODE == 0) {
 #pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    } else {
+      // G tile of this thread's row, pre-scaled by 1/H; zero outside the map
+      const float* grow = mean + (size_t)b * mean_bs + (size_t)(q0 + row) * N + kv0 + half * 64;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) acc[i] = (row_ok && kv0 + half * 64 + i < N) ? __ldg(grow + i) * invH : 0.f;
+    }
     uint32_t r[32];
     for (int h = 0; h < H; ++h) {
       const int ab = h & 1;
       const float lse2 = row_ok ? __ldg(lse + ((size_t)b * H + h) * N + q0 + row) * kLog2e : 0.f;
       tc::mbar_wait(&s.t_full[ab], (h >> 1) & 1);
       tc::tc_fence_after();
-      const bool want_row0 = (p_row0 != nullptr) && (q0 + row == 0);
+      const bool want_row0 = (MODE == 0) && (p_row0 != nullptr) && (q0 + row == 0);
+      float part = 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         tc::tmem_ld32(tmem + ab * 128 + lane_off + half * 64 + c * 32, r);
@@ -256,17 +268,22 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
           const int col = kv0 + half * 64 + c * 32 + i;
           float p = exp2f(__uint_as_float(r[i]) * scale_log2 - lse2);
           if (col >= N) p = 0.f;
-          acc[c * 32 + i] += p;
-          if (want_row0 && col < N) p_row0[((size_t)b * H + h) * N + col] = p;
+          if (MODE == 0) {
+            acc[c * 32 + i] += p;
+            if (want_row0 && col < N) p_row0[((size_t)b * H + h) * N + col] = p;
+          } else {
+            part = fmaf(p, acc[c * 32 + i], part);
+          }
         }
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&s.t_empty[ab]);
+      if (MODE == 1 && row_ok) atomicAdd(p_row0 + ((size_t)b * H + h) * N + q0 + row, part);
     }
+    if (MODE == 0) {
     // All MMAs have completed (the last t_full was observed) and every TMA load was consumed: the pipeline
     // buffers are free -> stage the tile so that global stores are row-contiguous.
     float* stage = reinterpret_cast<float*>(&s.qk[0][0][0]);
-    const float invH = 1.f / (float)H;
 #pragma unroll
     for (int i = 0; i < 64; ++i) stage[row * STAGE_LD + half * 64 + i] = acc[i] * invH;
     asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -279,6 +296,7 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
         if (kv0 + col < N) dst[(size_t)(q0 + rr) * N + kv0 + col] = stage[rr * STAGE_LD + col];
       }
     }
+    }  // MODE == 0
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -351,19 +369,326 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
     const size_t smem = sizeof(MeanSmem) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-      ACR_CUDA(cudaFuncSetAttribute(attn_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ACR_CUDA(cudaFuncSetAttribute(attn_mean_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
     dim3 grid(kt, qt, B);
-    attn_mean_kernel<<<grid, 384, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, p_row0, N, H, scale_log2);
+    attn_mean_kernel<0><<<grid, 384, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, p_row0, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel")) return e;
   }
   return 0;
 }
 
-extern "C" size_t acr_attn_bwd_bf16_workspace(int, int, int, int) { return 256; }
-extern "C" int acr_attn_bwd_bf16(const void*, const void*, const float*, const void*, int, int, int, int, float,
-                                 const float*, long long, void*, float*, void*, size_t, void*) {
-  acr::set_error("acr_attn_bwd_bf16: not built yet");
-  return ACR_E_NOSM100;
+
+// =============================================================================================
+// Backward.  dP_h = dO_h V_h^T + G/H ; dS_h = P_h * (dP_h - delta) ; delta[q] = sum_j P_h[q,j] dP_h[q,j]
+//   = dO_q . O_q + (1/H) sum_j P_h[q,j] G[q,j]   (the second term is what the affinity gradient adds).
+// Kernels: bwd_delta_kernel (dO.O) -> attn_mean_kernel<1> (+ P.G/H) -> attn_bwd_kernel (per (kv tile, h, b): K_j, V_j
+// stationary, loop over q tiles; everything is computed TRANSPOSED (rows = keys) so that P^T and dS^T are the
+// TMEM A operands of the dV / dK MMAs; dQ tiles are reduced across kv tiles with fp32 atomics) -> bwd_dq_convert_kernel.
+// =============================================================================================
+namespace {
+
+constexpr uint32_t IDESC_DQ = tc::idesc_bf16_f32(128, 64, 1, 1);   // dQ = dS K : A = dS^T tile in smem (MN-major), B = K MN-major
+
+__global__ void __launch_bounds__(256)
+bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ d_out, float* __restrict__ delta,
+                 int B, int N, int H) {
+  // one thread per (b, n, h): 64-element dot product of two 128-byte rows
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)B * N * H) return;
+  const int h = (int)(t % H);
+  const long long bn = t / H;
+  const int n = (int)(bn % N), b = (int)(bn / N);
+  const uint4* po = reinterpret_cast<const uint4*>(out + t * HD);
+  const uint4* pd = reinterpret_cast<const uint4*>(d_out + t * HD);
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < HD / 8; ++c) {
+    const uint4 a = __ldg(po + c), d = __ldg(pd + c);
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 fa = __bfloat1622float2(a2[i]), fd = __bfloat1622float2(d2[i]);
+      acc = fmaf(fa.x, fd.x, acc);
+      acc = fmaf(fa.y, fd.y, acc);
+    }
+  }
+  delta[((size_t)b * H + h) * N + n] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+bwd_dq_convert_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ d_qkv, int B, int N, int H, float scale) {
+  // dq_acc [B,H,N,64] fp32 -> d_qkv[b,n,0,h,:] bf16 (scaled); one thread per 8 elements
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)B * H * N * (HD / 8)) return;
+  const int c = (int)(t % (HD / 8));
+  const long long row = t / (HD / 8);               // (b*H + h)*N + n
+  const int n = (int)(row % N);
+  const int h = (int)((row / N) % H);
+  const int b = (int)(row / ((long long)N * H));
+  const float4* src = reinterpret_cast<const float4*>(dq_acc + row * HD + c * 8);
+  const float4 x = __ldg(src), y = __ldg(src + 1);
+  uint4 v;
+  v.x = tc::pack_bf16(x.x * scale, x.y * scale);
+  v.y = tc::pack_bf16(x.z * scale, x.w * scale);
+  v.z = tc::pack_bf16(y.x * scale, y.y * scale);
+  v.w = tc::pack_bf16(y.z * scale, y.w * scale);
+  *reinterpret_cast<uint4*>(d_qkv + (((size_t)b * N + n) * 3 + 0) * ((size_t)H * HD) + (size_t)h * HD + c * 8) = v;
+}
+
+struct BwdSmem {
+  uint8_t k[TILE_BYTES];
+  uint8_t v[TILE_BYTES];
+  uint8_t q[2][TILE_BYTES];
+  uint8_t d_o[2][TILE_BYTES];
+  uint8_t dst[2][TILE_BYTES];        // dS^T as the MN-major A operand of the dQ MMA: [q block of 64][kv row][64 q] swizzled
+  float lse2[2][BM];
+  float delta[2][BM];
+  uint64_t kv_full, qdo_full[2], qdo_empty[2], sdp_full, pds_full, dq_full, dq_read;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(384)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                const float* __restrict__ lse, const float* __restrict__ delta, const float* __restrict__ g_mean, long long g_bs,
+                __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ dq_acc, float* __restrict__ g_row0,
+                int N, int H, float scale, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  BwdSmem& s = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * BN, h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (N + BM - 1) / BM;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_qkv);
+    tc::prefetch_tmap(&tmap_do);
+    tc::mbar_init(&s.kv_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.qdo_full[i], 1); tc::mbar_init(&s.qdo_empty[i], 1); }
+    tc::mbar_init(&s.sdp_full, 1);
+    tc::mbar_init(&s.pds_full, 256);
+    tc::mbar_init(&s.dq_full, 1);
+    tc::mbar_init(&s.dq_read, 256);
+    tc::fence_barrier_init();
+  }
+  if (warp == 2) tc::tmem_alloc<512>(&s.tmem_base);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = s.tmem_base;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384, tP = tmem + 448;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(&s.kv_full, 2 * TILE_BYTES);
+      tc::tma_load_4d(s.k, &tmap_qkv, &s.kv_full, 0, H + h, kv0, b);
+      tc::tma_load_4d(s.v, &tmap_qkv, &s.kv_full, 0, 2 * H + h, kv0, b);
+      for (int i = 0; i < ntiles; ++i) {
+        const int st = i & 1;
+        tc::mbar_wait(&s.qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        tc::mbar_arrive_expect_tx(&s.qdo_full[st], 2 * TILE_BYTES);
+        tc::tma_load_4d(s.q[st], &tmap_qkv, &s.qdo_full[st], 0, h, i * BM, b);
+        tc::tma_load_4d(s.d_o[st], &tmap_do, &s.qdo_full[st], 0, h, i * BM, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      tc::mbar_wait(&s.kv_full, 0);
+      const uint32_t k_addr = tc::smem_u32(s.k), v_addr = tc::smem_u32(s.v);
+      for (int i = 0; i < ntiles; ++i) {
+        const int st = i & 1;
+        tc::mbar_wait(&s.qdo_full[st], (i >> 1) & 1);
+        if (i > 0) tc::mbar_wait(&s.dq_read, (i - 1) & 1);      // previous tile fully drained: S/dP/dQ regions reusable
+        tc::tc_fence_after();
+        const uint32_t q_addr = tc::smem_u32(s.q[st]), do_addr = tc::smem_u32(s.d_o[st]), ds_addr = tc::smem_u32(s.dst[0]);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)      // S^T = K Q^T
+          tc::mma_ss(tS, tc::smem_desc_sw128(k_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(q_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)      // dP^T = V dO^T
+          tc::mma_ss(tDP, tc::smem_desc_sw128(v_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(do_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
+        tc::tc_commit(&s.sdp_full);
+        tc::mbar_wait(&s.pds_full, i & 1);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < BM / 16; ++ks)      // dV += P^T dO
+          tc::mma_ts(tDV, tP + ks * 8, tc::smem_desc_sw128(do_addr + ks * 2048, 1024, 1024), IDESC_PV, (i > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < BM / 16; ++ks)      // dK += dS^T Q   (A = the same dS^T smem tile read K-major: block ks/4, 32-byte k step)
+          tc::mma_ss(tDK, tc::smem_desc_sw128(ds_addr + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024),
+                     tc::smem_desc_sw128(q_addr + ks * 2048, 1024, 1024), IDESC_PV, (i > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < BN / 16; ++ks)      // dQ_i = dS K   (A = dS^T smem, MN-major, two 64-row M blocks 16 KB apart)
+          tc::mma_ss(tDQ, tc::smem_desc_sw128(ds_addr + ks * 2048, TILE_BYTES, 1024), tc::smem_desc_sw128(k_addr + ks * 2048, 1024, 1024),
+                     IDESC_DQ, ks > 0);
+        tc::tc_commit(&s.dq_full);
+        tc::tc_commit(&s.qdo_empty[st]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int we = warp - 4;
+    const int row = (warp & 3) * 32 + lane;          // key row inside the tile (TMEM lane)
+    const int half = we >> 2;                        // which 64-column (query) half
+    const int tid_e = we * 32 + lane;                // 0..255
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const bool kv_ok = (kv0 + row) < N;
+    const float invH = 1.f / (float)H;
+    uint32_t rs[32], rd[32];
+    for (int i = 0; i < ntiles; ++i) {
+      const int q0 = i * BM, buf = i & 1;
+      // stage per-query-row statistics of this tile (double-buffered, one named barrier per iteration)
+      {
+        const int qi = q0 + (tid_e & 127);
+        const bool ok = qi < N;
+        if (tid_e < 128) s.lse2[buf][tid_e] = ok ? __ldg(lse + ((size_t)b * H + h) * N + qi) * kLog2e : INFINITY;
+        else s.delta[buf][tid_e - 128] = ok ? __ldg(delta + ((size_t)b * H + h) * N + qi) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tc::mbar_wait(&s.sdp_full, i & 1);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        tc::tmem_ld32(tS + lane_off + half * 64 + c * 32, rs);
+        tc::tmem_ld32(tDP + lane_off + half * 64 + c * 32, rd);
+        tc::tmem_ld_wait();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int col = half * 64 + c * 32 + 2 * e + u;       // query index inside the tile
+            const int qi = q0 + col;
+            float p = exp2f(__uint_as_float(rs[2 * e + u]) * scale_log2 - s.lse2[buf][col]);
+            if (!kv_ok) p = 0.f;
+            float dp = __uint_as_float(rd[2 * e + u]);
+            if (g_mean != nullptr && kv_ok && qi < N) dp = fmaf(__ldg(g_mean + (size_t)b * g_bs + (size_t)qi * N + kv0 + row), invH, dp);
+            if (g_row0 != nullptr && qi == 0 && kv_ok) g_row0[((size_t)b * H + h) * N + kv0 + row] = dp;
+            pv[u] = p;
+            dv[u] = p * (dp - s.delta[buf][col]);
+          }
+          pk[e] = tc::pack_bf16(pv[0], pv[1]);
+          dk[e] = tc::pack_bf16(dv[0], dv[1]);
+        }
+        tc::tmem_st16(tP + lane_off + half * 32 + c * 16, pk);       // P^T (bf16): the A operand of the dV MMA
+        // dS^T row -> smem, SWIZZLE_128B: block `half` (64 queries), row `row`, 16-byte chunk cc at position cc ^ (row & 7);
+        // read K-major by the dK MMA (A[kv][q]) and MN-major by the dQ MMA (A[q][kv])
+        uint8_t* base = s.dst[half] + row * 128;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int chunk = c * 4 + cc;
+          uint4 v = make_uint4(dk[cc * 4 + 0], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]);
+          *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = v;
+        }
+      }
+      tc::tmem_st_wait();
+      tc::fence_proxy_async_smem();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&s.pds_full);
+      // dQ tile: rows = queries (lanes), 64 columns = d; this thread reduces 32 of them into the fp32 accumulator
+      tc::mbar_wait(&s.dq_full, i & 1);
+      tc::tc_fence_after();
+      tc::tmem_ld32(tDQ + lane_off + half * 32, rs);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&s.dq_read);
+      if (q0 + row < N) {
+        float* dqp = dq_acc + (((size_t)b * H + h) * N + q0 + row) * HD + half * 32;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) atomicAdd(dqp + e, __uint_as_float(rs[e]));
+      }
+    }
+    // epilogue: dV, dK rows of this key tile (all MMAs are complete: the last dq_full covered them)
+    tc::tmem_ld32(tDV + lane_off + half * 32, rs);      // warp-collective: outside the per-row validity branch
+    tc::tmem_ld32(tDK + lane_off + half * 32, rd);
+    tc::tmem_ld_wait();
+    if (kv_ok) {
+      const size_t E = (size_t)H * HD;
+      __nv_bfloat16* dkp = d_qkv + (((size_t)b * N + kv0 + row) * 3 + 1) * E + (size_t)h * HD + half * 32;
+      __nv_bfloat16* dvp = d_qkv + (((size_t)b * N + kv0 + row) * 3 + 2) * E + (size_t)h * HD + half * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 v, k;
+        v.x = tc::pack_bf16(__uint_as_float(rs[c * 8 + 0]), __uint_as_float(rs[c * 8 + 1]));
+        v.y = tc::pack_bf16(__uint_as_float(rs[c * 8 + 2]), __uint_as_float(rs[c * 8 + 3]));
+        v.z = tc::pack_bf16(__uint_as_float(rs[c * 8 + 4]), __uint_as_float(rs[c * 8 + 5]));
+        v.w = tc::pack_bf16(__uint_as_float(rs[c * 8 + 6]), __uint_as_float(rs[c * 8 + 7]));
+        k.x = tc::pack_bf16(__uint_as_float(rd[c * 8 + 0]) * scale, __uint_as_float(rd[c * 8 + 1]) * scale);
+        k.y = tc::pack_bf16(__uint_as_float(rd[c * 8 + 2]) * scale, __uint_as_float(rd[c * 8 + 3]) * scale);
+        k.z = tc::pack_bf16(__uint_as_float(rd[c * 8 + 4]) * scale, __uint_as_float(rd[c * 8 + 5]) * scale);
+        k.w = tc::pack_bf16(__uint_as_float(rd[c * 8 + 6]) * scale, __uint_as_float(rd[c * 8 + 7]) * scale);
+        reinterpret_cast<uint4*>(dvp)[c] = v;
+        reinterpret_cast<uint4*>(dkp)[c] = k;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem);
+  }
+}
+
+}  // namespace
+
+extern "C" size_t acr_attn_bwd_bf16_workspace(int B, int N, int H, int D) {
+  if (B <= 0 || N <= 0 || H <= 0 || D <= 0) return 0;
+  const size_t rows = (size_t)B * H * N;
+  return acr::align_up(rows * sizeof(float), 256) + acr::align_up(rows * D * sizeof(float), 256);
+}
+
+extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* lse, const void* d_out,
+                                 int B, int N, int H, int D, float scale,
+                                 const float* g_mean, long long g_batch_stride,
+                                 void* d_qkv, float* g_row0, void* workspace, size_t workspace_bytes, void* stream) {
+  ACR_REQUIRE(qkv && out && lse && d_out && d_qkv && workspace, ACR_E_INVAL, "acr_attn_bwd_bf16: null pointer");
+  ACR_REQUIRE(B > 0 && N > 0 && H > 0, ACR_E_INVAL, "acr_attn_bwd_bf16: bad shape");
+  ACR_REQUIRE(D == HD, ACR_E_INVAL, "acr_attn_bwd_bf16: head dim %d unsupported (64 only)", D);
+  ACR_REQUIRE(B <= 65535 && H <= 65535, ACR_E_INVAL, "acr_attn_bwd_bf16: grid too large");
+  ACR_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ((uintptr_t)d_qkv & 15) == 0,
+              ACR_E_ALIGN, "acr_attn_bwd_bf16: tensors must be 16-byte aligned");
+  ACR_REQUIRE(((uintptr_t)workspace & 255) == 0, ACR_E_ALIGN, "acr_attn_bwd_bf16: workspace must be 256-byte aligned");
+  ACR_REQUIRE(workspace_bytes >= acr_attn_bwd_bf16_workspace(B, N, H, D), ACR_E_NOMEM, "acr_attn_bwd_bf16: workspace too small");
+  ACR_REQUIRE(acr_device_is_sm100(), ACR_E_NOSM100, "acr_attn_bwd_bf16: needs an sm_100 device");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t rows = (size_t)B * H * N;
+  float* delta = (float*)workspace;
+  float* dq_acc = (float*)((char*)workspace + acr::align_up(rows * sizeof(float), 256));
+  CUtensorMap tmap_qkv, tmap_do;
+  if (int e = make_tmap(&tmap_qkv, qkv, B, N, 3 * H, D)) return e;
+  if (int e = make_tmap(&tmap_do, d_out, B, N, H, D)) return e;
+  const float scale_log2 = scale * kLog2e;
+  const int qt = (N + BM - 1) / BM, kt = (N + BN - 1) / BN;
+
+  ACR_CUDA(cudaMemsetAsync(dq_acc, 0, rows * D * sizeof(float), st));
+  bwd_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)d_out, delta, B, N, H);
+  if (int e = acr::check_launch("bwd_delta_kernel")) return e;
+  if (g_mean) {
+    const size_t smem = sizeof(MeanSmem) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ACR_CUDA(cudaFuncSetAttribute(attn_mean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    dim3 grid(kt, qt, B);
+    attn_mean_kernel<1><<<grid, 384, smem, st>>>(tmap_qkv, lse, const_cast<float*>(g_mean), g_batch_stride, delta, N, H, scale_log2);
+    if (int e = acr::check_launch("attn_mean_kernel<1>")) return e;
+  }
+  {
+    const size_t smem = sizeof(BwdSmem) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      ACR_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    dim3 grid(kt, H, B);
+    attn_bwd_kernel<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, lse, delta, g_mean, g_batch_stride, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
+                                             N, H, scale, scale_log2);
+    if (int e = acr::check_launch("attn_bwd_kernel")) return e;
+  }
+  const long long nconv = (long long)rows * (HD / 8);
+  bwd_dq_convert_kernel<<<(unsigned)((nconv + 255) / 256), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)d_qkv, B, N, H, scale);
+  return acr::check_launch("bwd_dq_convert_kernel");
 }

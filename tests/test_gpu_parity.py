@@ -364,3 +364,32 @@ def test_attention_bf16_forward_vs_oracle(dev, B, N, H):
     assert rel_err(t2n(mean), t2n(P_r.mean(1))) < 2e-3          # fp32 softmax on exact bf16 products
     assert rel_err(t2n(st["row0"]), t2n(P_r[:, :, 0, :])) < 2e-3
     assert float((mean.sum(-1) - 1).abs().max()) < 1e-3         # rows of a head-mean of softmaxes sum to 1
+
+
+@pytest.mark.parametrize("B,N,H,with_g", [(1, 1, 1, True), (2, 17, 3, True), (1, 128, 2, False), (1, 197, 12, True),
+                                          (2, 785, 12, True), (1, 1025, 16, True)])
+def test_attention_bf16_backward_vs_oracle(dev, B, N, H, with_g):
+    from acr_wsss_b200 import ops
+    orc = _orc()
+    D = 64
+    g = torch.Generator().manual_seed(N + H + 1)
+    qkv = (torch.randn(B, N, 3 * H * D, generator=g) * 1.5).to(torch.bfloat16)
+    d_out = torch.randn(B, N, H * D, generator=g).to(torch.bfloat16)
+    G = torch.randn(B, N, N, generator=g) * 0.05 if with_g else None
+    dqkv_r, dP_r = orc.attention_core_backward(qkv.float(), H, D ** -0.5, d_out.float(), G)
+    q = qkv.to(dev).requires_grad_(True)
+    st = {"capture_grad": True}
+    out, mean = ops.attention_core(q, H, D ** -0.5, None, st, "bf16")
+    loss = (out.float() * d_out.to(dev).float()).sum()
+    if with_g:
+        loss = loss + (mean * G.to(dev)).sum()
+    loss.backward()
+    got = t2n(q.grad).reshape(B, N, 3, H * D)
+    ref = t2n(dqkv_r).reshape(B, N, 3, H * D)
+    for s_, name in enumerate("qkv"):
+        assert rel_err(got[:, :, s_], ref[:, :, s_]) < 2 * BF16_TOL, name
+    assert rel_err(t2n(st["grad_row0"]), t2n(dP_r[:, :, 0, :])) < BF16_TOL
+
+
+def test_train_step_bf16_vitb_64(dev):
+    _train_step_check(dev, "train_vitb_64.npz", "vitb", "bf16", 3 * BF16_TOL)
