@@ -13,6 +13,8 @@ from .model import ACR, Attention, Block, VisionTransformer  # noqa: F401
 from .losses import acr_consistency_loss, acr_total_loss, dense_crf_loss  # noqa: F401
 from .cam import affinity_refine, infer_cam_image, normalize_cam, pseudo_label  # noqa: F401
 from .pamr import PAMR  # noqa: F401
+from .train import Trainer, PolyOptimizer  # noqa: F401
+from .parallel import GradBuckets, shard_indices  # noqa: F401
 from .bilateralfilter import bilateralfilter_batch, bilateralfilter  # noqa: F401
 
 __version__ = "0.1.0"

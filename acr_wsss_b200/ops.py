@@ -13,6 +13,44 @@ from . import _lib
 _GETAM_FUNCS = {"grad": 0, "grad_s": 1, "cam_grad": 2, "cam_grad_s": 3}
 
 
+class _Profile:
+    """Optional per-entry-point timing (CUDA events on the launching stream) and launch counting.
+    Off by default; bench.py switches it on for the timed region."""
+
+    def __init__(self):
+        self.reset(False)
+
+    def reset(self, enabled=False):
+        self.enabled = enabled
+        self.events = {}     # name -> list of (start, end)
+        self.launches = 0
+
+    def summary(self):
+        torch.cuda.synchronize()
+        kernels = {}
+        for name, evs in self.events.items():
+            kernels[name] = {"name": name, "calls": len(evs), "ms": sum(a.elapsed_time(b) for a, b in evs)}
+        return {"launches": self.launches, "kernels": kernels}
+
+
+PROFILE = _Profile()
+
+
+def _call(name, nlaunch, *args):
+    """Invoke C-ABI entry `name`; raises on failure.  `nlaunch` = kernels this call launches (for gpu_launches)."""
+    fn = getattr(_lib.lib(), name)
+    if PROFILE.enabled:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        PROFILE.events.setdefault(name, []).append((a, b))
+        PROFILE.launches += nlaunch
+    else:
+        rc = fn(*args)
+    _lib.check(rc, name)
+
+
 def _p(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -57,8 +95,8 @@ class _AttnCoreF32(torch.autograd.Function):
         if mean_slot is None:
             mean_slot = torch.empty(B, N, N, device=qkv.device, dtype=torch.float32)
         assert mean_slot.stride(-1) == 1 and mean_slot.stride(-2) == N
-        _lib.check(_lib.lib().acr_attn_fwd_f32(_p(qkv), B, N, num_heads, D, scale, _p(P), _p(out),
-                                               _p(mean_slot), mean_slot.stride(0), _stream()), "acr_attn_fwd_f32")
+        _call("acr_attn_fwd_f32", 4, _p(qkv), B, N, num_heads, D, scale, _p(P), _p(out),
+                                               _p(mean_slot), mean_slot.stride(0), _stream())
         ctx.save_for_backward(qkv, P)
         ctx.dims = (B, N, num_heads, D, scale)
         ctx.state = state
@@ -79,8 +117,8 @@ class _AttnCoreF32(torch.autograd.Function):
         dP = torch.empty_like(P)
         dS = torch.empty_like(P)
         d_qkv = torch.empty_like(qkv)
-        _lib.check(_lib.lib().acr_attn_bwd_f32(_p(qkv), _p(P), _p(d_out), B, N, H, D, scale,
-                                               _p(g_mean), gs, _p(dP), _p(dS), _p(d_qkv), _stream()), "acr_attn_bwd_f32")
+        _call("acr_attn_bwd_f32", 5, _p(qkv), _p(P), _p(d_out), B, N, H, D, scale,
+                                               _p(g_mean), gs, _p(dP), _p(dS), _p(d_qkv), _stream())
         if ctx.state is not None and ctx.state.get("capture_grad", True):
             ctx.state["attn_grad"] = dP          # what save_attn_gradients keeps (vision_transformer.py:192-193)
         return d_qkv, None, None, None, None
@@ -102,9 +140,8 @@ class _AttnCoreBF16(torch.autograd.Function):
         if mean_slot is None:
             mean_slot = torch.empty(B, N, N, device=qkv.device, dtype=torch.float32)
         assert mean_slot.stride(-1) == 1 and mean_slot.stride(-2) == N
-        _lib.check(_lib.lib().acr_attn_fwd_bf16(_p(qkv), B, N, num_heads, D, scale, _p(out), _p(lse),
-                                                _p(mean_slot), mean_slot.stride(0), _p(p_row0), _stream()),
-                   "acr_attn_fwd_bf16")
+        _call("acr_attn_fwd_bf16", 2, _p(qkv), B, N, num_heads, D, scale, _p(out), _p(lse),
+                                                _p(mean_slot), mean_slot.stride(0), _p(p_row0), _stream())
         ctx.save_for_backward(qkv, out, lse)
         ctx.dims = (B, N, num_heads, D, scale)
         ctx.state = state
@@ -129,9 +166,8 @@ class _AttnCoreBF16(torch.autograd.Function):
         g_row0 = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32) if want_row0 else None
         wsb = _lib.lib().acr_attn_bwd_bf16_workspace(B, N, H, D)
         ws = torch.empty(wsb, device=qkv.device, dtype=torch.uint8)
-        _lib.check(_lib.lib().acr_attn_bwd_bf16(_p(qkv), _p(out), _p(lse), _p(d_out), B, N, H, D, scale,
-                                                _p(g_mean), gs, _p(d_qkv), _p(g_row0), _p(ws), wsb, _stream()),
-                   "acr_attn_bwd_bf16")
+        _call("acr_attn_bwd_bf16", 4, _p(qkv), _p(out), _p(lse), _p(d_out), B, N, H, D, scale,
+                                                _p(g_mean), gs, _p(d_qkv), _p(g_row0), _p(ws), wsb, _stream())
         if want_row0:
             ctx.state["grad_row0"] = g_row0
         return d_qkv, None, None, None, None
@@ -183,9 +219,8 @@ def consistency_fwd_bwd(attn1, attn2, p, alpha_cls=1.0, alpha_aff=1.0, need_grad
     g2 = torch.empty_like(a2) if need_grad else None
     wsb = _lib.lib().acr_consistency_workspace(B, L, N)
     ws = torch.empty(wsb, device=a1.device, dtype=torch.uint8)
-    _lib.check(_lib.lib().acr_consistency_fwd_bwd(_p(a1), _p(a2), B, L, N, int(p), float(alpha_cls), float(alpha_aff),
-                                                  _p(loss2), _p(g1), _p(g2), _p(ws), wsb, _stream()),
-               "acr_consistency_fwd_bwd")
+    _call("acr_consistency_fwd_bwd", 2, _p(a1), _p(a2), B, L, N, int(p), float(alpha_cls), float(alpha_aff),
+                                                  _p(loss2), _p(g1), _p(g2), _p(ws), wsb, _stream())
     return loss2, g1, g2
 
 
@@ -226,8 +261,8 @@ def getam_row0(p_row0, g_row0, start_layer=0, func="grad", skip=1, want_rows=Fal
     g_row0 = g_row0.contiguous().float()
     cam = torch.empty(1, N - skip, device=p_row0.device, dtype=torch.float32)
     rows = torch.empty(L, N, device=p_row0.device, dtype=torch.float32) if want_rows else None
-    _lib.check(_lib.lib().acr_getam_row0(_p(p_row0), _p(g_row0), L, H, N, int(start_layer), _GETAM_FUNCS[func], int(skip),
-                                         _p(cam), _p(rows), _stream()), "acr_getam_row0")
+    _call("acr_getam_row0", 1, _p(p_row0), _p(g_row0), L, H, N, int(start_layer), _GETAM_FUNCS[func], int(skip),
+                                         _p(cam), _p(rows), _stream())
     return (cam, rows) if want_rows else cam
 
 
@@ -237,7 +272,7 @@ def affinity_sum(attn, normalize=False):
     B, L, N, _ = attn.shape
     attn = attn.contiguous().float()
     A = torch.empty(B, N - 1, N - 1, device=attn.device, dtype=torch.float32)
-    _lib.check(_lib.lib().acr_affinity_sum(_p(attn), B, L, N, int(bool(normalize)), _p(A), _stream()), "acr_affinity_sum")
+    _call("acr_affinity_sum", 1, _p(attn), B, L, N, int(bool(normalize)), _p(A), _stream())
     return A
 
 
@@ -250,8 +285,7 @@ def affinity_apply(A, cam, t=1):
     cam = cam.contiguous().float()
     out = torch.empty_like(cam)
     tmp = torch.empty_like(cam) if t > 1 else None
-    _lib.check(_lib.lib().acr_affinity_refine(_p(A), _p(cam), B, Np, C, int(t), _p(out), _p(tmp), _stream()),
-               "acr_affinity_refine")
+    _call("acr_affinity_refine", 1, _p(A), _p(cam), B, Np, C, int(t), _p(out), _p(tmp), _stream())
     return out
 
 
@@ -269,8 +303,8 @@ def pamr_forward(x, mask, dilations, num_iter):
     out = torch.empty(B, C, H, W, device=x.device, dtype=torch.float32)
     wsb = _lib.lib().acr_pamr_workspace(B, K, C, H, W, nd)
     ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
-    _lib.check(_lib.lib().acr_pamr_fwd(_p(x), _p(mask), B, K, C, H, W, mh, mw, dil, nd, int(num_iter),
-                                       _p(out), _p(ws), wsb, _stream()), "acr_pamr_fwd")
+    _call("acr_pamr_fwd", 3, _p(x), _p(mask), B, K, C, H, W, mh, mw, dil, nd, int(num_iter),
+                                       _p(out), _p(ws), wsb, _stream())
     return out
 
 
@@ -286,9 +320,8 @@ def bilateral_filter(images, ins, sigmargb, sigmaxy, return_lattice_size=False):
     ws = torch.empty(wsb + 256, device=ins.device, dtype=torch.uint8)
     off = (-ws.data_ptr()) % 256
     msz = (ctypes.c_int * N)() if return_lattice_size else None
-    _lib.check(_lib.lib().acr_bilateral_batch(_p(images), _p(ins), _p(outs), N, K, H, W, float(sigmargb), float(sigmaxy),
-                                              ctypes.c_void_p(ws.data_ptr() + off), wsb, msz, _stream()),
-               "acr_bilateral_batch")
+    _call("acr_bilateral_batch", 14, _p(images), _p(ins), _p(outs), N, K, H, W, float(sigmargb), float(sigmaxy),
+                                              ctypes.c_void_p(ws.data_ptr() + off), wsb, msz, _stream())
     if return_lattice_size:
         return outs, list(msz)
     return outs

@@ -1,0 +1,81 @@
+"""Data-parallel plumbing for the ACR training step (one process per GPU, torch.distributed / NCCL).
+
+The reference wraps the model in DistributedDataParallel but calls `model.module.forward_mirror`, which bypasses
+the reducer, so no gradient is ever all-reduced (train_acr.py:99,138).  The north star asks for a real
+all-reduce, so `GradBuckets` implements one: every trainable parameter's .grad is a VIEW into one flat fp32 buffer
+(no flatten / unflatten copies); the buffer is cut into buckets in reverse registration order (the order gradients
+become ready in backward); a post-accumulate hook launches an asynchronous NCCL all-reduce (AVG) of a bucket as
+soon as its last gradient has landed, so communication over NVLink/NVSwitch overlaps the rest of the backward pass.
+CAM inference shards images round-robin with no collective (`shard_indices`).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_items, rank, world_size):
+    """Round-robin image sharding for CAM inference (the reference makes every rank redo all images,
+    infer_cam.py:119-128).  No collective is needed."""
+    return list(range(rank, n_items, world_size))
+
+
+class GradBuckets:
+    def __init__(self, params, bucket_bytes=64 << 20, process_group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        order = list(reversed(self.params))
+        total = sum(p.numel() for p in order)
+        dev = order[0].device
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.buckets = []            # (start, end, n_params)
+        self._bucket_of = {}
+        off, start, count = 0, 0, 0
+        for p in order:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            self._bucket_of[p] = len(self.buckets)
+            off += n
+            count += 1
+            if (off - start) * 4 >= bucket_bytes:
+                self.buckets.append([start, off, count])
+                start, count = off, 0
+        if count:
+            self.buckets.append([start, off, count])
+        self._pending = [b[2] for b in self.buckets]
+        self._works = []
+        self._used = set()
+        # gloo (CPU tests) has no AVG: sum, then scale after the wait
+        self._avg = self.world > 1 and dist.get_backend(process_group) == "nccl"
+        if self.world > 1:
+            for p in order:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def _hook(self, p):
+        b = self._bucket_of[p]
+        self._pending[b] -= 1
+        self._used.add(p)
+        if self._pending[b] == 0:
+            s, e, _ = self.buckets[b]
+            self._works.append(self._reduce(s, e))
+
+    def _reduce(self, s, e):
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        return dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True)
+
+    def zero(self):
+        self.flat.zero_()
+
+    def finish(self):
+        """Call after backward: reduce buckets whose hooks did not all fire (parameters without gradient this step,
+        e.g. norm/head/bkg_token) and wait for every outstanding all-reduce."""
+        if self.world > 1:
+            for b, left in enumerate(self._pending):
+                if left > 0:
+                    s, e, _ = self.buckets[b]
+                    self._works.append(self._reduce(s, e))
+            for w in self._works:
+                w.wait()
+            if not self._avg:
+                self.flat.div_(self.world)
+        self._works = []
+        self._pending = [b[2] for b in self.buckets]

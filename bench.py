@@ -1,0 +1,234 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: ACR training throughput (BASELINE.json configs[1]).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    the reference algorithm's CPU path (oracle port) on host cores
+
+A "step" = one pass of train_acr.py:127-174 over one synthetic batch: two views forward (ViT-B/16, 448x448, 20
+classes, B=8 per GPU), BCE + all-pairs consistency loss, backward, gradient all-reduce (N>1), SGD step.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S, C, B_PER_GPU, ALPHA, LR = 448, 20, 8, 100.0, 0.01
+N_TOK, HEADS, HD, LAYERS = (S // 16) ** 2 + 1, 12, 64, 12
+METRIC, UNIT = "train_imgs_per_sec", "img/s"
+WORKLOAD = "train_acr.py VOC-shaped: ViT-B/16 448x448, two-view all-pairs consistency loss, B=8/GPU, bf16 operands"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_step_time(steps, warmup, batch=1):
+    """The reference algorithm on host cores: oracle port (torch-CPU fp32, all threads) of one training step on a
+    bounded sample (batch `batch` of the same 448x448 workload).  Returns (img/s, seconds per step, cores)."""
+    import torch
+    from oracle import acr_oracle as orc
+    from acr_wsss_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = orc.synth_state_dict(orc.vit_shapes(768, LAYERS, C))
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.SGD([p for p in params.values()], lr=LR, momentum=5e-4)
+    img, label = synth.images(batch, S), synth.labels(batch, C)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _, _ = orc.train_step_loss(params, img, label, ALPHA)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    v, sec, cores = cpu_reference_step_time(steps, warmup)
+    sample = f"{steps} timed steps (+{warmup} warm-up) of batch 1 of the same workload; fp32; torch CPU threads={cores}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference algorithm on host CPU cores (oracle port of train_acr.py:127-174)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from acr_wsss_b200 import ACR, Trainer, synth, ops, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    precision = args.precision
+    if precision == "bf16" and not _lib.lib().acr_device_is_sm100():
+        raise SystemExit("bench.py: bf16 fused path needs sm_100a")
+
+    torch.manual_seed(0)
+    model = ACR(C, "vitb", precision=precision).to(dev)
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    for n, p in model.named_parameters():   # parameters without gradient on the ACR path
+        if n.startswith(("pretrained.model.norm.", "pretrained.model.head.", "scratch.")) or n.endswith("bkg_token"):
+            p.requires_grad_(False)
+    trainer = Trainer(model, lr=LR, max_step=10 ** 6, alpha=ALPHA)
+    B = args.batch
+    img_h = synth.images(B, S, seed=rank).pin_memory()
+    lab_h = synth.labels(B, C, seed=rank).pin_memory()
+    img_d, lab_d = img_h.to(dev), lab_h.to(dev)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(max(args.warmup, 3)):
+        trainer.step(img_d, lab_d)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.PROFILE.reset(enabled=True)
+    ms_dev = timed(lambda: trainer.step(img_d, lab_d), args.steps)
+    prof = ops.PROFILE.summary()
+    ops.PROFILE.reset(enabled=False)
+    launches = prof["launches"]
+
+    def e2e_step():
+        loss = trainer.step(img_h, lab_h)      # H2D of the batch from pinned memory inside the step
+        return float(loss)                     # D2H read of the loss
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        pk = peaks()
+        imgs = B * world * args.steps
+        value = imgs / (ms_dev / 1e3)
+        e2e = imgs / (ms_e2e / 1e3)
+        # dominant kernel group: the fused attention backward (one C-ABI call per block and view)
+        dom = prof["kernels"].get("acr_attn_bwd_bf16" if precision == "bf16" else "acr_attn_bwd_f32", None)
+        flops_bwd = 8.0 * B * HEADS * N_TOK * N_TOK * HD            # algorithmic, recompute not counted
+        roof = None
+        if dom and dom["calls"]:
+            avg_ms = dom["ms"] / dom["calls"]
+            ach = flops_bwd / (avg_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": dom["name"], "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tflops_sustained"], "traffic": None, "avg_launch_ms": avg_ms, "calls_per_step": dom["calls"] / args.steps,
+                    "peak_source": pk["src"] + " (sustained bf16 cuBLAS)",
+                    "share_of_step": dom["ms"] / ms_dev, "per_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof["kernels"].items()}}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "tokens": N_TOK, "parallelism": f"dp{world}",
+                       "precision": precision, "l2": "inputs larger than L2: each step streams 2 x 237 MB attention stacks + gradients"},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(img_h.numel() * 4 + lab_h.numel() * 4) * world,
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, sec, cores = cpu_reference_step_time(2, 1)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": "2 timed steps (+1 warm-up) of batch 1 of the same workload, fp32 torch CPU (oracle port)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
