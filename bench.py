@@ -162,6 +162,12 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         trainer.step(img_d, lab_d)
+    if args.profile_range:      # one step between cudaProfilerStart/Stop for `ncu --profile-from-start off`
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        trainer.step(img_d, lab_d)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -223,6 +229,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true", help="wrap one extra step in cudaProfilerStart/Stop (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
