@@ -438,15 +438,16 @@ bwd_dq_convert_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restric
   *reinterpret_cast<uint4*>(d_qkv + (((size_t)b * N + n) * 3 + 0) * ((size_t)H * HD) + (size_t)h * HD + c * 8) = v;
 }
 
+constexpr int BWD_MAX_N = 4096;      // per-(b,h) row statistics are staged once in smem
 struct BwdSmem {
   uint8_t k[TILE_BYTES];
   uint8_t v[TILE_BYTES];
   uint8_t q[2][TILE_BYTES];
   uint8_t d_o[2][TILE_BYTES];
   uint8_t dst[2][TILE_BYTES];        // dS^T as the MN-major A operand of the dQ MMA: [q block of 64][kv row][64 q] swizzled
-  float lse2[2][BM];
-  float delta[2][BM];
-  uint64_t kv_full, qdo_full[2], qdo_empty[2], sdp_full, pds_full, dq_full, dq_read;
+  float lse2[BWD_MAX_N];             // log2-domain LSE of every query row of this (b,h); +inf past N
+  float delta[BWD_MAX_N];
+  uint64_t kv_full, qdo_full[2], qdo_empty[2], sdp_full, pds_full, dq_full;
   uint32_t tmem_base;
 };
 
@@ -469,7 +470,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     tc::mbar_init(&s.sdp_full, 1);
     tc::mbar_init(&s.pds_full, 256);
     tc::mbar_init(&s.dq_full, 1);
-    tc::mbar_init(&s.dq_read, 256);
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc<512>(&s.tmem_base);
@@ -495,35 +495,42 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       tc::mbar_wait(&s.kv_full, 0);
-      const uint32_t k_addr = tc::smem_u32(s.k), v_addr = tc::smem_u32(s.v);
-      for (int i = 0; i < ntiles; ++i) {
+      const uint32_t k_addr = tc::smem_u32(s.k), v_addr = tc::smem_u32(s.v), ds_addr = tc::smem_u32(s.dst[0]);
+      // S^T = K Q^T and dP^T = V dO^T of tile i (issued one tile ahead, under the softmax of the previous tile)
+      auto issue_scores = [&](int i) {
         const int st = i & 1;
         tc::mbar_wait(&s.qdo_full[st], (i >> 1) & 1);
-        if (i > 0) tc::mbar_wait(&s.dq_read, (i - 1) & 1);      // previous tile fully drained: S/dP/dQ regions reusable
         tc::tc_fence_after();
-        const uint32_t q_addr = tc::smem_u32(s.q[st]), do_addr = tc::smem_u32(s.d_o[st]), ds_addr = tc::smem_u32(s.dst[0]);
+        const uint32_t q_addr = tc::smem_u32(s.q[st]), do_addr = tc::smem_u32(s.d_o[st]);
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)      // S^T = K Q^T
+        for (int ks = 0; ks < HD / 16; ++ks)
           tc::mma_ss(tS, tc::smem_desc_sw128(k_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(q_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)      // dP^T = V dO^T
+        for (int ks = 0; ks < HD / 16; ++ks)
           tc::mma_ss(tDP, tc::smem_desc_sw128(v_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(do_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
         tc::tc_commit(&s.sdp_full);
+      };
+      issue_scores(0);
+      for (int i = 0; i < ntiles; ++i) {
+        const int st = i & 1;
+        const uint32_t q_addr = tc::smem_u32(s.q[st]), do_addr = tc::smem_u32(s.d_o[st]);
+        // pds_full(i): the softmax warps have consumed S^T/dP^T(i) and dQ(i-1), and published P^T (TMEM) and dS^T (smem)
         tc::mbar_wait(&s.pds_full, i & 1);
         tc::tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < BM / 16; ++ks)      // dV += P^T dO
           tc::mma_ts(tDV, tP + ks * 8, tc::smem_desc_sw128(do_addr + ks * 2048, 1024, 1024), IDESC_PV, (i > 0) || (ks > 0));
 #pragma unroll
-        for (int ks = 0; ks < BM / 16; ++ks)      // dK += dS^T Q   (A = the same dS^T smem tile read K-major: block ks/4, 32-byte k step)
+        for (int ks = 0; ks < BM / 16; ++ks)      // dK += dS^T Q   (A = the dS^T smem tile read K-major: block ks/4, 32-byte k step)
           tc::mma_ss(tDK, tc::smem_desc_sw128(ds_addr + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024),
                      tc::smem_desc_sw128(q_addr + ks * 2048, 1024, 1024), IDESC_PV, (i > 0) || (ks > 0));
 #pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks)      // dQ_i = dS K   (A = dS^T smem, MN-major, two 64-row M blocks 16 KB apart)
+        for (int ks = 0; ks < BN / 16; ++ks)      // dQ_i = dS K   (A = the dS^T smem tile read MN-major, two 64-row M blocks 16 KB apart)
           tc::mma_ss(tDQ, tc::smem_desc_sw128(ds_addr + ks * 2048, TILE_BYTES, 1024), tc::smem_desc_sw128(k_addr + ks * 2048, 1024, 1024),
                      IDESC_DQ, ks > 0);
         tc::tc_commit(&s.dq_full);
         tc::tc_commit(&s.qdo_empty[st]);
+        if (i + 1 < ntiles) issue_scores(i + 1);
       }
     }
   } else if (warp >= 4) {
@@ -535,16 +542,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const bool kv_ok = (kv0 + row) < N;
     const float invH = 1.f / (float)H;
     uint32_t rs[32], rd[32];
+    // stage the per-query-row statistics of this (b,h) once
+    for (int qi = tid_e; qi < ntiles * BM; qi += 256) {
+      const bool ok = qi < N;
+      s.lse2[qi] = ok ? __ldg(lse + ((size_t)b * H + h) * N + qi) * kLog2e : INFINITY;
+      s.delta[qi] = ok ? __ldg(delta + ((size_t)b * H + h) * N + qi) : 0.f;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     for (int i = 0; i < ntiles; ++i) {
-      const int q0 = i * BM, buf = i & 1;
-      // stage per-query-row statistics of this tile (double-buffered, one named barrier per iteration)
-      {
-        const int qi = q0 + (tid_e & 127);
-        const bool ok = qi < N;
-        if (tid_e < 128) s.lse2[buf][tid_e] = ok ? __ldg(lse + ((size_t)b * H + h) * N + qi) * kLog2e : INFINITY;
-        else s.delta[buf][tid_e - 128] = ok ? __ldg(delta + ((size_t)b * H + h) * N + qi) : 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int q0 = i * BM;
       tc::mbar_wait(&s.sdp_full, i & 1);
       tc::tc_fence_after();
 #pragma unroll
@@ -560,13 +566,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           for (int u = 0; u < 2; ++u) {
             const int col = half * 64 + c * 32 + 2 * e + u;       // query index inside the tile
             const int qi = q0 + col;
-            float p = exp2f(__uint_as_float(rs[2 * e + u]) * scale_log2 - s.lse2[buf][col]);
+            float p = exp2f(__uint_as_float(rs[2 * e + u]) * scale_log2 - s.lse2[qi]);
             if (!kv_ok) p = 0.f;
             float dp = __uint_as_float(rd[2 * e + u]);
             if (g_mean != nullptr && kv_ok && qi < N) dp = fmaf(__ldg(g_mean + (size_t)b * g_bs + (size_t)qi * N + kv0 + row), invH, dp);
             if (g_row0 != nullptr && qi == 0 && kv_ok) g_row0[((size_t)b * H + h) * N + kv0 + row] = dp;
             pv[u] = p;
-            dv[u] = p * (dp - s.delta[buf][col]);
+            dv[u] = p * (dp - s.delta[qi]);
           }
           pk[e] = tc::pack_bf16(pv[0], pv[1]);
           dk[e] = tc::pack_bf16(dv[0], dv[1]);
@@ -591,12 +597,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       tc::tc_fence_after();
       tc::tmem_ld32(tDQ + lane_off + half * 32, rs);
       tc::tmem_ld_wait();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&s.dq_read);
       if (q0 + row < N) {
         float* dqp = dq_acc + (((size_t)b * H + h) * N + q0 + row) * HD + half * 32;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) atomicAdd(dqp + e, __uint_as_float(rs[e]));
+        for (int e = 0; e < 8; ++e)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + 4 * e), "f"(__uint_as_float(rs[4 * e])),
+                       "f"(__uint_as_float(rs[4 * e + 1])), "f"(__uint_as_float(rs[4 * e + 2])), "f"(__uint_as_float(rs[4 * e + 3]))
+                       : "memory");
       }
     }
     // epilogue: dV, dK rows of this key tile (all MMAs are complete: the last dq_full covered them)
@@ -647,6 +654,7 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
   ACR_REQUIRE(B > 0 && N > 0 && H > 0, ACR_E_INVAL, "acr_attn_bwd_bf16: bad shape");
   ACR_REQUIRE(D == HD, ACR_E_INVAL, "acr_attn_bwd_bf16: head dim %d unsupported (64 only)", D);
   ACR_REQUIRE(B <= 65535 && H <= 65535, ACR_E_INVAL, "acr_attn_bwd_bf16: grid too large");
+  ACR_REQUIRE(((N + BM - 1) / BM) * BM <= BWD_MAX_N, ACR_E_INVAL, "acr_attn_bwd_bf16: N=%d > %d unsupported", N, BWD_MAX_N);
   ACR_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ((uintptr_t)d_qkv & 15) == 0,
               ACR_E_ALIGN, "acr_attn_bwd_bf16: tensors must be 16-byte aligned");
   ACR_REQUIRE(((uintptr_t)workspace & 255) == 0, ACR_E_ALIGN, "acr_attn_bwd_bf16: workspace must be 256-byte aligned");
