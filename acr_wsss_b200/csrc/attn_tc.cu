@@ -34,7 +34,9 @@ struct FwdSmem {
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(256)
+// 2 CTAs per SM: 256 threads x 128 registers at launch; the control warpgroup (TMA / MMA issue / TMEM alloc) hands
+// its registers to the softmax warpgroup (setmaxnreg), so one CTA's softmax overlaps the other's MMAs.
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                 int N, int H, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
@@ -60,6 +62,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
   const uint32_t tS = tmem, tP = tmem + 128, tO = tmem + 192;
 
   if (warp == 0) {
+    tc::reg_dealloc<40>();
     if (lane == 0) {
       tc::mbar_arrive_expect_tx(&s.q_full, TILE_BYTES);
       tc::tma_load_4d(s.q, &tmap_qkv, &s.q_full, 0, h, q0, b);
@@ -72,6 +75,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
       }
     }
   } else if (warp == 1) {
+    tc::reg_dealloc<40>();
     if (lane == 0) {
       tc::mbar_wait(&s.q_full, 0);
       const uint32_t q_addr = tc::smem_u32(s.q);
@@ -93,7 +97,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
         tc::tc_commit(&s.kv_empty[st]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    tc::reg_dealloc<40>();
+  } else {
+    tc::reg_alloc<216>();
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     float m = -INFINITY, l = 0.f;
