@@ -21,7 +21,7 @@ SIGNATURES = {
                                   c_void_p, c_longlong, c_void_p, c_void_p]),
     "acr_attn_bwd_bf16_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
     "acr_attn_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                                  c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                  c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "acr_attn_fwd_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                  c_void_p, c_longlong, c_void_p]),
     "acr_attn_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,

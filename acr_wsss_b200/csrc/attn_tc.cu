@@ -103,7 +103,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
     tc::reg_alloc<216>();
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    float m = -INFINITY, l = 0.f;
+    float m = -INFINITY, l = 0.f;      // m: running row max of the RAW scores (scale > 0, so max commutes with scaling)
     float o[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) o[i] = 0.f;
@@ -118,14 +118,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
       for (int c = 0; c < 4; ++c) {
         tc::tmem_ld32(tS + lane_off + c * 32, r);
         tc::tmem_ld_wait();
+        if (!tail) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(r[i]) * scale_log2;
-          if (tail && col0 + c * 32 + i >= N) t = -INFINITY;
-          mx = fmaxf(mx, t);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + c * 32 + i < N) mx = fmaxf(mx, __uint_as_float(r[i]));
         }
       }
-      const float alpha = exp2f(m - mx);
+      const float ms = mx * scale_log2;
+      const float alpha = tc::fast_exp2((m - mx) * scale_log2);
       float rowsum = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -134,11 +137,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float t0 = __uint_as_float(r[2 * i]) * scale_log2 - mx;
-          float t1 = __uint_as_float(r[2 * i + 1]) * scale_log2 - mx;
-          if (tail && col0 + c * 32 + 2 * i >= N) t0 = -INFINITY;
-          if (tail && col0 + c * 32 + 2 * i + 1 >= N) t1 = -INFINITY;
-          const float p0 = exp2f(t0), p1 = exp2f(t1);
+          float p0 = tc::fast_exp2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -ms));
+          float p1 = tc::fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -ms));
+          if (tail) {
+            if (col0 + c * 32 + 2 * i >= N) p0 = 0.f;
+            if (col0 + c * 32 + 2 * i + 1 >= N) p1 = 0.f;
+          }
           rowsum += p0 + p1;
           pk[i] = tc::pack_bf16(p0, p1);
         }
@@ -156,7 +160,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
         tc::tmem_ld32(tO + lane_off + c * 32, r);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(r[i]);
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
       }
     }
     if (q0 + row < N) {
@@ -171,7 +175,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
         v.w = tc::pack_bf16(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
         reinterpret_cast<uint4*>(dst)[c] = v;
       }
-      lse[((size_t)b * H + h) * N + q0 + row] = (m + log2f(l)) * kLn2;
+      lse[((size_t)b * H + h) * N + q0 + row] = (m * scale_log2 + log2f(l)) * kLn2;
     }
   }
   tc::tc_fence_before();
@@ -184,8 +188,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
 
 // ---------------------------------------------------------------------------------------------
 constexpr int MEAN_STAGES = 3;
+constexpr int MEAN_MAX_H = 32;
 struct MeanSmem {
   uint8_t qk[MEAN_STAGES][2][TILE_BYTES];      // [stage][0=Q,1=K]; reused as the fp32 staging tile at the end
+  float lse2[MEAN_MAX_H][BM];
   uint64_t full[MEAN_STAGES], empty[MEAN_STAGES], t_full[2], t_empty[2];
   uint32_t tmem_base;
 };
@@ -197,7 +203,7 @@ static_assert(sizeof(float) * BM * STAGE_LD <= sizeof(uint8_t) * MEAN_STAGES * 2
 template <int MODE>
 __global__ void __launch_bounds__(384)
 attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __restrict__ lse, float* __restrict__ mean,
-                 long long mean_bs, float* __restrict__ p_row0, int N, int H, float scale_log2) {
+                 long long mean_bs, long long mean_ld, float* __restrict__ p_row0, int N, int H, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   MeanSmem& s = *reinterpret_cast<MeanSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -254,33 +260,49 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
     } else {
       // G tile of this thread's row, pre-scaled by 1/H; zero outside the map
-      const float* grow = mean + (size_t)b * mean_bs + (size_t)(q0 + row) * N + kv0 + half * 64;
+      const float* grow = mean + (size_t)b * mean_bs + (size_t)(q0 + row) * mean_ld + kv0 + half * 64;
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = (row_ok && kv0 + half * 64 + i < N) ? __ldg(grow + i) * invH : 0.f;
     }
+    // log2-domain LSE of this tile's rows for every head, staged once: s.lse2[h][row] (+inf for rows past N -> P = 0)
+    for (int e = we * 32 + lane; e < H * BM; e += 256) {
+      const int hh = e / BM, rr = e % BM;
+      s.lse2[hh][rr] = (q0 + rr < N) ? __ldg(lse + ((size_t)b * H + hh) * N + q0 + rr) * kLog2e : INFINITY;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const bool tail = (kv0 + BN > N);
+    const bool row0_warp = (MODE == 0) && (p_row0 != nullptr) && (q0 == 0) && ((warp & 3) == 0);
     uint32_t r[32];
     for (int h = 0; h < H; ++h) {
       const int ab = h & 1;
-      const float lse2 = row_ok ? __ldg(lse + ((size_t)b * H + h) * N + q0 + row) * kLog2e : 0.f;
+      const float lse2 = s.lse2[h][row];
       tc::mbar_wait(&s.t_full[ab], (h >> 1) & 1);
       tc::tc_fence_after();
-      const bool want_row0 = (MODE == 0) && (p_row0 != nullptr) && (q0 + row == 0);
       float part = 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         tc::tmem_ld32(tmem + ab * 128 + lane_off + half * 64 + c * 32, r);
         tc::tmem_ld_wait();
+        const int colbase = kv0 + half * 64 + c * 32;
+        if (!tail) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int col = kv0 + half * 64 + c * 32 + i;
-          float p = exp2f(__uint_as_float(r[i]) * scale_log2 - lse2);
-          if (col >= N) p = 0.f;
-          if (MODE == 0) {
-            acc[c * 32 + i] += p;
-            if (want_row0 && col < N) p_row0[((size_t)b * H + h) * N + col] = p;
-          } else {
-            part = fmaf(p, acc[c * 32 + i], part);
+          for (int i = 0; i < 32; ++i) {
+            const float p = tc::fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -lse2));
+            if (MODE == 0) { acc[c * 32 + i] += p; r[i] = __float_as_uint(p); } else part = fmaf(p, acc[c * 32 + i], part);
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float p = tc::fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -lse2));
+            if (colbase + i >= N) p = 0.f;
+            if (MODE == 0) { acc[c * 32 + i] += p; r[i] = __float_as_uint(p); } else part = fmaf(p, acc[c * 32 + i], part);
+          }
+        }
+        if (row0_warp && lane == 0) {       // cls-token row of this head's P (GETAM input)
+          float* dst0 = p_row0 + ((size_t)b * H + h) * N + colbase;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (colbase + i < N) dst0[i] = __uint_as_float(r[i]);
         }
       }
       tc::tc_fence_before();
@@ -352,7 +374,7 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
   ACR_REQUIRE(qkv && out && lse, ACR_E_INVAL, "acr_attn_fwd_bf16: null pointer");
   ACR_REQUIRE(B > 0 && N > 0 && H > 0, ACR_E_INVAL, "acr_attn_fwd_bf16: bad shape");
   ACR_REQUIRE(D == HD, ACR_E_INVAL, "acr_attn_fwd_bf16: head dim %d unsupported (64 only)", D);
-  ACR_REQUIRE(B <= 65535 && H <= 65535, ACR_E_INVAL, "acr_attn_fwd_bf16: grid too large");
+  ACR_REQUIRE(B <= 65535 && H <= MEAN_MAX_H, ACR_E_INVAL, "acr_attn_fwd_bf16: B <= 65535 and H <= %d required", MEAN_MAX_H);
   ACR_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, ACR_E_ALIGN, "acr_attn_fwd_bf16: qkv/out must be 16-byte aligned");
   ACR_REQUIRE(p_row0 == nullptr || attn_mean != nullptr, ACR_E_INVAL, "acr_attn_fwd_bf16: p_row0 needs attn_mean");
   ACR_REQUIRE(acr_device_is_sm100(), ACR_E_NOSM100, "acr_attn_fwd_bf16: needs an sm_100 device");
@@ -380,7 +402,7 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
       attr_set = true;
     }
     dim3 grid(kt, qt, B);
-    attn_mean_kernel<0><<<grid, 384, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, p_row0, N, H, scale_log2);
+    attn_mean_kernel<0><<<grid, 384, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, (long long)N, p_row0, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel")) return e;
   }
   return 0;
@@ -445,23 +467,28 @@ bwd_dq_convert_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restric
   *reinterpret_cast<uint4*>(d_qkv + (((size_t)b * N + n) * 3 + 0) * ((size_t)H * HD) + (size_t)h * HD + c * 8) = v;
 }
 
-constexpr int BWD_MAX_N = 4096;      // per-(b,h) row statistics are staged once in smem
 struct BwdSmem {
   uint8_t k[TILE_BYTES];
   uint8_t v[TILE_BYTES];
   uint8_t q[2][TILE_BYTES];
   uint8_t d_o[2][TILE_BYTES];
-  uint8_t dst[2][TILE_BYTES];        // dS^T as the MN-major A operand of the dQ MMA: [q block of 64][kv row][64 q] swizzled
-  float lse2[BWD_MAX_N];             // log2-domain LSE of every query row of this (b,h); +inf past N
-  float delta[BWD_MAX_N];
+  uint8_t p[2][2][TILE_BYTES];       // [buffer][kv block of 64][q row][64 kv] bf16 P tile, SWIZZLE_128B rows (one row per thread)
+  uint8_t ds[2][2][TILE_BYTES];      // dS tile, same layout: read MN-major (A = dS^T / P^T) and K-major (A = dS)
   uint64_t kv_full, qdo_full[2], qdo_empty[2], sdp_full, pds_full, dq_full;
   uint32_t tmem_base;
 };
 
+// One CTA per (key tile j, head, image); K_j, V_j stationary, loop over query tiles i.  Rows (TMEM lanes) = queries:
+//   S = Q_i K_j^T, dP = dO_i V_j^T  (SS MMAs)  ->  per thread: one query row, 64 key columns:
+//   P = exp2(S*c - lse_row), dP += G[row, cols]/H (row-contiguous loads), dS = P*(dP - delta_row)
+//   P, dS -> bf16 rows of two swizzled smem tiles, then
+//   dV += P^T dO (A = P tile read MN-major), dK += dS^T Q (A = dS tile MN-major), dQ_i = dS K_j (A = dS tile K-major).
+// MMA issue order: the scores of tile i+1 are issued BEFORE the gradient MMAs of tile i, so the softmax warps of tile
+// i+1 only wait for 2 of the 5 MMAs; dQ tiles are reduced over key tiles with vectorised fp32 reductions.
 __global__ void __launch_bounds__(384)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const float* __restrict__ lse, const float* __restrict__ delta, const float* __restrict__ g_mean, long long g_bs,
-                __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ dq_acc, float* __restrict__ g_row0,
+                long long g_ld, __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ dq_acc, float* __restrict__ g_row0,
                 int N, int H, float scale, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& s = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -484,7 +511,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = s.tmem_base;
-  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384, tP = tmem + 448;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -502,68 +529,101 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       tc::mbar_wait(&s.kv_full, 0);
-      const uint32_t k_addr = tc::smem_u32(s.k), v_addr = tc::smem_u32(s.v), ds_addr = tc::smem_u32(s.dst[0]);
-      // S^T = K Q^T and dP^T = V dO^T of tile i (issued one tile ahead, under the softmax of the previous tile)
-      auto issue_scores = [&](int i) {
+      const uint32_t k_addr = tc::smem_u32(s.k), v_addr = tc::smem_u32(s.v);
+      auto issue_scores = [&](int i) {      // S = Q K^T, dP = dO V^T
         const int st = i & 1;
         tc::mbar_wait(&s.qdo_full[st], (i >> 1) & 1);
         tc::tc_fence_after();
         const uint32_t q_addr = tc::smem_u32(s.q[st]), do_addr = tc::smem_u32(s.d_o[st]);
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks)
-          tc::mma_ss(tS, tc::smem_desc_sw128(k_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(q_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
+          tc::mma_ss(tS, tc::smem_desc_sw128(q_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(k_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks)
-          tc::mma_ss(tDP, tc::smem_desc_sw128(v_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(do_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
+          tc::mma_ss(tDP, tc::smem_desc_sw128(do_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(v_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
         tc::tc_commit(&s.sdp_full);
       };
       issue_scores(0);
       for (int i = 0; i < ntiles; ++i) {
         const int st = i & 1;
         const uint32_t q_addr = tc::smem_u32(s.q[st]), do_addr = tc::smem_u32(s.d_o[st]);
-        // pds_full(i): the softmax warps have consumed S^T/dP^T(i) and dQ(i-1), and published P^T (TMEM) and dS^T (smem)
+        const uint32_t p_addr = tc::smem_u32(s.p[st][0]), ds_addr = tc::smem_u32(s.ds[st][0]);
+        // pds_full(i): softmax warps consumed S/dP(i) and dQ(i-1), and published the P / dS smem tiles of buffer i&1
         tc::mbar_wait(&s.pds_full, i & 1);
+        if (i + 1 < ntiles) issue_scores(i + 1);       // scores of the next tile first: shortens the softmax critical path
         tc::tc_fence_after();
 #pragma unroll
-        for (int ks = 0; ks < BM / 16; ++ks)      // dV += P^T dO
-          tc::mma_ts(tDV, tP + ks * 8, tc::smem_desc_sw128(do_addr + ks * 2048, 1024, 1024), IDESC_PV, (i > 0) || (ks > 0));
+        for (int ks = 0; ks < BM / 16; ++ks)      // dV += P^T dO   (A = P tile MN-major: M = kv, K = q; two 64-wide M blocks 16 KB apart)
+          tc::mma_ss(tDV, tc::smem_desc_sw128(p_addr + ks * 2048, TILE_BYTES, 1024), tc::smem_desc_sw128(do_addr + ks * 2048, 1024, 1024),
+                     IDESC_DQ, (i > 0) || (ks > 0));
 #pragma unroll
-        for (int ks = 0; ks < BM / 16; ++ks)      // dK += dS^T Q   (A = the dS^T smem tile read K-major: block ks/4, 32-byte k step)
-          tc::mma_ss(tDK, tc::smem_desc_sw128(ds_addr + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024),
-                     tc::smem_desc_sw128(q_addr + ks * 2048, 1024, 1024), IDESC_PV, (i > 0) || (ks > 0));
+        for (int ks = 0; ks < BM / 16; ++ks)      // dK += dS^T Q
+          tc::mma_ss(tDK, tc::smem_desc_sw128(ds_addr + ks * 2048, TILE_BYTES, 1024), tc::smem_desc_sw128(q_addr + ks * 2048, 1024, 1024),
+                     IDESC_DQ, (i > 0) || (ks > 0));
 #pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks)      // dQ_i = dS K   (A = the dS^T smem tile read MN-major, two 64-row M blocks 16 KB apart)
-          tc::mma_ss(tDQ, tc::smem_desc_sw128(ds_addr + ks * 2048, TILE_BYTES, 1024), tc::smem_desc_sw128(k_addr + ks * 2048, 1024, 1024),
-                     IDESC_DQ, ks > 0);
+        for (int ks = 0; ks < BN / 16; ++ks)      // dQ_i = dS K   (A = dS tile K-major: block ks/4, 32-byte k step; B = K MN-major)
+          tc::mma_ss(tDQ, tc::smem_desc_sw128(ds_addr + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024),
+                     tc::smem_desc_sw128(k_addr + ks * 2048, 1024, 1024), IDESC_PV, ks > 0);
         tc::tc_commit(&s.dq_full);
         tc::tc_commit(&s.qdo_empty[st]);
-        if (i + 1 < ntiles) issue_scores(i + 1);
       }
     }
   } else if (warp >= 4) {
     const int we = warp - 4;
-    const int row = (warp & 3) * 32 + lane;          // key row inside the tile (TMEM lane)
-    const int half = we >> 2;                        // which 64-column (query) half
-    const int tid_e = we * 32 + lane;                // 0..255
+    const int row = (warp & 3) * 32 + lane;          // query row inside the tile (TMEM lane)
+    const int half = we >> 2;                        // which 64-column (key) half
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const bool kv_ok = (kv0 + row) < N;
     const float invH = 1.f / (float)H;
+    const int colbase = kv0 + half * 64;
+    const bool tail = (kv0 + BN > N);
+    const bool g_vec = (g_mean != nullptr) && ((g_ld & 3) == 0) && ((g_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(g_mean) & 15) == 0);
+    const float* stat_l = lse + ((size_t)b * H + h) * N;
+    const float* stat_d = delta + ((size_t)b * H + h) * N;
     uint32_t rs[32], rd[32];
-    // stage the per-query-row statistics of this (b,h) once
-    for (int qi = tid_e; qi < ntiles * BM; qi += 256) {
-      const bool ok = qi < N;
-      s.lse2[qi] = ok ? __ldg(lse + ((size_t)b * H + h) * N + qi) * kLog2e : INFINITY;
-      s.delta[qi] = ok ? __ldg(delta + ((size_t)b * H + h) * N + qi) : 0.f;
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // rows = queries (lanes), 64 columns = d; this thread reduces its 32 columns of query row q into the fp32 accumulator
+    auto reduce_dq = [&](int q) {
+      float* dqp = dq_acc + (((size_t)b * H + h) * N + q) * HD + half * 32;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + 4 * e), "f"(__uint_as_float(rs[4 * e])),
+                     "f"(__uint_as_float(rs[4 * e + 1])), "f"(__uint_as_float(rs[4 * e + 2])), "f"(__uint_as_float(rs[4 * e + 3]))
+                     : "memory");
+    };
+    float lse2_n = (row < N) ? __ldg(stat_l + row) * kLog2e : INFINITY;
+    float dlt_n = (row < N) ? __ldg(stat_d + row) : 0.f;
     for (int i = 0; i < ntiles; ++i) {
       const int q0 = i * BM;
+      const int qi = q0 + row;
+      const bool q_ok = qi < N;
+      const float lse2 = lse2_n, dlt = dlt_n;
+      if (i + 1 < ntiles) {                          // row statistics of the next tile, off the critical path
+        const int qn = qi + BM;
+        lse2_n = (qn < N) ? __ldg(stat_l + qn) * kLog2e : INFINITY;
+        dlt_n = (qn < N) ? __ldg(stat_d + qn) : 0.f;
+      }
+      const float* grow = (g_mean != nullptr && q_ok) ? g_mean + (size_t)b * g_bs + (size_t)qi * g_ld + colbase : nullptr;
       tc::mbar_wait(&s.sdp_full, i & 1);
       tc::tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         tc::tmem_ld32(tS + lane_off + half * 64 + c * 32, rs);
         tc::tmem_ld32(tDP + lane_off + half * 64 + c * 32, rd);
+        float g[32];
+        if (grow != nullptr) {
+          if (g_vec && !tail) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(grow + c * 32) + e);
+              g[4 * e] = t.x; g[4 * e + 1] = t.y; g[4 * e + 2] = t.z; g[4 * e + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) g[e] = (colbase + c * 32 + e < N) ? __ldg(grow + c * 32 + e) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) g[e] = 0.f;
+        }
         tc::tmem_ld_wait();
         uint32_t pk[16], dk[16];
 #pragma unroll
@@ -571,49 +631,53 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           float pv[2], dv[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int col = half * 64 + c * 32 + 2 * e + u;       // query index inside the tile
-            const int qi = q0 + col;
-            float p = exp2f(__uint_as_float(rs[2 * e + u]) * scale_log2 - s.lse2[qi]);
-            if (!kv_ok) p = 0.f;
-            float dp = __uint_as_float(rd[2 * e + u]);
-            if (g_mean != nullptr && kv_ok && qi < N) dp = fmaf(__ldg(g_mean + (size_t)b * g_bs + (size_t)qi * N + kv0 + row), invH, dp);
-            if (g_row0 != nullptr && qi == 0 && kv_ok) g_row0[((size_t)b * H + h) * N + kv0 + row] = dp;
+            const int cc = c * 32 + 2 * e + u;
+            float p = tc::fast_exp2(fmaf(__uint_as_float(rs[2 * e + u]), scale_log2, -lse2));
+            if (tail && colbase + cc >= N) p = 0.f;
+            const float dp = fmaf(g[2 * e + u], invH, __uint_as_float(rd[2 * e + u]));
+            rd[2 * e + u] = __float_as_uint(dp);
             pv[u] = p;
-            dv[u] = p * (dp - s.delta[qi]);
+            dv[u] = p * (dp - dlt);
           }
           pk[e] = tc::pack_bf16(pv[0], pv[1]);
           dk[e] = tc::pack_bf16(dv[0], dv[1]);
         }
-        tc::tmem_st16(tP + lane_off + half * 32 + c * 16, pk);       // P^T (bf16): the A operand of the dV MMA
-        // dS^T row -> smem, SWIZZLE_128B: block `half` (64 queries), row `row`, 16-byte chunk cc at position cc ^ (row & 7);
-        // read K-major by the dK MMA (A[kv][q]) and MN-major by the dQ MMA (A[q][kv])
-        uint8_t* base = s.dst[half] + row * 128;
+        if (g_row0 != nullptr && qi == 0) {             // row 0 of dP_h: what the reference's hook keeps for GETAM
+          float* dst0 = g_row0 + ((size_t)b * H + h) * N + colbase + c * 32;
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (colbase + c * 32 + e < N) dst0[e] = __uint_as_float(rd[e]);
+        }
+        // this thread's row of block `half`: 16-byte chunk j at position j ^ (row & 7)
+        uint8_t* prow = s.p[i & 1][half] + row * 128;
+        uint8_t* drow = s.ds[i & 1][half] + row * 128;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          const int chunk = c * 4 + cc;
-          uint4 v = make_uint4(dk[cc * 4 + 0], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]);
-          *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = v;
+          const int pos = ((c * 4 + cc) ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + pos) = make_uint4(pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
+          *reinterpret_cast<uint4*>(drow + pos) = make_uint4(dk[cc * 4 + 0], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]);
         }
       }
-      tc::tmem_st_wait();
       tc::fence_proxy_async_smem();
+      // dQ of the PREVIOUS query tile (its MMAs ran under this tile's softmax) must leave TMEM before pds_full(i)
+      // lets the MMA warp overwrite tDQ; the global reductions themselves are issued after the arrive.
+      if (i > 0) {
+        tc::mbar_wait(&s.dq_full, (i - 1) & 1);
+        tc::tc_fence_after();
+        tc::tmem_ld32(tDQ + lane_off + half * 32, rs);
+        tc::tmem_ld_wait();
+      }
       tc::tc_fence_before();
       tc::mbar_arrive(&s.pds_full);
-      // dQ tile: rows = queries (lanes), 64 columns = d; this thread reduces 32 of them into the fp32 accumulator
-      tc::mbar_wait(&s.dq_full, i & 1);
-      tc::tc_fence_after();
-      tc::tmem_ld32(tDQ + lane_off + half * 32, rs);
-      tc::tmem_ld_wait();
-      if (q0 + row < N) {
-        float* dqp = dq_acc + (((size_t)b * H + h) * N + q0 + row) * HD + half * 32;
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + 4 * e), "f"(__uint_as_float(rs[4 * e])),
-                       "f"(__uint_as_float(rs[4 * e + 1])), "f"(__uint_as_float(rs[4 * e + 2])), "f"(__uint_as_float(rs[4 * e + 3]))
-                       : "memory");
-      }
+      if (i > 0 && qi - BM < N) reduce_dq(qi - BM);
     }
-    // epilogue: dV, dK rows of this key tile (all MMAs are complete: the last dq_full covered them)
+    tc::mbar_wait(&s.dq_full, (ntiles - 1) & 1);
+    tc::tc_fence_after();
+    tc::tmem_ld32(tDQ + lane_off + half * 32, rs);
+    tc::tmem_ld_wait();
+    if ((ntiles - 1) * BM + row < N) reduce_dq((ntiles - 1) * BM + row);
+    // epilogue: dV, dK rows (lanes = keys) of this key tile; all MMAs are complete (the last dq_full covered them)
+    const bool kv_ok = (kv0 + row) < N;
     tc::tmem_ld32(tDV + lane_off + half * 32, rs);      // warp-collective: outside the per-row validity branch
     tc::tmem_ld32(tDK + lane_off + half * 32, rd);
     tc::tmem_ld_wait();
@@ -655,13 +719,13 @@ extern "C" size_t acr_attn_bwd_bf16_workspace(int B, int N, int H, int D) {
 
 extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* lse, const void* d_out,
                                  int B, int N, int H, int D, float scale,
-                                 const float* g_mean, long long g_batch_stride,
+                                 const float* g_mean, long long g_batch_stride, long long g_row_stride,
                                  void* d_qkv, float* g_row0, void* workspace, size_t workspace_bytes, void* stream) {
   ACR_REQUIRE(qkv && out && lse && d_out && d_qkv && workspace, ACR_E_INVAL, "acr_attn_bwd_bf16: null pointer");
   ACR_REQUIRE(B > 0 && N > 0 && H > 0, ACR_E_INVAL, "acr_attn_bwd_bf16: bad shape");
   ACR_REQUIRE(D == HD, ACR_E_INVAL, "acr_attn_bwd_bf16: head dim %d unsupported (64 only)", D);
-  ACR_REQUIRE(B <= 65535 && H <= 65535, ACR_E_INVAL, "acr_attn_bwd_bf16: grid too large");
-  ACR_REQUIRE(((N + BM - 1) / BM) * BM <= BWD_MAX_N, ACR_E_INVAL, "acr_attn_bwd_bf16: N=%d > %d unsupported", N, BWD_MAX_N);
+  ACR_REQUIRE(B <= 65535 && H <= MEAN_MAX_H, ACR_E_INVAL, "acr_attn_bwd_bf16: B <= 65535 and H <= %d required", MEAN_MAX_H);
+  ACR_REQUIRE(g_mean == nullptr || g_row_stride >= N, ACR_E_INVAL, "acr_attn_bwd_bf16: g_row_stride < N");
   ACR_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ((uintptr_t)d_qkv & 15) == 0,
               ACR_E_ALIGN, "acr_attn_bwd_bf16: tensors must be 16-byte aligned");
   ACR_REQUIRE(((uintptr_t)workspace & 255) == 0, ACR_E_ALIGN, "acr_attn_bwd_bf16: workspace must be 256-byte aligned");
@@ -688,7 +752,7 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
       attr_set = true;
     }
     dim3 grid(kt, qt, B);
-    attn_mean_kernel<1><<<grid, 384, smem, st>>>(tmap_qkv, lse, const_cast<float*>(g_mean), g_batch_stride, delta, N, H, scale_log2);
+    attn_mean_kernel<1><<<grid, 384, smem, st>>>(tmap_qkv, lse, const_cast<float*>(g_mean), g_batch_stride, g_row_stride, delta, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel<1>")) return e;
   }
   {
@@ -699,7 +763,7 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
       attr_set = true;
     }
     dim3 grid(kt, H, B);
-    attn_bwd_kernel<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, lse, delta, g_mean, g_batch_stride, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
+    attn_bwd_kernel<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, lse, delta, g_mean, g_batch_stride, g_row_stride, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
                                              N, H, scale, scale_log2);
     if (int e = acr::check_launch("attn_bwd_kernel")) return e;
   }

@@ -143,6 +143,13 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N, int a_mn, in
          ((uint32_t)(M >> 4) << 24);
 }
 
+// 2^x on the SFU: one MUFU.EX2 (exp2f() adds range fix-ups the softmax does not need; -inf -> 0 holds)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);

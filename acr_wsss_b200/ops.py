@@ -71,10 +71,17 @@ def _alias(t):
 
 
 def _dense_map(t):
-    """A [B,N,N] map whose rows are dense; returns (tensor, batch_stride_in_elements)."""
+    """A [B,N,N] map with dense rows; returns (tensor, batch_stride_in_elements)."""
     if t.stride(-1) != 1 or t.stride(-2) != t.shape[-1]:
         t = t.contiguous()
     return t, t.stride(0)
+
+
+def _strided_map(t):
+    """A [B,N,N] map with unit column stride (rows may be padded); returns (tensor, batch stride, row stride)."""
+    if t.stride(-1) != 1:
+        t = t.contiguous()
+    return t, t.stride(0), t.stride(1)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -158,16 +165,16 @@ class _AttnCoreBF16(torch.autograd.Function):
         B, N, H, D, scale = ctx.dims
         d_out = (torch.zeros(B, N, H * D, device=qkv.device, dtype=torch.bfloat16) if d_out is None
                  else d_out.contiguous().to(torch.bfloat16))
-        gs = 0
+        gs, gl = 0, 0
         if g_mean is not None:
-            g_mean, gs = _dense_map(g_mean.float())
+            g_mean, gs, gl = _strided_map(g_mean.float())
         d_qkv = torch.empty_like(qkv)
         want_row0 = ctx.state is not None and ctx.state.get("capture_grad", True)
         g_row0 = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32) if want_row0 else None
         wsb = _lib.lib().acr_attn_bwd_bf16_workspace(B, N, H, D)
         ws = torch.empty(wsb, device=qkv.device, dtype=torch.uint8)
         _call("acr_attn_bwd_bf16", 4, _p(qkv), _p(out), _p(lse), _p(d_out), B, N, H, D, scale,
-                                                _p(g_mean), gs, _p(d_qkv), _p(g_row0), _p(ws), wsb, _stream())
+              _p(g_mean), gs, gl, _p(d_qkv), _p(g_row0), _p(ws), wsb, _stream())
         if want_row0:
             ctx.state["grad_row0"] = g_row0
         return d_qkv, None, None, None, None

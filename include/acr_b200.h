@@ -56,14 +56,15 @@ int acr_attn_fwd_bf16(const void* qkv_bf16, int B, int N, int H, int D, float sc
 
 /* Backward of the above with the dense affinity-gradient term:
  *   dP_h = dO_h V_h^T + g_mean / H ;  dS_h = P_h * (dP_h - rowsum(P_h * dP_h)) ; dQ,dK,dV as usual.
- * g_mean (nullable) = dLoss/dA-bar for this block, image b at g_mean + b*g_batch_stride, rows dense.
+ * g_mean (nullable) = dLoss/dA-bar for this block: element (b,i,j) at g_mean + b*g_batch_stride + i*g_row_stride + j
+ * (a row stride that is a multiple of 4 with a 16-byte aligned base enables 128-bit loads).
  * d_qkv_bf16 has the layout of qkv.  g_row0 (nullable, [B,H,N] fp32) receives row 0 of dP_h, which is
  * what the reference's save_attn_gradients hook keeps and getam consumes (DPT/ACR.py:182-213).
  * workspace: acr_attn_bwd_bf16_workspace() bytes, 256-byte aligned. */
 size_t acr_attn_bwd_bf16_workspace(int B, int N, int H, int D);
 int acr_attn_bwd_bf16(const void* qkv_bf16, const void* out_bf16, const float* lse,
                       const void* d_out_bf16, int B, int N, int H, int D, float scale,
-                      const float* g_mean, long long g_batch_stride,
+                      const float* g_mean, long long g_batch_stride, long long g_row_stride,
                       void* d_qkv_bf16, float* g_row0,
                       void* workspace, size_t workspace_bytes, void* stream);
 

@@ -10,7 +10,8 @@ dev = torch.device("cuda:0")
 g = torch.Generator(device="cuda").manual_seed(0)
 qkv = (torch.randn(B, N, 3 * H * D, device=dev, generator=g) * 1.5).to(torch.bfloat16)
 d_out = torch.randn(B, N, H * D, device=dev, generator=g).to(torch.bfloat16)
-G = torch.randn(B, N, N, device=dev, generator=g) * 0.01
+NP = (N + 3) // 4 * 4
+G = (torch.randn(B, N, NP, device=dev, generator=g) * 0.01)[:, :, :N]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 L = _lib.lib()
 p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
@@ -37,7 +38,7 @@ def fwd(with_mean=True):
     rc = L.acr_attn_fwd_bf16(p(qkv), B, N, H, D, D ** -0.5, p(out), p(lse), p(mean) if with_mean else None, N * N, p(row0) if with_mean else None, st)
     assert rc == 0, _lib.last_error()
 def bwd(with_g=True):
-    rc = L.acr_attn_bwd_bf16(p(qkv), p(out), p(lse), p(d_out), B, N, H, D, D ** -0.5, p(G) if with_g else None, N * N, p(d_qkv), None, p(ws), wsb, st)
+    rc = L.acr_attn_bwd_bf16(p(qkv), p(out), p(lse), p(d_out), B, N, H, D, D ** -0.5, p(G) if with_g else None, G.stride(0), G.stride(1), p(d_qkv), None, p(ws), wsb, st)
     assert rc == 0, _lib.last_error()
 
 f_core = 4.0 * B * H * N * N * D
