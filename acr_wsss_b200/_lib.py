@@ -21,14 +21,16 @@ SIGNATURES = {
                                   c_void_p, c_longlong, c_void_p, c_void_p]),
     "acr_attn_bwd_bf16_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
     "acr_attn_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                                  c_void_p, c_longlong, c_longlong, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                  c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_longlong, c_float, c_float, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "acr_attn_fwd_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                  c_void_p, c_longlong, c_void_p]),
     "acr_attn_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                  c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
     "acr_consistency_workspace": (c_size_t, [c_int, c_int, c_int]),
     "acr_consistency_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
-                                        c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                        c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong,
+                                        c_void_p, c_size_t, c_void_p]),
     "acr_getam_row0": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p, c_void_p]),
     "acr_affinity_sum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

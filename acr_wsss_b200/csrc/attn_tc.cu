@@ -200,10 +200,24 @@ static_assert(sizeof(float) * BM * STAGE_LD <= sizeof(uint8_t) * MEAN_STAGES * 2
 
 // MODE 0: mean[b,q,kv] = (1/H) sum_h P_h ; MODE 1 (backward pre-pass): delta[b,h,q] += (1/H) sum_kv P_h[q,kv] * G[b,q,kv]
 // (`mean` is then the read-only G, `p_row0` the delta accumulator).
+// Sign-code form of G (acr_consistency_fwd_bwd): one byte per element = top byte of +-0.5f; strides in bytes.
+struct GCode {
+  const unsigned char* ptr;
+  long long bs, ld;
+  float w_cls, w_aff;
+  const float* scale;     // optional device scalar
+};
+__device__ __forceinline__ float gcode_weight(const GCode& gc, int q, float invH) {   // 2*w*scale/H of query row q
+  const float sc = gc.scale ? __ldg(gc.scale) : 1.f;
+  return 2.f * invH * sc * (q == 0 ? gc.w_cls : gc.w_aff);
+}
+// byte k (0..3) of a word moved to the top byte of an fp32: 0x3F -> +0.5f, 0xBF -> -0.5f, 0x00 -> 0
+#define ACR_CODE_F(word, k) __uint_as_float(__byte_perm((word), 0u, 0x0444u | ((k) << 12)))
+
 template <int MODE>
 __global__ void __launch_bounds__(384)
 attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __restrict__ lse, float* __restrict__ mean,
-                 long long mean_bs, long long mean_ld, float* __restrict__ p_row0, int N, int H, float scale_log2) {
+                 long long mean_bs, long long mean_ld, GCode gc, float* __restrict__ p_row0, int N, int H, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   MeanSmem& s = *reinterpret_cast<MeanSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -258,11 +272,27 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
     if (MODE == 0) {
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-    } else {
+    } else if (gc.ptr == nullptr) {
       // G tile of this thread's row, pre-scaled by 1/H; zero outside the map
       const float* grow = mean + (size_t)b * mean_bs + (size_t)(q0 + row) * mean_ld + kv0 + half * 64;
 #pragma unroll
       for (int i = 0; i < 64; ++i) acc[i] = (row_ok && kv0 + half * 64 + i < N) ? __ldg(grow + i) * invH : 0.f;
+    } else {
+      // sign codes: 64 bytes of this row (rows are padded to a multiple of 128 bytes, so the loads stay in bounds)
+      const float w2 = gcode_weight(gc, q0 + row, invH);
+      const uint4* crow = reinterpret_cast<const uint4*>(gc.ptr + (size_t)b * gc.bs + (size_t)min(q0 + row, N - 1) * gc.ld + kv0 + half * 64);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const uint4 t = __ldg(crow + v);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = v * 16 + j * 4 + k;
+            acc[i] = (row_ok && kv0 + half * 64 + i < N) ? ACR_CODE_F(w[j], k) * w2 : 0.f;
+          }
+      }
     }
     // log2-domain LSE of this tile's rows for every head, staged once: s.lse2[h][row] (+inf for rows past N -> P = 0)
     for (int e = we * 32 + lane; e < H * BM; e += 256) {
@@ -402,7 +432,7 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
       attr_set = true;
     }
     dim3 grid(kt, qt, B);
-    attn_mean_kernel<0><<<grid, 384, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, (long long)N, p_row0, N, H, scale_log2);
+    attn_mean_kernel<0><<<grid, 384, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, (long long)N, GCode{}, p_row0, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel")) return e;
   }
   return 0;
@@ -478,6 +508,75 @@ struct BwdSmem {
   uint32_t tmem_base;
 };
 
+// Softmax-backward of one thread's share of a tile: query row `row`, 64 key columns starting at `colbase`.
+// grow == nullptr <=> no affinity gradient was given (warp-uniform).
+// GMODE: 0 no affinity gradient, 1 fp32 rows (scalar loads), 2 fp32 rows (128-bit loads), 3 sign codes (`grow` then points
+// at bytes and `invH` carries 2*w*scale/H of this row).
+template <int GMODE, bool TAIL>
+__device__ __forceinline__ void bwd_tile_body(BwdSmem& s, int buf, uint32_t tS, uint32_t tDP, uint32_t lane_off, int half, int row,
+                                              int colbase, int N, const float* __restrict__ grow, float invH, float scale_log2,
+                                              float lse2, float dlt, float* __restrict__ rd_row0) {
+  constexpr bool HAS_G = GMODE != 0;
+  uint32_t rs[32], rd[32];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    tc::tmem_ld32(tS + lane_off + half * 64 + c * 32, rs);
+    tc::tmem_ld32(tDP + lane_off + half * 64 + c * 32, rd);
+    float g[32];
+    if (GMODE == 3) {
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(grow) + c * 32) + v);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) g[v * 16 + j * 4 + k] = ACR_CODE_F(w[j], k);
+      }
+    } else if (GMODE == 2) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(grow + c * 32) + e);
+        g[4 * e] = t.x; g[4 * e + 1] = t.y; g[4 * e + 2] = t.z; g[4 * e + 3] = t.w;
+      }
+    } else if (GMODE == 1) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) g[e] = (!TAIL || colbase + c * 32 + e < N) ? __ldg(grow + c * 32 + e) : 0.f;
+    }
+    tc::tmem_ld_wait();
+    uint32_t pk[16], dk[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      float pv[2], dv[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int cc = c * 32 + 2 * e + u;
+        float p = tc::fast_exp2(fmaf(__uint_as_float(rs[2 * e + u]), scale_log2, -lse2));
+        if (TAIL && colbase + cc >= N) p = 0.f;
+        float dp = __uint_as_float(rd[2 * e + u]);
+        if (HAS_G) { dp = fmaf(g[2 * e + u], invH, dp); rd[2 * e + u] = __float_as_uint(dp); }
+        pv[u] = p;
+        dv[u] = p * (dp - dlt);
+      }
+      pk[e] = tc::pack_bf16(pv[0], pv[1]);
+      dk[e] = tc::pack_bf16(dv[0], dv[1]);
+    }
+    if (rd_row0 != nullptr) {                       // row 0 of dP_h (one thread of one tile): what the reference's hook keeps
+      for (int e = 0; e < 32; ++e)
+        if (colbase + c * 32 + e < N) rd_row0[c * 32 + e] = __uint_as_float(rd[e]);
+    }
+    // this thread's row of block `half`: 16-byte chunk j at position j ^ (row & 7)
+    uint8_t* prow = s.p[buf][half] + row * 128;
+    uint8_t* drow = s.ds[buf][half] + row * 128;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int pos = ((c * 4 + cc) ^ (row & 7)) << 4;
+      *reinterpret_cast<uint4*>(prow + pos) = make_uint4(pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
+      *reinterpret_cast<uint4*>(drow + pos) = make_uint4(dk[cc * 4 + 0], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]);
+    }
+  }
+}
+
 // One CTA per (key tile j, head, image); K_j, V_j stationary, loop over query tiles i.  Rows (TMEM lanes) = queries:
 //   S = Q_i K_j^T, dP = dO_i V_j^T  (SS MMAs)  ->  per thread: one query row, 64 key columns:
 //   P = exp2(S*c - lse_row), dP += G[row, cols]/H (row-contiguous loads), dS = P*(dP - delta_row)
@@ -485,10 +584,10 @@ struct BwdSmem {
 //   dV += P^T dO (A = P tile read MN-major), dK += dS^T Q (A = dS tile MN-major), dQ_i = dS K_j (A = dS tile K-major).
 // MMA issue order: the scores of tile i+1 are issued BEFORE the gradient MMAs of tile i, so the softmax warps of tile
 // i+1 only wait for 2 of the 5 MMAs; dQ tiles are reduced over key tiles with vectorised fp32 reductions.
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(384, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const float* __restrict__ lse, const float* __restrict__ delta, const float* __restrict__ g_mean, long long g_bs,
-                long long g_ld, __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ dq_acc, float* __restrict__ g_row0,
+                long long g_ld, GCode gc, __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ dq_acc, float* __restrict__ g_row0,
                 int N, int H, float scale, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
   BwdSmem& s = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -514,6 +613,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
 
   if (warp == 0) {
+    tc::reg_dealloc<40>();
     if (lane == 0) {
       tc::mbar_arrive_expect_tx(&s.kv_full, 2 * TILE_BYTES);
       tc::tma_load_4d(s.k, &tmap_qkv, &s.kv_full, 0, H + h, kv0, b);
@@ -527,6 +627,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       }
     }
   } else if (warp == 1) {
+    tc::reg_dealloc<40>();
     if (lane == 0) {
       tc::mbar_wait(&s.kv_full, 0);
       const uint32_t k_addr = tc::smem_u32(s.k), v_addr = tc::smem_u32(s.v);
@@ -568,7 +669,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         tc::tc_commit(&s.qdo_empty[st]);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    tc::reg_dealloc<40>();
+  } else {
+    tc::reg_alloc<232>();
     const int we = warp - 4;
     const int row = (warp & 3) * 32 + lane;          // query row inside the tile (TMEM lane)
     const int half = we >> 2;                        // which 64-column (key) half
@@ -579,7 +683,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const bool g_vec = (g_mean != nullptr) && ((g_ld & 3) == 0) && ((g_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(g_mean) & 15) == 0);
     const float* stat_l = lse + ((size_t)b * H + h) * N;
     const float* stat_d = delta + ((size_t)b * H + h) * N;
-    uint32_t rs[32], rd[32];
+    uint32_t rs[32];
     // rows = queries (lanes), 64 columns = d; this thread reduces its 32 columns of query row q into the fp32 accumulator
     auto reduce_dq = [&](int q) {
       float* dqp = dq_acc + (((size_t)b * H + h) * N + q) * HD + half * 32;
@@ -589,74 +693,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                      "f"(__uint_as_float(rs[4 * e + 1])), "f"(__uint_as_float(rs[4 * e + 2])), "f"(__uint_as_float(rs[4 * e + 3]))
                      : "memory");
     };
-    float lse2_n = (row < N) ? __ldg(stat_l + row) * kLog2e : INFINITY;
+    float lse_n = (row < N) ? __ldg(stat_l + row) : INFINITY;   // natural-log LSE; scaled to log2 at use
     float dlt_n = (row < N) ? __ldg(stat_d + row) : 0.f;
     for (int i = 0; i < ntiles; ++i) {
       const int q0 = i * BM;
       const int qi = q0 + row;
       const bool q_ok = qi < N;
-      const float lse2 = lse2_n, dlt = dlt_n;
+      const float lse2 = lse_n * kLog2e, dlt = dlt_n;
       if (i + 1 < ntiles) {                          // row statistics of the next tile, off the critical path
         const int qn = qi + BM;
-        lse2_n = (qn < N) ? __ldg(stat_l + qn) * kLog2e : INFINITY;
+        lse_n = (qn < N) ? __ldg(stat_l + qn) : INFINITY;
         dlt_n = (qn < N) ? __ldg(stat_d + qn) : 0.f;
       }
-      const float* grow = (g_mean != nullptr && q_ok) ? g_mean + (size_t)b * g_bs + (size_t)qi * g_ld + colbase : nullptr;
+      // rows past N read a clamped (valid) row: their P is 0, so the value is irrelevant, and the branch on the
+      // presence of G stays warp-uniform (the tile body contains warp-collective tcgen05.ld)
+      const float* grow = (g_mean != nullptr) ? g_mean + (size_t)b * g_bs + (size_t)min(qi, N - 1) * g_ld + colbase : nullptr;
+      const unsigned char* crow = (gc.ptr != nullptr) ? gc.ptr + (size_t)b * gc.bs + (size_t)min(qi, N - 1) * gc.ld + colbase : nullptr;
+      float* rd_row0 = (g_row0 != nullptr && qi == 0) ? g_row0 + ((size_t)b * H + h) * N + colbase : nullptr;
       tc::mbar_wait(&s.sdp_full, i & 1);
       tc::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tc::tmem_ld32(tS + lane_off + half * 64 + c * 32, rs);
-        tc::tmem_ld32(tDP + lane_off + half * 64 + c * 32, rd);
-        float g[32];
-        if (grow != nullptr) {
-          if (g_vec && !tail) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(grow + c * 32) + e);
-              g[4 * e] = t.x; g[4 * e + 1] = t.y; g[4 * e + 2] = t.z; g[4 * e + 3] = t.w;
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) g[e] = (colbase + c * 32 + e < N) ? __ldg(grow + c * 32 + e) : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) g[e] = 0.f;
-        }
-        tc::tmem_ld_wait();
-        uint32_t pk[16], dk[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          float pv[2], dv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int cc = c * 32 + 2 * e + u;
-            float p = tc::fast_exp2(fmaf(__uint_as_float(rs[2 * e + u]), scale_log2, -lse2));
-            if (tail && colbase + cc >= N) p = 0.f;
-            const float dp = fmaf(g[2 * e + u], invH, __uint_as_float(rd[2 * e + u]));
-            rd[2 * e + u] = __float_as_uint(dp);
-            pv[u] = p;
-            dv[u] = p * (dp - dlt);
-          }
-          pk[e] = tc::pack_bf16(pv[0], pv[1]);
-          dk[e] = tc::pack_bf16(dv[0], dv[1]);
-        }
-        if (g_row0 != nullptr && qi == 0) {             // row 0 of dP_h: what the reference's hook keeps for GETAM
-          float* dst0 = g_row0 + ((size_t)b * H + h) * N + colbase + c * 32;
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (colbase + c * 32 + e < N) dst0[e] = __uint_as_float(rd[e]);
-        }
-        // this thread's row of block `half`: 16-byte chunk j at position j ^ (row & 7)
-        uint8_t* prow = s.p[i & 1][half] + row * 128;
-        uint8_t* drow = s.ds[i & 1][half] + row * 128;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int pos = ((c * 4 + cc) ^ (row & 7)) << 4;
-          *reinterpret_cast<uint4*>(prow + pos) = make_uint4(pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-          *reinterpret_cast<uint4*>(drow + pos) = make_uint4(dk[cc * 4 + 0], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]);
-        }
+      // specialised bodies (uniform branches): affinity gradient present / key tail tile
+      if (crow != nullptr) {
+        const float w2 = gcode_weight(gc, qi, invH);
+        const float* cp = reinterpret_cast<const float*>(crow);
+        if (!tail) bwd_tile_body<3, false>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, cp, w2, scale_log2, lse2, dlt, rd_row0);
+        else bwd_tile_body<3, true>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, cp, w2, scale_log2, lse2, dlt, rd_row0);
+      } else if (grow != nullptr) {
+        if (!tail && g_vec) bwd_tile_body<2, false>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, grow, invH, scale_log2, lse2, dlt, rd_row0);
+        else bwd_tile_body<1, true>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, grow, invH, scale_log2, lse2, dlt, rd_row0);
+      } else {
+        if (!tail) bwd_tile_body<0, false>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, nullptr, invH, scale_log2, lse2, dlt, rd_row0);
+        else bwd_tile_body<0, true>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, nullptr, invH, scale_log2, lse2, dlt, rd_row0);
       }
       tc::fence_proxy_async_smem();
       // dQ of the PREVIOUS query tile (its MMAs ran under this tile's softmax) must leave TMEM before pds_full(i)
@@ -678,6 +745,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     if ((ntiles - 1) * BM + row < N) reduce_dq((ntiles - 1) * BM + row);
     // epilogue: dV, dK rows (lanes = keys) of this key tile; all MMAs are complete (the last dq_full covered them)
     const bool kv_ok = (kv0 + row) < N;
+    uint32_t rd[32];
     tc::tmem_ld32(tDV + lane_off + half * 32, rs);      // warp-collective: outside the per-row validity branch
     tc::tmem_ld32(tDK + lane_off + half * 32, rd);
     tc::tmem_ld_wait();
@@ -720,12 +788,19 @@ extern "C" size_t acr_attn_bwd_bf16_workspace(int B, int N, int H, int D) {
 extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* lse, const void* d_out,
                                  int B, int N, int H, int D, float scale,
                                  const float* g_mean, long long g_batch_stride, long long g_row_stride,
+                                 const unsigned char* g_code, long long code_batch_stride, long long code_row_stride,
+                                 float w_cls, float w_aff, const float* g_scale,
                                  void* d_qkv, float* g_row0, void* workspace, size_t workspace_bytes, void* stream) {
   ACR_REQUIRE(qkv && out && lse && d_out && d_qkv && workspace, ACR_E_INVAL, "acr_attn_bwd_bf16: null pointer");
   ACR_REQUIRE(B > 0 && N > 0 && H > 0, ACR_E_INVAL, "acr_attn_bwd_bf16: bad shape");
   ACR_REQUIRE(D == HD, ACR_E_INVAL, "acr_attn_bwd_bf16: head dim %d unsupported (64 only)", D);
   ACR_REQUIRE(B <= 65535 && H <= MEAN_MAX_H, ACR_E_INVAL, "acr_attn_bwd_bf16: B <= 65535 and H <= %d required", MEAN_MAX_H);
   ACR_REQUIRE(g_mean == nullptr || g_row_stride >= N, ACR_E_INVAL, "acr_attn_bwd_bf16: g_row_stride < N");
+  ACR_REQUIRE(g_mean == nullptr || g_code == nullptr, ACR_E_INVAL, "acr_attn_bwd_bf16: give g_mean OR g_code");
+  ACR_REQUIRE(g_code == nullptr || ((code_row_stride % 128) == 0 && code_row_stride >= (long long)((N + 127) / 128) * 128 &&
+                                    (code_batch_stride % 16) == 0 && ((uintptr_t)g_code & 15) == 0),
+              ACR_E_ALIGN, "acr_attn_bwd_bf16: g_code rows must be 128-byte padded and 16-byte aligned");
+  const GCode gc{g_code, code_batch_stride, code_row_stride, w_cls, w_aff, g_scale};
   ACR_REQUIRE(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)d_out & 15) == 0 && ((uintptr_t)d_qkv & 15) == 0,
               ACR_E_ALIGN, "acr_attn_bwd_bf16: tensors must be 16-byte aligned");
   ACR_REQUIRE(((uintptr_t)workspace & 255) == 0, ACR_E_ALIGN, "acr_attn_bwd_bf16: workspace must be 256-byte aligned");
@@ -744,7 +819,7 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
   ACR_CUDA(cudaMemsetAsync(dq_acc, 0, rows * D * sizeof(float), st));
   bwd_delta_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)out, (const __nv_bfloat16*)d_out, delta, B, N, H);
   if (int e = acr::check_launch("bwd_delta_kernel")) return e;
-  if (g_mean) {
+  if (g_mean || g_code) {
     const size_t smem = sizeof(MeanSmem) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
@@ -752,7 +827,7 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
       attr_set = true;
     }
     dim3 grid(kt, qt, B);
-    attn_mean_kernel<1><<<grid, 384, smem, st>>>(tmap_qkv, lse, const_cast<float*>(g_mean), g_batch_stride, g_row_stride, delta, N, H, scale_log2);
+    attn_mean_kernel<1><<<grid, 384, smem, st>>>(tmap_qkv, lse, const_cast<float*>(g_mean), g_batch_stride, g_row_stride, gc, delta, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel<1>")) return e;
   }
   {
@@ -763,7 +838,7 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
       attr_set = true;
     }
     dim3 grid(kt, H, B);
-    attn_bwd_kernel<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, lse, delta, g_mean, g_batch_stride, g_row_stride, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
+    attn_bwd_kernel<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, lse, delta, g_mean, g_batch_stride, g_row_stride, gc, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
                                              N, H, scale, scale_log2);
     if (int e = acr::check_launch("attn_bwd_kernel")) return e;
   }

@@ -23,11 +23,14 @@ __device__ __forceinline__ int flip_token(int t, int p) {
   return 1 + r * p + (p - 1 - c);
 }
 
-template <bool kGrad>
+// kGrad: 0 = loss only, 1 = dense fp32 gradients, 2 = sign codes (one byte per element: 0x00 zero, 0x3F plus, 0xBF minus,
+// i.e. the top byte of +-0.5f, so that a consumer decodes with one byte-permute: float(code << 24) * 2w).
+template <int kGrad>
 __global__ void __launch_bounds__(kThreads)
 consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ a2,
                         int N, int p, float w_cls, float w_aff,
-                        float* __restrict__ g1, float* __restrict__ g2,
+                        float* __restrict__ g1, float* __restrict__ g2, long long g_ld,
+                        unsigned char* __restrict__ c1, unsigned char* __restrict__ c2, long long c_ld,
                         float* __restrict__ partials) {
   __shared__ float red[32];
   const long long row = blockIdx.x;            // (b*L + l)*N + i
@@ -53,22 +56,31 @@ consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ 
     }
   }
   float acc = 0.f;
-  float* o1 = kGrad ? g1 + (img * N + i) * (long long)N : nullptr;
-  float* o2 = kGrad ? g2 + (img * N + pi_i) * (long long)N : nullptr;
+  float* o1 = (kGrad == 1) ? g1 + (img * N + i) * g_ld : nullptr;
+  float* o2 = (kGrad == 1) ? g2 + (img * N + pi_i) * g_ld : nullptr;
+  unsigned char* b1 = (kGrad == 2) ? c1 + (img * N + i) * c_ld : nullptr;
+  unsigned char* b2 = (kGrad == 2) ? c2 + (img * N + pi_i) * c_ld : nullptr;
 #pragma unroll
   for (int k = 0; k < kMaxPerThread; ++k) {
     if (k < per) {
       const int j = threadIdx.x + k * kThreads;
       if (j < N) {
         float s = 0.f;
+        unsigned char code = 0, ncode = 0;
         if (j > 0) {
           const float d = v1[k] - v2[k];
           acc += fabsf(d);
           s = (d > 0.f) ? w : ((d < 0.f) ? -w : 0.f);
+          code = (d > 0.f) ? 0x3F : ((d < 0.f) ? 0xBF : 0x00);
+          ncode = (d > 0.f) ? 0xBF : ((d < 0.f) ? 0x3F : 0x00);
         }
-        if (kGrad) {
+        if (kGrad == 1) {
           o1[j] = s;
           o2[pj[k]] = -s;
+        }
+        if (kGrad == 2) {
+          b1[j] = code;
+          b2[pj[k]] = ncode;
         }
       }
     }
@@ -119,7 +131,8 @@ extern "C" size_t acr_consistency_workspace(int B, int L, int N) {
 
 extern "C" int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, int B, int L, int N, int p,
                                        float alpha_cls, float alpha_aff,
-                                       float* loss2, float* g1, float* g2,
+                                       float* loss2, float* g1, float* g2, long long g_row_stride,
+                                       unsigned char* code1, unsigned char* code2, long long code_row_stride,
                                        void* workspace, size_t workspace_bytes, void* stream) {
   ACR_REQUIRE(attn1 && attn2 && loss2 && workspace, ACR_E_INVAL, "acr_consistency_fwd_bwd: null pointer");
   ACR_REQUIRE(B > 0 && L > 0 && p > 0, ACR_E_INVAL, "acr_consistency_fwd_bwd: bad B/L/p");
@@ -127,6 +140,10 @@ extern "C" int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, i
   ACR_REQUIRE(N <= kThreads * kMaxPerThread, ACR_E_INVAL, "acr_consistency_fwd_bwd: N=%d > %d unsupported", N,
               kThreads * kMaxPerThread);
   ACR_REQUIRE((g1 == nullptr) == (g2 == nullptr), ACR_E_INVAL, "acr_consistency_fwd_bwd: g1/g2 must both be set or null");
+  ACR_REQUIRE(g1 == nullptr || g_row_stride >= N, ACR_E_INVAL, "acr_consistency_fwd_bwd: g_row_stride < N");
+  ACR_REQUIRE((code1 == nullptr) == (code2 == nullptr), ACR_E_INVAL, "acr_consistency_fwd_bwd: code1/code2 must both be set or null");
+  ACR_REQUIRE(code1 == nullptr || g1 == nullptr, ACR_E_INVAL, "acr_consistency_fwd_bwd: ask for dense gradients OR sign codes");
+  ACR_REQUIRE(code1 == nullptr || code_row_stride >= N, ACR_E_INVAL, "acr_consistency_fwd_bwd: code_row_stride < N");
   ACR_REQUIRE(workspace_bytes >= acr_consistency_workspace(B, L, N), ACR_E_NOMEM,
               "acr_consistency_fwd_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -138,9 +155,11 @@ extern "C" int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, i
   const float w_aff = (float)((double)alpha_aff / cnt_aff);
   float* partials = (float*)workspace;
   if (g1) {
-    consistency_rows_kernel<true><<<(unsigned)rows, kThreads, 0, st>>>(attn1, attn2, N, p, w_cls, w_aff, g1, g2, partials);
+    consistency_rows_kernel<1><<<(unsigned)rows, kThreads, 0, st>>>(attn1, attn2, N, p, w_cls, w_aff, g1, g2, g_row_stride, nullptr, nullptr, 0, partials);
+  } else if (code1) {
+    consistency_rows_kernel<2><<<(unsigned)rows, kThreads, 0, st>>>(attn1, attn2, N, p, w_cls, w_aff, nullptr, nullptr, 0, code1, code2, code_row_stride, partials);
   } else {
-    consistency_rows_kernel<false><<<(unsigned)rows, kThreads, 0, st>>>(attn1, attn2, N, p, w_cls, w_aff, nullptr, nullptr, partials);
+    consistency_rows_kernel<0><<<(unsigned)rows, kThreads, 0, st>>>(attn1, attn2, N, p, w_cls, w_aff, nullptr, nullptr, 0, nullptr, nullptr, 0, partials);
   }
   if (int e = acr::check_launch("consistency_rows_kernel")) return e;
   consistency_finish_kernel<<<1, 1024, 0, st>>>(partials, rows, N, 1.0 / cnt_cls, 1.0 / cnt_aff, loss2);

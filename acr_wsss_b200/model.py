@@ -270,7 +270,7 @@ class ACR(nn.Module):
         for blk in vit.blocks:
             blk.attn._slot = None
         if record:
-            attn = ops.stack_views(stack, [blk.attn.attn_mean for blk in vit.blocks])
+            attn = ops.stack_views(stack, [blk.attn.attn_mean for blk in vit.blocks], [blk.attn._state for blk in vit.blocks])
         else:
             # no_grad: the reference returns the stale maps of the last recorded forward
             maps = [blk.attn.attn_mean for blk in vit.blocks]

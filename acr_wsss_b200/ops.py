@@ -156,6 +156,7 @@ class _AttnCoreBF16(torch.autograd.Function):
             state["attn"] = None
             state["row0"] = p_row0
             state["qkv"] = qkv
+            state["fused"] = True       # lets consistency_loss hand its gradient over as sign codes
         ctx.set_materialize_grads(False)
         return out, _alias(mean_slot)
 
@@ -166,15 +167,22 @@ class _AttnCoreBF16(torch.autograd.Function):
         d_out = (torch.zeros(B, N, H * D, device=qkv.device, dtype=torch.bfloat16) if d_out is None
                  else d_out.contiguous().to(torch.bfloat16))
         gs, gl = 0, 0
+        code, cbs, cld, w_cls, w_aff, g_scale = None, 0, 0, 0.0, 0.0, None
         if g_mean is not None:
             g_mean, gs, gl = _strided_map(g_mean.float())
+        elif ctx.state is not None and ctx.state.get("g_code") is not None:
+            code = ctx.state.pop("g_code")                      # [B,N,ld] uint8 view of the [B,L,N,ld] code tensor
+            cbs, cld = code.stride(0), code.stride(1)
+            w_cls, w_aff = ctx.state.pop("g_w")
+            g_scale = ctx.state.pop("g_scale")
         d_qkv = torch.empty_like(qkv)
         want_row0 = ctx.state is not None and ctx.state.get("capture_grad", True)
         g_row0 = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32) if want_row0 else None
         wsb = _lib.lib().acr_attn_bwd_bf16_workspace(B, N, H, D)
         ws = torch.empty(wsb, device=qkv.device, dtype=torch.uint8)
         _call("acr_attn_bwd_bf16", 4, _p(qkv), _p(out), _p(lse), _p(d_out), B, N, H, D, scale,
-              _p(g_mean), gs, gl, _p(d_qkv), _p(g_row0), _p(ws), wsb, _stream())
+              _p(g_mean), gs, gl, _p(code), cbs, cld, w_cls, w_aff, _p(g_scale),
+              _p(d_qkv), _p(g_row0), _p(ws), wsb, _stream())
         if want_row0:
             ctx.state["grad_row0"] = g_row0
         return d_qkv, None, None, None, None
@@ -207,13 +215,33 @@ class _StackViews(torch.autograd.Function):
         return (None,) + tuple(g[:, l] for l in range(ctx.n))
 
 
-def stack_views(stack, maps):
-    return _StackViews.apply(stack, *maps)
+def stack_views(stack, maps, states=None):
+    out = _StackViews.apply(stack, *maps)
+    if states is not None:
+        out._acr_states = list(states)      # per-block state dicts of the forward pass that produced this stack
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
 # (a7) consistency loss
 # ----------------------------------------------------------------------------------------------
+def consistency_codes(attn1, attn2, p):
+    """loss2 plus the gradient as SIGN CODES: uint8 [B,L,N,ld] (ld = N padded to 128), 0x00 / 0x3F (+) / 0xBF (-)."""
+    _need_cuda(attn1, attn2)
+    B, L, N, _ = attn1.shape
+    a1 = attn1.contiguous().float()
+    a2 = attn2.contiguous().float()
+    ld = (N + 127) // 128 * 128
+    loss2 = torch.empty(2, device=a1.device, dtype=torch.float32)
+    c1 = torch.empty(B, L, N, ld, device=a1.device, dtype=torch.uint8)
+    c2 = torch.empty(B, L, N, ld, device=a1.device, dtype=torch.uint8)
+    wsb = _lib.lib().acr_consistency_workspace(B, L, N)
+    ws = torch.empty(wsb, device=a1.device, dtype=torch.uint8)
+    _call("acr_consistency_fwd_bwd", 2, _p(a1), _p(a2), B, L, N, int(p), 1.0, 1.0, _p(loss2), None, None, 0,
+          _p(c1), _p(c2), ld, _p(ws), wsb, _stream())
+    return loss2, c1, c2
+
+
 def consistency_fwd_bwd(attn1, attn2, p, alpha_cls=1.0, alpha_aff=1.0, need_grad=True):
     """Returns (loss2 [2] = (cls_align, aff_align), g1, g2); g = alpha_cls*dcls/dA + alpha_aff*daff/dA."""
     _need_cuda(attn1, attn2)
@@ -222,12 +250,17 @@ def consistency_fwd_bwd(attn1, attn2, p, alpha_cls=1.0, alpha_aff=1.0, need_grad
     a1 = attn1.contiguous().float()
     a2 = attn2.contiguous().float()
     loss2 = torch.empty(2, device=a1.device, dtype=torch.float32)
-    g1 = torch.empty_like(a1) if need_grad else None
-    g2 = torch.empty_like(a2) if need_grad else None
+    # gradient rows are padded to a multiple of 4 floats (16-byte aligned rows for the attention backward's
+    # 128-bit loads); callers see the dense [B,L,N,N] view
+    Np = (N + 3) // 4 * 4
+    g1 = torch.empty(B, L, N, Np, device=a1.device, dtype=torch.float32) if need_grad else None
+    g2 = torch.empty(B, L, N, Np, device=a1.device, dtype=torch.float32) if need_grad else None
     wsb = _lib.lib().acr_consistency_workspace(B, L, N)
     ws = torch.empty(wsb, device=a1.device, dtype=torch.uint8)
     _call("acr_consistency_fwd_bwd", 2, _p(a1), _p(a2), B, L, N, int(p), float(alpha_cls), float(alpha_aff),
-                                                  _p(loss2), _p(g1), _p(g2), _p(ws), wsb, _stream())
+                                             _p(loss2), _p(g1), _p(g2), Np, None, None, 0, _p(ws), wsb, _stream())
+    if need_grad:
+        g1, g2 = g1[..., :N], g2[..., :N]
     return loss2, g1, g2
 
 
@@ -252,8 +285,44 @@ class _ConsistencyLoss(torch.autograd.Function):
         return g1.mul_(g_total), g2.mul_(g_total), None, None
 
 
+class _ConsistencyLossCodes(torch.autograd.Function):
+    """Same loss, but the gradient never exists as fp32 [B,L,N,N]: backward hands each attention block its slice of the
+    sign-code tensor (plus the two weights and autograd's upstream scalar, kept on the device) through the block's
+    state dict, and returns no tensor gradient.  The fused attention backward picks the codes up (autograd runs it
+    after this node because the stack it produced feeds this loss)."""
+
+    @staticmethod
+    def forward(ctx, attn1, attn2, p, alpha, states1, states2):
+        B, L, N, _ = attn1.shape
+        loss2, c1, c2 = consistency_codes(attn1.detach(), attn2.detach(), p)
+        ctx.codes = (c1, c2)
+        ctx.states = (states1, states2)
+        ctx.w = (alpha / (B * L * (N - 1)), alpha / (B * L * float(N - 1) ** 2))
+        total = alpha * (loss2[0] + loss2[1])
+        ctx.mark_non_differentiable(loss2)
+        return total, loss2
+
+    @staticmethod
+    def backward(ctx, g_total, _g_loss2):
+        scale = g_total.detach().reshape(1).float().contiguous()
+        for codes, states in zip(ctx.codes, ctx.states):
+            for l, st in enumerate(states):
+                st["g_code"] = codes[:, l]
+                st["g_w"] = ctx.w
+                st["g_scale"] = scale
+        return None, None, None, None, None, None
+
+
 def consistency_loss(attn1, attn2, p, alpha):
-    """alpha*(cls_align + aff_align) with its gradient fused; also returns the two components (detached)."""
+    """alpha*(cls_align + aff_align) with its gradient fused; also returns the two components (detached).
+
+    When both stacks come straight from the fused attention path (ops.stack_views with per-block states), the gradient
+    travels as one sign byte per element instead of dense fp32 maps (4x less HBM traffic in the loss kernel and in
+    every attention backward); otherwise dense fp32 gradients flow through autograd as usual."""
+    st1, st2 = getattr(attn1, "_acr_states", None), getattr(attn2, "_acr_states", None)
+    if (st1 is not None and st2 is not None and attn1.requires_grad and attn2.requires_grad
+            and all(s is not None and s.get("fused") for s in st1 + st2)):
+        return _ConsistencyLossCodes.apply(attn1, attn2, int(p), float(alpha), st1, st2)
     return _ConsistencyLoss.apply(attn1, attn2, int(p), float(alpha))
 
 

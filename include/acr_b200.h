@@ -58,6 +58,9 @@ int acr_attn_fwd_bf16(const void* qkv_bf16, int B, int N, int H, int D, float sc
  *   dP_h = dO_h V_h^T + g_mean / H ;  dS_h = P_h * (dP_h - rowsum(P_h * dP_h)) ; dQ,dK,dV as usual.
  * g_mean (nullable) = dLoss/dA-bar for this block: element (b,i,j) at g_mean + b*g_batch_stride + i*g_row_stride + j
  * (a row stride that is a multiple of 4 with a 16-byte aligned base enables 128-bit loads).
+ * Alternatively (g_mean NULL) the gradient may be given as sign codes from acr_consistency_fwd_bwd: g_code with strides in
+ * BYTES (row stride a multiple of 128 and >= the 128-padded N, base 16-byte aligned), the two weights, and an optional
+ * DEVICE scalar g_scale multiplying them (NULL = 1; lets autograd's upstream gradient through without a host sync).
  * d_qkv_bf16 has the layout of qkv.  g_row0 (nullable, [B,H,N] fp32) receives row 0 of dP_h, which is
  * what the reference's save_attn_gradients hook keeps and getam consumes (DPT/ACR.py:182-213).
  * workspace: acr_attn_bwd_bf16_workspace() bytes, 256-byte aligned. */
@@ -65,6 +68,8 @@ size_t acr_attn_bwd_bf16_workspace(int B, int N, int H, int D);
 int acr_attn_bwd_bf16(const void* qkv_bf16, const void* out_bf16, const float* lse,
                       const void* d_out_bf16, int B, int N, int H, int D, float scale,
                       const float* g_mean, long long g_batch_stride, long long g_row_stride,
+                      const unsigned char* g_code, long long code_batch_stride, long long code_row_stride,
+                      float w_cls, float w_aff, const float* g_scale,
                       void* d_qkv_bf16, float* g_row0,
                       void* workspace, size_t workspace_bytes, void* stream);
 
@@ -86,13 +91,19 @@ int acr_attn_bwd_f32(const float* qkv, const float* P, const float* d_out,
  * Replaces train_acr.py:143-161 (= train_acr_coco.py:140-158): the slicing, the 3*p in-place
  * flips and the two F.l1_loss calls.  attn1/attn2 are the [B,L,N,N] fp32 stacks of the two views
  * (N = p*p+1), NOT modified.  loss2[0] = cls_align, loss2[1] = aff_align (means, before alpha).
- * g1/g2 (nullable together) receive alpha_cls*d(cls_align)/dA + alpha_aff*d(aff_align)/dA.
- * partials: scratch of acr_consistency_workspace() bytes.
+ * g1/g2 (nullable together) receive alpha_cls*d(cls_align)/dA + alpha_aff*d(aff_align)/dA as [B,L,N] rows of
+ * g_row_stride (>= N) floats; a stride that is a multiple of 4 lets the attention backward use 128-bit loads.
+ * code1/code2 (nullable together; exclusive with g1/g2): the same gradients as one SIGN CODE byte per element, rows of
+ * code_row_stride bytes: 0x00 = 0, 0x3F = +w, 0xBF = -w with w = alpha_cls/(B*L*(N-1)) on row 0 and
+ * alpha_aff/(B*L*(N-1)^2) elsewhere (the code is the top byte of +-0.5f).  4x less HBM traffic than fp32 gradients;
+ * acr_attn_bwd_bf16 consumes them directly.  Padding bytes of a row are not written.
+ * workspace: scratch of acr_consistency_workspace() bytes.
  * ------------------------------------------------------------------------------------------ */
 size_t acr_consistency_workspace(int B, int L, int N);
 int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, int B, int L, int N, int p,
                             float alpha_cls, float alpha_aff,
-                            float* loss2, float* g1, float* g2,
+                            float* loss2, float* g1, float* g2, long long g_row_stride,
+                            unsigned char* code1, unsigned char* code2, long long code_row_stride,
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -37,16 +37,20 @@ def timeit(fn):
 def fwd(with_mean=True):
     rc = L.acr_attn_fwd_bf16(p(qkv), B, N, H, D, D ** -0.5, p(out), p(lse), p(mean) if with_mean else None, N * N, p(row0) if with_mean else None, st)
     assert rc == 0, _lib.last_error()
-def bwd(with_g=True):
-    rc = L.acr_attn_bwd_bf16(p(qkv), p(out), p(lse), p(d_out), B, N, H, D, D ** -0.5, p(G) if with_g else None, G.stride(0), G.stride(1), p(d_qkv), None, p(ws), wsb, st)
+LD = (N + 127) // 128 * 128
+codes = torch.tensor([0x00, 0x3F, 0xBF], dtype=torch.uint8, device=dev)[torch.randint(0, 3, (B, N, LD), device=dev, generator=g)]
+def bwd(with_g=1):
+    rc = L.acr_attn_bwd_bf16(p(qkv), p(out), p(lse), p(d_out), B, N, H, D, D ** -0.5, p(G) if with_g == 1 else None, G.stride(0), G.stride(1), p(codes) if with_g == 2 else None, codes.stride(0), codes.stride(1), 1e-7, 1e-9, None, p(d_qkv), None, p(ws), wsb, st)
     assert rc == 0, _lib.last_error()
 
 f_core = 4.0 * B * H * N * N * D
 res = {}
 t = timeit(lambda: fwd(False)); res["fwd_flash_only_us"] = t; res["fwd_flash_TFLOPs"] = f_core / t / 1e6
 t2 = timeit(lambda: fwd(True)); res["fwd_with_mean_us"] = t2; res["mean_kernel_us"] = t2 - t
-t = timeit(lambda: bwd(False)); res["bwd_noG_us"] = t; res["bwd_noG_TFLOPs"] = 2 * f_core / t / 1e6
-t = timeit(lambda: bwd(True)); res["bwd_withG_us"] = t; res["bwd_withG_TFLOPs"] = 2 * f_core / t / 1e6
+t = timeit(lambda: bwd(0)); res["bwd_noG_us"] = t; res["bwd_noG_TFLOPs"] = 2 * f_core / t / 1e6
+t = timeit(lambda: bwd(1)); res["bwd_withG_us"] = t; res["bwd_withG_TFLOPs"] = 2 * f_core / t / 1e6
+t = timeit(lambda: bwd(2)); res["bwd_codes_us"] = t; res["bwd_codes_TFLOPs"] = 2 * f_core / t / 1e6
 a1 = torch.softmax(torch.randn(B, 12, N, N, device=dev, generator=g), -1); a2 = torch.softmax(torch.randn(B, 12, N, N, device=dev, generator=g), -1)
 t = timeit(lambda: ops.consistency_fwd_bwd(a1, a2, int((N - 1) ** 0.5), 100.0, 100.0)); res["consistency_us"] = t; res["consistency_GBs"] = 16.0 * B * 12 * N * N / t / 1e3
+t = timeit(lambda: ops.consistency_codes(a1, a2, int((N - 1) ** 0.5))); res["consistency_codes_us"] = t
 print(json.dumps({k: round(v, 2) for k, v in res.items()}))

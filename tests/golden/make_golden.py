@@ -198,11 +198,12 @@ def bilateral_golden():
 
 if __name__ == "__main__":
     assert loader.available(), "reference tree not found"
-    which = sys.argv[1:] or ["attention", "pamr", "bilateral", "train64", "train448", "vitl64", "infer448", "infer_ms"]
+    which = sys.argv[1:] or ["attention", "pamr", "bilateral", "train64", "train64g2", "train448", "vitl64", "infer448", "infer_ms"]
     if "attention" in which: attention_golden()
     if "pamr" in which: pamr_golden()
     if "bilateral" in which: bilateral_golden()
     if "train64" in which: train_golden("train_vitb_64.npz", "vitb", 64, 2, 20, 100.0)
+    if "train64g2" in which: train_golden("train_vitb_64_g2.npz", "vitb", 64, 2, 20, 100.0, qkv_gain=2.0)
     if "train448" in which: train_golden("train_vitb_448.npz", "vitb", 448, 1, 20, 100.0)
     if "vitl64" in which: train_golden("train_vitl_96.npz", "vitl", 96, 1, 20, 100.0, depth_key=23, qkv_gain=2.5)
     if "infer448" in which: infer_golden("infer_vitb_448.npz", 448, 20, (3, 7, 14), (60, 80), 10, "grad")

@@ -392,4 +392,38 @@ def test_attention_bf16_backward_vs_oracle(dev, B, N, H, with_g):
 
 
 def test_train_step_bf16_vitb_64(dev):
-    _train_step_check(dev, "train_vitb_64.npz", "vitb", "bf16", 3 * BF16_TOL)
+    # bf16-autocast trunk vs the fp32 reference.  The distance is set by bf16 rounding in the Linear layers, not by the
+    # attention kernels: scripts/diag_bf16.py measures 0.9e-2 (ours) vs 1.0e-2 (stock PyTorch bf16 trunk) at gain 2.
+    _train_step_check(dev, "train_vitb_64_g2.npz", "vitb", "bf16", 3 * BF16_TOL)
+
+
+def test_sign_code_gradient_path_matches_dense_path(dev):
+    """The loss gradient as sign codes (fused path) == dense fp32 gradients through autograd."""
+    from acr_wsss_b200 import ops
+    B, L, p, H, D = 2, 2, 5, 3, 64
+    N = p * p + 1
+    g = torch.Generator().manual_seed(3)
+    qkvs = [(torch.randn(B, N, 3 * H * D, generator=g) * 1.5).to(torch.bfloat16).to(dev) for _ in range(2 * L)]
+    d_out = [torch.randn(B, N, H * D, generator=g).to(torch.bfloat16).to(dev) for _ in range(2 * L)]
+
+    def run(compact):
+        leaves = [q.clone().requires_grad_(True) for q in qkvs]
+        stacks, outs = [], []
+        for v in range(2):
+            stack = torch.empty(B, L, N, N, device=dev)
+            maps, states = [], []
+            for l in range(L):
+                st = {"capture_grad": False}
+                o, m = ops.attention_core(leaves[v * L + l], H, D ** -0.5, stack[:, l], st, "bf16")
+                outs.append(o); maps.append(m); states.append(st)
+            stacks.append(ops.stack_views(stack, maps, states if compact else None))
+        total, loss2 = ops.consistency_loss(stacks[0], stacks[1], p, 100.0)
+        loss = 0.5 * total + sum((o.float() * d.float()).sum() for o, d in zip(outs, d_out)) * 1e-3
+        loss.backward()
+        return loss2, [q.grad.float() for q in leaves]
+
+    l_a, g_a = run(True)
+    l_b, g_b = run(False)
+    assert torch.equal(l_a, l_b)
+    for a, b_ in zip(g_a, g_b):
+        assert rel_err(t2n(a), t2n(b_)) < 2e-3

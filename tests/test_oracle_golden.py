@@ -47,7 +47,7 @@ def test_consistency_loss_forms_agree_and_match_reference():
     assert torch.allclose(g1, a1g.grad, atol=1e-9) and torch.allclose(g2, a2g.grad, atol=1e-9)
 
 
-@pytest.mark.parametrize("name,heads", [("train_vitb_64.npz", 12), ("train_vitl_96.npz", 16)])
+@pytest.mark.parametrize("name,heads", [("train_vitb_64.npz", 12), ("train_vitb_64_g2.npz", 12), ("train_vitl_96.npz", 16)])
 def test_train_step_matches_reference(name, heads):
     g = load_golden(name)
     S, B, C = int(g["S"]), int(g["B"]), int(g["C"])
