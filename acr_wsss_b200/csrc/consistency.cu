@@ -5,15 +5,13 @@
 // neither input is modified and nothing is copied.
 //
 // HBM-bound: compulsory traffic = read A1, A2 once + write G1, G2 once = 16*B*L*N*N bytes.
-// One CTA per (b,l,i) row: row i of A1 is paired with row pi(i) of A2; column j with pi(j).
+// One warp per (b,l,i) row: row i of A1 is paired with row pi(i) of A2; column j with pi(j).
 // Per-row partial |d| sums go to a scratch array and are folded by a second, single-CTA kernel in a
 // fixed order (deterministic; no float atomics).
 #include "common.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kMaxPerThread = 16;  // supports N <= 4096
 
 __device__ __forceinline__ int flip_token(int t, int p) {
   if (t == 0) return 0;
@@ -25,45 +23,48 @@ __device__ __forceinline__ int flip_token(int t, int p) {
 
 // kGrad: 0 = loss only, 1 = dense fp32 gradients, 2 = sign codes (one byte per element: 0x00 zero, 0x3F plus, 0xBF minus,
 // i.e. the top byte of +-0.5f, so that a consumer decodes with one byte-permute: float(code << 24) * 2w).
+// One WARP per (b,l,i) row, kRowsPerCta rows per CTA, no block-level synchronisation; each lane keeps kUnroll
+// independent load pairs in flight.
+constexpr int kRowsPerCta = 8;
+constexpr int kUnroll = 8;
+
 template <int kGrad>
-__global__ void __launch_bounds__(kThreads)
-consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ a2,
+__global__ void __launch_bounds__(kRowsPerCta * 32)
+consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ a2, long long rows,
                         int N, int p, float w_cls, float w_aff,
                         float* __restrict__ g1, float* __restrict__ g2, long long g_ld,
                         unsigned char* __restrict__ c1, unsigned char* __restrict__ c2, long long c_ld,
                         float* __restrict__ partials) {
-  __shared__ float red[32];
-  const long long row = blockIdx.x;            // (b*L + l)*N + i
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);      // (b*L + l)*N + i
+  if (row >= rows) return;
   const int i = (int)(row % N);
   const long long img = row / N;               // b*L + l
   const int pi_i = flip_token(i, p);
   const float* r1 = a1 + (img * N + i) * (long long)N;
   const float* r2 = a2 + (img * N + pi_i) * (long long)N;
   const float w = (i == 0) ? w_cls : w_aff;
+  float* o1 = (kGrad == 1) ? g1 + (img * N + i) * g_ld : nullptr;
+  float* o2 = (kGrad == 1) ? g2 + (img * N + pi_i) * g_ld : nullptr;
+  unsigned char* b1 = (kGrad == 2) ? c1 + (img * N + i) * c_ld : nullptr;
+  unsigned char* b2 = (kGrad == 2) ? c2 + (img * N + pi_i) * c_ld : nullptr;
 
-  float v1[kMaxPerThread], v2[kMaxPerThread];
-  int pj[kMaxPerThread];
-  const int per = (N + kThreads - 1) / kThreads;
+  float acc = 0.f;
+  for (int j0 = 0; j0 < N; j0 += 32 * kUnroll) {
+    float v1[kUnroll], v2[kUnroll];
+    int pj[kUnroll];
 #pragma unroll
-  for (int k = 0; k < kMaxPerThread; ++k) {
-    if (k < per) {
-      const int j = threadIdx.x + k * kThreads;
+    for (int k = 0; k < kUnroll; ++k) {
+      const int j = j0 + k * 32 + lane;
       if (j < N) {
         pj[k] = flip_token(j, p);
         v1[k] = __ldg(r1 + j);
         v2[k] = __ldg(r2 + pj[k]);
       }
     }
-  }
-  float acc = 0.f;
-  float* o1 = (kGrad == 1) ? g1 + (img * N + i) * g_ld : nullptr;
-  float* o2 = (kGrad == 1) ? g2 + (img * N + pi_i) * g_ld : nullptr;
-  unsigned char* b1 = (kGrad == 2) ? c1 + (img * N + i) * c_ld : nullptr;
-  unsigned char* b2 = (kGrad == 2) ? c2 + (img * N + pi_i) * c_ld : nullptr;
 #pragma unroll
-  for (int k = 0; k < kMaxPerThread; ++k) {
-    if (k < per) {
-      const int j = threadIdx.x + k * kThreads;
+    for (int k = 0; k < kUnroll; ++k) {
+      const int j = j0 + k * 32 + lane;
       if (j < N) {
         float s = 0.f;
         unsigned char code = 0, ncode = 0;
@@ -85,8 +86,8 @@ consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ 
       }
     }
   }
-  const float tot = acr::block_sum(acc, red);
-  if (threadIdx.x == 0) partials[row] = tot;
+  acc = acr::warp_sum(acc);
+  if (lane == 0) partials[row] = acc;
 }
 
 // Folds the per-row partials: rows with i==0 feed cls_align, the rest aff_align.
@@ -137,8 +138,6 @@ extern "C" int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, i
   ACR_REQUIRE(attn1 && attn2 && loss2 && workspace, ACR_E_INVAL, "acr_consistency_fwd_bwd: null pointer");
   ACR_REQUIRE(B > 0 && L > 0 && p > 0, ACR_E_INVAL, "acr_consistency_fwd_bwd: bad B/L/p");
   ACR_REQUIRE(N == p * p + 1, ACR_E_INVAL, "acr_consistency_fwd_bwd: N=%d is not p*p+1 (p=%d)", N, p);
-  ACR_REQUIRE(N <= kThreads * kMaxPerThread, ACR_E_INVAL, "acr_consistency_fwd_bwd: N=%d > %d unsupported", N,
-              kThreads * kMaxPerThread);
   ACR_REQUIRE((g1 == nullptr) == (g2 == nullptr), ACR_E_INVAL, "acr_consistency_fwd_bwd: g1/g2 must both be set or null");
   ACR_REQUIRE(g1 == nullptr || g_row_stride >= N, ACR_E_INVAL, "acr_consistency_fwd_bwd: g_row_stride < N");
   ACR_REQUIRE((code1 == nullptr) == (code2 == nullptr), ACR_E_INVAL, "acr_consistency_fwd_bwd: code1/code2 must both be set or null");
@@ -154,12 +153,13 @@ extern "C" int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, i
   const float w_cls = (float)((double)alpha_cls / cnt_cls);
   const float w_aff = (float)((double)alpha_aff / cnt_aff);
   float* partials = (float*)workspace;
+  const unsigned grid = (unsigned)((rows + kRowsPerCta - 1) / kRowsPerCta);
   if (g1) {
-    consistency_rows_kernel<1><<<(unsigned)rows, kThreads, 0, st>>>(attn1, attn2, N, p, w_cls, w_aff, g1, g2, g_row_stride, nullptr, nullptr, 0, partials);
+    consistency_rows_kernel<1><<<grid, kRowsPerCta * 32, 0, st>>>(attn1, attn2, rows, N, p, w_cls, w_aff, g1, g2, g_row_stride, nullptr, nullptr, 0, partials);
   } else if (code1) {
-    consistency_rows_kernel<2><<<(unsigned)rows, kThreads, 0, st>>>(attn1, attn2, N, p, w_cls, w_aff, nullptr, nullptr, 0, code1, code2, code_row_stride, partials);
+    consistency_rows_kernel<2><<<grid, kRowsPerCta * 32, 0, st>>>(attn1, attn2, rows, N, p, w_cls, w_aff, nullptr, nullptr, 0, code1, code2, code_row_stride, partials);
   } else {
-    consistency_rows_kernel<0><<<(unsigned)rows, kThreads, 0, st>>>(attn1, attn2, N, p, w_cls, w_aff, nullptr, nullptr, 0, nullptr, nullptr, 0, partials);
+    consistency_rows_kernel<0><<<grid, kRowsPerCta * 32, 0, st>>>(attn1, attn2, rows, N, p, w_cls, w_aff, nullptr, nullptr, 0, nullptr, nullptr, 0, partials);
   }
   if (int e = acr::check_launch("consistency_rows_kernel")) return e;
   consistency_finish_kernel<<<1, 1024, 0, st>>>(partials, rows, N, 1.0 / cnt_cls, 1.0 / cnt_aff, loss2);

@@ -215,6 +215,38 @@ class _StackViews(torch.autograd.Function):
         return (None,) + tuple(g[:, l] for l in range(ctx.n))
 
 
+class _StackViewsSplit(torch.autograd.Function):
+    """stack_views for a batch that holds the two views back to back ([2B,L,N,N]): returns the two halves as separate
+    autograd outputs (attn1, attn2), still without copying the stack."""
+
+    @staticmethod
+    def forward(ctx, stack, *maps):
+        ctx.n = len(maps)
+        ctx.set_materialize_grads(False)
+        B = stack.shape[0] // 2
+        return _alias(stack[:B]), _alias(stack[B:])
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        if g1 is None and g2 is None:
+            return (None,) * (ctx.n + 1)
+        # dense-gradient fallback (e.g. the reference's inline loss): one concatenation per step
+        if g1 is None:
+            g1 = torch.zeros_like(g2)
+        if g2 is None:
+            g2 = torch.zeros_like(g1)
+        g = torch.cat([g1, g2], dim=0)
+        return (None,) + tuple(g[:, l] for l in range(ctx.n))
+
+
+def stack_views_split(stack, maps, states=None):
+    a1, a2 = _StackViewsSplit.apply(stack, *maps)
+    if states is not None:
+        a1._acr_states = a2._acr_states = list(states)
+        a1._acr_half, a2._acr_half = 0, 1
+    return a1, a2
+
+
 def stack_views(stack, maps, states=None):
     out = _StackViews.apply(stack, *maps)
     if states is not None:
@@ -225,16 +257,21 @@ def stack_views(stack, maps, states=None):
 # ----------------------------------------------------------------------------------------------
 # (a7) consistency loss
 # ----------------------------------------------------------------------------------------------
-def consistency_codes(attn1, attn2, p):
-    """loss2 plus the gradient as SIGN CODES: uint8 [B,L,N,ld] (ld = N padded to 128), 0x00 / 0x3F (+) / 0xBF (-)."""
+def consistency_codes(attn1, attn2, p, one_buffer=False):
+    """loss2 plus the gradient as SIGN CODES: uint8 [B,L,N,ld] (ld = N padded to 128), 0x00 / 0x3F (+) / 0xBF (-).
+    one_buffer: c1/c2 are the two halves of a single [2B,L,N,ld] tensor (views batched through the trunk together)."""
     _need_cuda(attn1, attn2)
     B, L, N, _ = attn1.shape
     a1 = attn1.contiguous().float()
     a2 = attn2.contiguous().float()
     ld = (N + 127) // 128 * 128
     loss2 = torch.empty(2, device=a1.device, dtype=torch.float32)
-    c1 = torch.empty(B, L, N, ld, device=a1.device, dtype=torch.uint8)
-    c2 = torch.empty(B, L, N, ld, device=a1.device, dtype=torch.uint8)
+    if one_buffer:
+        c = torch.empty(2 * B, L, N, ld, device=a1.device, dtype=torch.uint8)
+        c1, c2 = c[:B], c[B:]
+    else:
+        c1 = torch.empty(B, L, N, ld, device=a1.device, dtype=torch.uint8)
+        c2 = torch.empty(B, L, N, ld, device=a1.device, dtype=torch.uint8)
     wsb = _lib.lib().acr_consistency_workspace(B, L, N)
     ws = torch.empty(wsb, device=a1.device, dtype=torch.uint8)
     _call("acr_consistency_fwd_bwd", 2, _p(a1), _p(a2), B, L, N, int(p), 1.0, 1.0, _p(loss2), None, None, 0,
@@ -294,9 +331,14 @@ class _ConsistencyLossCodes(torch.autograd.Function):
     @staticmethod
     def forward(ctx, attn1, attn2, p, alpha, states1, states2):
         B, L, N, _ = attn1.shape
-        loss2, c1, c2 = consistency_codes(attn1.detach(), attn2.detach(), p)
-        ctx.codes = (c1, c2)
-        ctx.states = (states1, states2)
+        merged = states1 is states2 or (len(states1) == len(states2) and all(a is b for a, b in zip(states1, states2)))
+        loss2, c1, c2 = consistency_codes(attn1.detach(), attn2.detach(), p, merged)
+        if merged:      # both views went through the trunk as one batch of 2B: c1/c2 are the halves of one buffer
+            ctx.codes = (c1._base if c1._base is not None else c1,)
+            ctx.states = (states1,)
+        else:
+            ctx.codes = (c1, c2)
+            ctx.states = (states1, states2)
         ctx.w = (alpha / (B * L * (N - 1)), alpha / (B * L * float(N - 1) ** 2))
         total = alpha * (loss2[0] + loss2[1])
         ctx.mark_non_differentiable(loss2)
