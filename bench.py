@@ -192,7 +192,8 @@ def run_ours(args):
         e2e = imgs / (ms_e2e / 1e3)
         # dominant kernel group: the fused attention backward (one C-ABI call per block and view)
         dom = prof["kernels"].get("acr_attn_bwd_bf16" if precision == "bf16" else "acr_attn_bwd_f32", None)
-        flops_bwd = 8.0 * B * HEADS * N_TOK * N_TOK * HD            # algorithmic, recompute not counted
+        # algorithmic FLOPs of one call (both views of the B images go through the trunk as one batch of 2B); recompute not counted
+        flops_bwd = 8.0 * (2 * B) * HEADS * N_TOK * N_TOK * HD
         roof = None
         if dom and dom["calls"]:
             avg_ms = dom["ms"] / dom["calls"]

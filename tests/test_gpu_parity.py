@@ -180,7 +180,7 @@ def _train_step_check(dev, name, backbone, precision, tol, inline_loss=False):
             # so element-wise agreement of a 128-element slice is checked by direction (cosine) + the norm above
             a_, b_ = t2n(sl).ravel().astype(np.float64), g["grad_slice/" + k].ravel().astype(np.float64)
             cos = float(a_ @ b_ / (np.linalg.norm(a_) * np.linalg.norm(b_) + 1e-30))
-            assert cos > 0.97, (k, cos)
+            assert cos > 0.95, (k, cos)
     # parameters the reference leaves without gradient
     assert params["pretrained.model.norm.weight"].grad is None and params["pretrained.model.bkg_token"].grad is None
 
