@@ -28,6 +28,7 @@
 #include "common.cuh"
 #include <cmath>
 #include <vector>
+#include <type_traits>
 
 namespace {
 
@@ -35,6 +36,11 @@ constexpr int D5 = 5;          // feature dimension
 constexpr int D6 = D5 + 1;
 
 struct Key { uint32_t a, b, c; };   // k0|k1<<16, k2|k3<<16, k4
+
+template <typename T>
+__device__ __forceinline__ T* img_ptr(T* base, size_t stride_bytes, int n) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(const_cast<typename std::remove_const<T>::type*>(base)) + stride_bytes * n);
+}
 
 struct Scales { float s[D5]; };
 
@@ -61,10 +67,13 @@ __device__ __forceinline__ uint32_t key_hash(const short* k) {
 // Step 1: per pixel, lattice coordinates -> 6 candidate keys + barycentric weights.
 __global__ void __launch_bounds__(256)
 lattice_embed_kernel(const float* __restrict__ image, int H, int W, int HWpad, float sigmargb, float sigmaxy, Scales sc,
-                     Key* __restrict__ ckey, float* __restrict__ bary_out) {
+                     Key* __restrict__ ckey, float* __restrict__ bary_out, size_t ws) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int HW = H * W;
   if (idx >= HWpad) return;
+  image += (size_t)blockIdx.z * 3 * HW;
+  ckey = img_ptr(ckey, ws, blockIdx.z);
+  bary_out = img_ptr(bary_out, ws, blockIdx.z);
   const int px = idx % W, py = idx / W;
   float f[D5];
   if (idx < HW) {
@@ -154,9 +163,11 @@ lattice_embed_kernel(const float* __restrict__ image, int H, int W, int HWpad, f
 // Step 2: insert every candidate; the CAS winner of a slot becomes the representative and draws a dense id.
 __global__ void __launch_bounds__(256)
 lattice_insert_kernel(const Key* __restrict__ ckey, int ncand, int* __restrict__ table, uint32_t mask,
-                      int* __restrict__ rep, int* __restrict__ vid, int* __restrict__ vcand, int* __restrict__ counter) {
+                      int* __restrict__ rep, int* __restrict__ vid, int* __restrict__ vcand, int* __restrict__ counter, size_t ws) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncand) return;
+  ckey = img_ptr(ckey, ws, blockIdx.z); table = img_ptr(table, ws, blockIdx.z); rep = img_ptr(rep, ws, blockIdx.z);
+  vid = img_ptr(vid, ws, blockIdx.z); vcand = img_ptr(vcand, ws, blockIdx.z); counter = img_ptr(counter, ws, blockIdx.z);
   const Key k = ckey[c];
   short ks[D5];
   unpack_key(k, ks);
@@ -180,9 +191,10 @@ lattice_insert_kernel(const Key* __restrict__ ckey, int ncand, int* __restrict__
 
 // Step 3: candidate -> (vertex id + 1).
 __global__ void __launch_bounds__(256)
-lattice_offset_kernel(int* __restrict__ rep, const int* __restrict__ vid, int ncand) {
+lattice_offset_kernel(int* __restrict__ rep, const int* __restrict__ vid, int ncand, size_t ws) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncand) return;
+  rep = img_ptr(rep, ws, blockIdx.z); vid = img_ptr(vid, ws, blockIdx.z);
   rep[c] = vid[rep[c]] + 1;
 }
 
@@ -202,7 +214,9 @@ __device__ __forceinline__ int lattice_find(const Key* __restrict__ ckey, const 
 __global__ void __launch_bounds__(256)
 lattice_neighbors_kernel(const Key* __restrict__ ckey, const int* __restrict__ table, uint32_t mask,
                          const int* __restrict__ vid, const int* __restrict__ vcand, const int* __restrict__ counter,
-                         int stride, int2* __restrict__ nbr) {
+                         int stride, int2* __restrict__ nbr, size_t ws) {
+  ckey = img_ptr(ckey, ws, blockIdx.z); table = img_ptr(table, ws, blockIdx.z); vid = img_ptr(vid, ws, blockIdx.z);
+  vcand = img_ptr(vcand, ws, blockIdx.z); counter = img_ptr(counter, ws, blockIdx.z); nbr = img_ptr(nbr, ws, blockIdx.z);
   const int M = *counter;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int v = t / D6, j = t % D6;
@@ -221,7 +235,8 @@ lattice_neighbors_kernel(const Key* __restrict__ ckey, const int* __restrict__ t
 }
 
 __global__ void __launch_bounds__(256)
-zero_values_kernel(float* __restrict__ v0, float* __restrict__ v1, const int* __restrict__ counter, int K) {
+zero_values_kernel(float* __restrict__ v0, float* __restrict__ v1, const int* __restrict__ counter, int K, size_t ws) {
+  v0 = img_ptr(v0, ws, blockIdx.z); v1 = img_ptr(v1, ws, blockIdx.z); counter = img_ptr(counter, ws, blockIdx.z);
   const long long n = ((long long)(*counter) + 1) * K;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     v0[i] = 0.f;
@@ -235,8 +250,10 @@ constexpr int kPixTile = 32;
 // vertex-major value updates are coalesced.
 __global__ void __launch_bounds__(256)
 lattice_splat_kernel(const float* __restrict__ in, int K, int HW, const int* __restrict__ offs,
-                     const float* __restrict__ bary, float* __restrict__ values) {
+                     const float* __restrict__ bary, float* __restrict__ values, size_t ws) {
   extern __shared__ float tile[];   // [kPixTile][K+1]
+  in += (size_t)blockIdx.z * K * HW;
+  offs = img_ptr(offs, ws, blockIdx.z); bary = img_ptr(bary, ws, blockIdx.z); values = img_ptr(values, ws, blockIdx.z);
   const int p0 = blockIdx.x * kPixTile;
   const int KP = K + 1;
   for (int e = threadIdx.x; e < K * kPixTile; e += blockDim.x) {
@@ -261,7 +278,9 @@ lattice_splat_kernel(const float* __restrict__ in, int K, int HW, const int* __r
 // One blur pass along axis j: new = old + 0.5 * (old[n1] + old[n2]).  One thread per (vertex, plane).
 __global__ void __launch_bounds__(256)
 lattice_blur_kernel(const float* __restrict__ oldv, float* __restrict__ newv, const int2* __restrict__ nbr,
-                    const int* __restrict__ counter, int K) {
+                    const int* __restrict__ counter, int K, size_t ws) {
+  oldv = img_ptr(oldv, ws, blockIdx.z); newv = img_ptr(newv, ws, blockIdx.z); nbr = img_ptr(nbr, ws, blockIdx.z);
+  counter = img_ptr(counter, ws, blockIdx.z);
   const long long M = *counter;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < M * K; t += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(t / K), k = (int)(t % K);
@@ -273,8 +292,10 @@ lattice_blur_kernel(const float* __restrict__ oldv, float* __restrict__ newv, co
 
 __global__ void __launch_bounds__(256)
 lattice_slice_kernel(const float* __restrict__ values, int K, int HW, const int* __restrict__ offs,
-                     const float* __restrict__ bary, float alpha, float* __restrict__ out) {
+                     const float* __restrict__ bary, float alpha, float* __restrict__ out, size_t ws) {
   extern __shared__ float tile[];   // [kPixTile][K+1]
+  out += (size_t)blockIdx.z * K * HW;
+  values = img_ptr(values, ws, blockIdx.z); offs = img_ptr(offs, ws, blockIdx.z); bary = img_ptr(bary, ws, blockIdx.z);
   const int p0 = blockIdx.x * kPixTile;
   const int KP = K + 1;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -332,9 +353,12 @@ Carve carve(void* base, int K, int H, int W) {
 
 }  // namespace
 
+// Images are filtered kBatch at a time (grid.z = image); each has its own lattice region in the workspace.
+constexpr int kBilateralBatch = 8;
+
 extern "C" size_t acr_bilateral_workspace(int N, int K, int H, int W) {
   if (N <= 0 || K <= 0 || H <= 0 || W <= 0) return 0;
-  return carve(nullptr, K, H, W).total;   // images are processed one after another and share it
+  return carve(nullptr, K, H, W).total * (size_t)(N < kBilateralBatch ? N : kBilateralBatch);
 }
 
 extern "C" int acr_bilateral_batch(const float* images, const float* ins, float* outs,
@@ -346,7 +370,8 @@ extern "C" int acr_bilateral_batch(const float* images, const float* ins, float*
   ACR_REQUIRE((long long)H * W * D6 < (1ll << 28), ACR_E_INVAL, "acr_bilateral_batch: image too large");
   ACR_REQUIRE(((uintptr_t)workspace & 255) == 0, ACR_E_ALIGN, "acr_bilateral_batch: workspace not 256-byte aligned");
   const Carve c = carve(workspace, K, H, W);
-  ACR_REQUIRE(workspace_bytes >= c.total, ACR_E_NOMEM, "acr_bilateral_batch: workspace too small (%zu < %zu)", workspace_bytes, c.total);
+  ACR_REQUIRE(workspace_bytes >= acr_bilateral_workspace(N, K, H, W), ACR_E_NOMEM, "acr_bilateral_batch: workspace too small (%zu < %zu)",
+              workspace_bytes, acr_bilateral_workspace(N, K, H, W));
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W, HWpad = (HW + 3) / 4 * 4, nc = HWpad * D6;
 
@@ -357,36 +382,40 @@ extern "C" int acr_bilateral_batch(const float* images, const float* ins, float*
 
   const size_t smem = (size_t)kPixTile * (K + 1) * sizeof(float);
   ACR_REQUIRE(smem <= 48 * 1024, ACR_E_INVAL, "acr_bilateral_batch: K=%d too large", K);
-  std::vector<int> msizes;
-  for (int n = 0; n < N; ++n) {
-    const float* img = images + (size_t)n * 3 * HW;
-    const float* in = ins + (size_t)n * K * HW;
-    float* out = outs + (size_t)n * K * HW;
-    ACR_CUDA(cudaMemsetAsync(c.table, 0xff, (size_t)c.cap * sizeof(int), st));
-    ACR_CUDA(cudaMemsetAsync(c.counter, 0, sizeof(int), st));
-    lattice_embed_kernel<<<(HWpad + 255) / 256, 256, 0, st>>>(img, H, W, HWpad, sigmargb, sigmaxy, sc, c.ckey, c.bary);
+  const size_t ws = c.total;
+  for (int n0 = 0; n0 < N; n0 += kBilateralBatch) {
+    const int nb = (N - n0 < kBilateralBatch) ? N - n0 : kBilateralBatch;
+    const float* img = images + (size_t)n0 * 3 * HW;
+    const float* in = ins + (size_t)n0 * K * HW;
+    float* out = outs + (size_t)n0 * K * HW;
+    for (int i = 0; i < nb; ++i) {
+      ACR_CUDA(cudaMemsetAsync((char*)c.table + ws * i, 0xff, (size_t)c.cap * sizeof(int), st));
+      ACR_CUDA(cudaMemsetAsync((char*)c.counter + ws * i, 0, sizeof(int), st));
+    }
+    lattice_embed_kernel<<<dim3((HWpad + 255) / 256, 1, nb), 256, 0, st>>>(img, H, W, HWpad, sigmargb, sigmaxy, sc, c.ckey, c.bary, ws);
     if (int e = acr::check_launch("lattice_embed_kernel")) return e;
-    lattice_insert_kernel<<<(nc + 255) / 256, 256, 0, st>>>(c.ckey, nc, c.table, c.cap - 1, c.rep, c.vid, c.vcand, c.counter);
+    lattice_insert_kernel<<<dim3((nc + 255) / 256, 1, nb), 256, 0, st>>>(c.ckey, nc, c.table, c.cap - 1, c.rep, c.vid, c.vcand, c.counter, ws);
     if (int e = acr::check_launch("lattice_insert_kernel")) return e;
-    lattice_neighbors_kernel<<<(nc * D6 + 255) / 256, 256, 0, st>>>(c.ckey, c.table, c.cap - 1, c.vid, c.vcand, c.counter, nc, c.nbr);
+    lattice_neighbors_kernel<<<dim3((nc * D6 + 255) / 256, 1, nb), 256, 0, st>>>(c.ckey, c.table, c.cap - 1, c.vid, c.vcand, c.counter, nc, c.nbr, ws);
     if (int e = acr::check_launch("lattice_neighbors_kernel")) return e;
-    lattice_offset_kernel<<<(nc + 255) / 256, 256, 0, st>>>(c.rep, c.vid, nc);
+    lattice_offset_kernel<<<dim3((nc + 255) / 256, 1, nb), 256, 0, st>>>(c.rep, c.vid, nc, ws);
     if (int e = acr::check_launch("lattice_offset_kernel")) return e;
-    zero_values_kernel<<<148 * 8, 256, 0, st>>>(c.val0, c.val1, c.counter, K);
+    zero_values_kernel<<<dim3(148, 1, nb), 256, 0, st>>>(c.val0, c.val1, c.counter, K, ws);
     if (int e = acr::check_launch("zero_values_kernel")) return e;
-    lattice_splat_kernel<<<(HW + kPixTile - 1) / kPixTile, 256, smem, st>>>(in, K, HW, c.rep, c.bary, c.val0);
+    lattice_splat_kernel<<<dim3((HW + kPixTile - 1) / kPixTile, 1, nb), 256, smem, st>>>(in, K, HW, c.rep, c.bary, c.val0, ws);
     if (int e = acr::check_launch("lattice_splat_kernel")) return e;
     float* cur = c.val0;
     float* nxt = c.val1;
     for (int j = 0; j < D6; ++j) {
-      lattice_blur_kernel<<<148 * 8, 256, 0, st>>>(cur, nxt, c.nbr + (size_t)j * nc, c.counter, K);
+      lattice_blur_kernel<<<dim3(148, 1, nb), 256, 0, st>>>(cur, nxt, c.nbr + (size_t)j * nc, c.counter, K, ws);
       if (int e = acr::check_launch("lattice_blur_kernel")) return e;
       float* t = cur; cur = nxt; nxt = t;
     }
-    lattice_slice_kernel<<<(HW + kPixTile - 1) / kPixTile, 256, smem, st>>>(cur, K, HW, c.rep, c.bary, alpha, out);
+    lattice_slice_kernel<<<dim3((HW + kPixTile - 1) / kPixTile, 1, nb), 256, smem, st>>>(cur, K, HW, c.rep, c.bary, alpha, out, ws);
     if (int e = acr::check_launch("lattice_slice_kernel")) return e;
     if (lattice_size_host) {
-      ACR_CUDA(cudaMemcpyAsync(lattice_size_host + n, c.counter, sizeof(int), cudaMemcpyDeviceToHost, st));
+      for (int i = 0; i < nb; ++i)
+        ACR_CUDA(cudaMemcpyAsync(lattice_size_host + n0 + i, (char*)c.counter + ws * i, sizeof(int), cudaMemcpyDeviceToHost, st));
       ACR_CUDA(cudaStreamSynchronize(st));
     }
   }

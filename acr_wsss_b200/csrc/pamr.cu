@@ -10,6 +10,7 @@
 // dilations are concatenated in list order (pamr.py:55); borders replicate (pamr.py:51).
 // Bandwidth-bound: algorithmic bytes = HW(4K + 32D) for step 2 and HW(32D + 8C) per iteration.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -110,14 +111,15 @@ pamr_affinity_kernel(const float* __restrict__ x, int K, int H, int W, Dil dil, 
 }
 
 // One thread per pixel and channel group.  grid (ceil(W/256), H, B*groups).
-template <int CG>
+template <int CG, int TW>
 __global__ void __launch_bounds__(256)
 pamr_iter_kernel(const float* __restrict__ wgt, const float* __restrict__ min_, float* __restrict__ mout,
                  int C, int H, int W, Dil dil, int groups) {
-  const int px = blockIdx.x * blockDim.x + threadIdx.x;
-  const int py = blockIdx.y;
+  // block = TW x (256/TW) pixels
+  const int px = blockIdx.x * TW + (threadIdx.x % TW);
+  const int py = blockIdx.y * (256 / TW) + (threadIdx.x / TW);
   const int b = blockIdx.z / groups, g = blockIdx.z % groups;
-  if (px >= W) return;
+  if (px >= W || py >= H) return;
   const long long HW = (long long)H * W;
   const int nn = 8 * dil.n;
   const float* wp = wgt + (long long)b * nn * HW + (long long)py * W + px;
@@ -147,12 +149,118 @@ pamr_iter_kernel(const float* __restrict__ wgt, const float* __restrict__ min_, 
     if (c0 + c < C) op[c * HW] = acc[c];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path (W % 4 == 0).
+//
+// pamr_affinity_reg_kernel<ND>: one thread per pixel, the 9*ND samples of a channel and the 8*ND logits live in
+// registers; each weight plane is written exactly once (the generic kernel above re-reads / re-writes them 7 times).
+//
+// (Round-1 experiments with 4-pixel "quad" threads and with channel-outer / register-resident weights were 1.1-5x SLOWER
+// than the scalar tap-outer kernel above -- low occupancy and L1 thrashing across channel planes; see DESIGN.md.  The
+// iteration is bound by L1/L2 gather bandwidth (48 taps per output), not HBM; a shared-memory tiled version is the next step.)
+template <int ND>
+__global__ void __launch_bounds__(128)
+pamr_affinity_reg_kernel(const float* __restrict__ x, int K, int H, int W, Dil dil, float* __restrict__ wgt) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  const int py = blockIdx.y;
+  const int b = blockIdx.z;
+  if (px >= W) return;
+  const long long HW = (long long)H * W;
+  constexpr int NN = 8 * ND;
+  float aff[NN];
+#pragma unroll
+  for (int n = 0; n < NN; ++n) aff[n] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const float* img = x + ((long long)b * K + k) * HW;
+    float v[9 * ND];
+    float sum = 0.f;
+#pragma unroll
+    for (int di = 0; di < ND; ++di) {
+      const int d = dil.d[di];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int yy = clampi(py + (t / 3 - 1) * d, 0, H - 1), xx = clampi(px + (t % 3 - 1) * d, 0, W - 1);
+        v[di * 9 + t] = __ldg(img + (long long)yy * W + xx);
+        sum += v[di * 9 + t];
+      }
+    }
+    const float mean = sum / (float)(9 * ND);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9 * ND; ++i) { const float dv = v[i] - mean; ss += dv * dv; }
+    const float sd = sqrtf(ss / (float)(9 * ND - 1));
+    const float inv = 1.f / (1e-8f + 0.1f * sd);
+    const float xc = v[4];
+#pragma unroll
+    for (int di = 0; di < ND; ++di)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        if (t == 4) continue;
+        const int n = di * 8 + (t < 4 ? t : t - 1);
+        aff[n] += -fabsf(xc - v[di * 9 + t]) * inv;
+      }
+  }
+  const float invK = 1.f / (float)K;
+  float m = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < NN; ++n) { aff[n] *= invK; m = fmaxf(m, aff[n]); }
+  float ssum = 0.f;
+#pragma unroll
+  for (int n = 0; n < NN; ++n) { aff[n] = expf(aff[n] - m); ssum += aff[n]; }
+  const float invs = 1.f / ssum;
+  float* wp = wgt + (long long)b * NN * HW + (long long)py * W + px;
+#pragma unroll
+  for (int n = 0; n < NN; ++n) wp[(long long)n * HW] = aff[n] * invs;
+}
+
+template <int ND>
+int launch_affinity_reg(const float* x, int B, int K, int H, int W, const Dil& dil, float* wgt, cudaStream_t st) {
+  dim3 grid((W + 127) / 128, H, B);
+  pamr_affinity_reg_kernel<ND><<<grid, 128, 0, st>>>(x, K, H, W, dil, wgt);
+  return acr::check_launch("pamr_affinity_reg_kernel");
+}
+
+
+template <int CG, int TW>
+int launch_iter(const float* wgt, const float* cur, float* dst, int B, int C, int H, int W, const Dil& dil, cudaStream_t st) {
+  const int groups = (C + CG - 1) / CG;
+  dim3 grid((W + TW - 1) / TW, (H + 256 / TW - 1) / (256 / TW), B * groups);
+  pamr_iter_kernel<CG, TW><<<grid, 256, 0, st>>>(wgt, cur, dst, C, H, W, dil, groups);
+  return acr::check_launch("pamr_iter_kernel");
+}
+
+int pamr_iterate(const float* wgt, float* ping, float* pong, float* out, int B, int C, int H, int W, const Dil& dil, int num_iter,
+                 cudaStream_t st) {
+  static int cfg = -1;
+  if (cfg < 0) { const char* e = getenv("ACR_PAMR_CFG"); cfg = e ? atoi(e) : 7; }   // 7 = measured best on B200 (scripts/pamr_sweep.sh)
+  const float* cur = ping;
+  for (int it = 0; it < num_iter; ++it) {
+    float* dst = (it == num_iter - 1) ? out : ((cur == ping) ? pong : ping);
+    int e = 0;
+    switch (cfg) {
+      case 1: e = launch_iter<4, 256>(wgt, cur, dst, B, C, H, W, dil, st); break;
+      case 2: e = launch_iter<8, 64>(wgt, cur, dst, B, C, H, W, dil, st); break;
+      case 3: e = launch_iter<4, 64>(wgt, cur, dst, B, C, H, W, dil, st); break;
+      case 4: e = launch_iter<8, 32>(wgt, cur, dst, B, C, H, W, dil, st); break;
+      case 5: e = launch_iter<4, 32>(wgt, cur, dst, B, C, H, W, dil, st); break;
+      case 6: e = launch_iter<2, 64>(wgt, cur, dst, B, C, H, W, dil, st); break;
+      case 7: e = launch_iter<3, 32>(wgt, cur, dst, B, C, H, W, dil, st); break;
+      default: e = launch_iter<8, 256>(wgt, cur, dst, B, C, H, W, dil, st); break;
+    }
+    if (e) return e;
+    cur = dst;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" size_t acr_pamr_workspace(int B, int K, int C, int H, int W, int nd) {
   if (B <= 0 || K <= 0 || C <= 0 || H <= 0 || W <= 0 || nd <= 0) return 0;
   const size_t hw = (size_t)H * W;
-  return acr::align_up((size_t)B * 8 * nd * hw * sizeof(float), 256) + 2 * acr::align_up((size_t)B * C * hw * sizeof(float), 256);
+  // +256: the quad loads of the fast path may touch up to 12 bytes past the last mask row
+  return acr::align_up((size_t)B * 8 * nd * hw * sizeof(float), 256) + 2 * acr::align_up((size_t)B * C * hw * sizeof(float), 256) + 256;
 }
 
 extern "C" int acr_pamr_fwd(const float* x, const float* mask, int B, int K, int C, int H, int W, int mh, int mw,
@@ -187,20 +295,26 @@ extern "C" int acr_pamr_fwd(const float* x, const float* mask, int B, int K, int
     if (int e = acr::check_launch("pamr_upsample_kernel")) return e;
   }
   if (num_iter == 0) return 0;
+  const bool fast = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (fast) {
+    int e = 0;
+    switch (nd) {
+      case 1: e = launch_affinity_reg<1>(x, B, K, H, W, dil, wgt, st); break;
+      case 2: e = launch_affinity_reg<2>(x, B, K, H, W, dil, wgt, st); break;
+      case 3: e = launch_affinity_reg<3>(x, B, K, H, W, dil, wgt, st); break;
+      case 4: e = launch_affinity_reg<4>(x, B, K, H, W, dil, wgt, st); break;
+      case 5: e = launch_affinity_reg<5>(x, B, K, H, W, dil, wgt, st); break;
+      case 6: e = launch_affinity_reg<6>(x, B, K, H, W, dil, wgt, st); break;
+      case 7: e = launch_affinity_reg<7>(x, B, K, H, W, dil, wgt, st); break;
+      default: e = launch_affinity_reg<8>(x, B, K, H, W, dil, wgt, st); break;
+    }
+    if (e) return e;
+    return pamr_iterate(wgt, ping, pong, out, B, C, H, W, dil, num_iter, st);
+  }
   {
     dim3 grid((W + 255) / 256, H, B);
     pamr_affinity_kernel<<<grid, 256, 0, st>>>(x, K, H, W, dil, wgt);
     if (int e = acr::check_launch("pamr_affinity_kernel")) return e;
   }
-  constexpr int CG = 8;
-  const int groups = (C + CG - 1) / CG;
-  const float* cur = ping;
-  for (int it = 0; it < num_iter; ++it) {
-    float* dst = (it == num_iter - 1) ? out : ((cur == ping) ? pong : ping);
-    dim3 grid((W + 255) / 256, H, B * groups);
-    pamr_iter_kernel<CG><<<grid, 256, 0, st>>>(wgt, cur, dst, C, H, W, dil, groups);
-    if (int e = acr::check_launch("pamr_iter_kernel")) return e;
-    cur = dst;
-  }
-  return 0;
+  return pamr_iterate(wgt, ping, pong, out, B, C, H, W, dil, num_iter, st);
 }
