@@ -43,12 +43,13 @@ def pseudo_label(cam_dict, num_classes, threshold):
 
 
 def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, getam_func="cam_grad_s",
-                    aff=True, t=1, normalize=False):
+                    aff=True, t=1, normalize=False, truncate_backward=True):
     """One image of the infer_cam.py loop body (:145-215).
 
     img [1,3,h,w] (normalised), label [1,C] multi-hot, out_size = (rows, cols) of the original image (the
     reference calls these W,H at infer_cam.py:136).  Returns (cam_dict, patch_cam_dict, norm_cam [C,rows,cols])
     with {class_index: float32 [rows,cols]} dicts as saved by np.save at :227-228.
+    truncate_backward: stop each per-class backward at block `start_layer` (identical GETAM).
     """
     assert img.shape[0] == 1, "the reference infers one image at a time (infer_cam.py:122)"
     C = label.shape[1]
@@ -74,8 +75,11 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
             output = cls_pred[0, :]
             rows0 = []
             for ci in present:
-                model.zero_grad()
-                output[ci].backward(retain_graph=True)          # one_hot * output, infer_cam.py:173-179
+                if truncate_backward:
+                    model.backward_for_getam(output[ci], start_layer)
+                else:
+                    model.zero_grad()
+                    output[ci].backward(retain_graph=True)      # one_hot * output, infer_cam.py:173-179
                 cam, _, _ = model.getam(0, start_layer=start_layer, func=getam_func)
                 rows0.append(cam[0])
             cam_matrix = torch.zeros(C, rows, cols, device=img.device)

@@ -188,7 +188,9 @@ class VisionTransformer(nn.Module):
         cls_tokens = self.cls_token.expand(b, -1, -1)
         x = torch.cat((cls_tokens.to(x.dtype), x), dim=1)
         x = x + pos_embed.to(x.dtype)
+        self._block_in = []            # input of every block (references): lets GETAM stop its backward at start_layer
         for blk in self.blocks:
+            self._block_in.append(x)
             x = blk(x)
         if last_block_out is not None:
             last_block_out.append(x)
@@ -323,15 +325,22 @@ class ACR(nn.Module):
         blocks = self.pretrained.model.blocks
         skip = 2 if self.cur_backbone == "deitb16_distil_384" else 1
         attn_list = [blk.attn.attn_mean for blk in blocks]
-        p0 = torch.stack([blk.attn.get_attn_row0()[batch] for blk in blocks])              # [L,H,N]
-        g0 = torch.stack([blk.attn.get_attn_gradients_row0()[batch] for blk in blocks])    # [L,H,N]
-        cls_cam, rows = ops.getam_row0(p0, g0, start_layer, func, skip, want_rows=True)
+        used = blocks[start_layer:]          # only these reach the result (DPT/ACR.py:208-209), so only they need a gradient
+        p0 = torch.stack([blk.attn.get_attn_row0()[batch] for blk in used])              # [L',H,N]
+        g0 = torch.stack([blk.attn.get_attn_gradients_row0()[batch] for blk in used])    # [L',H,N]
+        cls_cam, rows = ops.getam_row0(p0, g0, 0, func, skip, want_rows=True)
         if full:
             cam_list = [_getam_full(blk.attn.get_attn()[batch], blk.attn.get_attn_gradients()[batch], func).unsqueeze(0)
-                        for blk in blocks]
+                        for blk in used]
         else:
-            cam_list = [rows[l].view(1, 1, -1) for l in range(len(blocks))]
-        return cls_cam, attn_list, cam_list[start_layer:]
+            cam_list = [rows[l].view(1, 1, -1) for l in range(len(used))]
+        return cls_cam, attn_list, cam_list
+
+    def backward_for_getam(self, logit, start_layer=0):
+        """Gradient pass that feeds getam().  The reference calls logit.backward(retain_graph=True) through the whole
+        model and all parameters (infer_cam.py:173-179); only dP of blocks >= start_layer is ever read, so this stops
+        at the input of block `start_layer` and accumulates no parameter gradients (same GETAM result)."""
+        torch.autograd.grad(logit, self.pretrained.model._block_in[start_layer], retain_graph=True)
 
 
 def _getam_full(cam, grad, func):

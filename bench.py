@@ -185,6 +185,23 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # secondary metric: CAM inference (BASELINE.json configs[0]): forward_cam + GETAM over 3 present classes + affinity
+    # refinement, 2 flips, one 448x448 image at a time, images sharded per rank, no collective
+    cam = None
+    if not args.no_cam:
+        from acr_wsss_b200 import infer_cam_image
+        model.eval()
+        model.set_capture_grad(True)
+        for p in model.parameters():
+            p.grad = None
+        img1 = synth.images(1, S, seed=100 + rank).to(dev)
+        lab1 = synth.labels(1, C, present=(3, 7, 14)).to(dev)
+        n_img = 3
+        infer_cam_image(model, img1, lab1, (S, S), start_layer=10, getam_func="grad")
+        ms_cam = timed(lambda: infer_cam_image(model, img1, lab1, (S, S), start_layer=10, getam_func="grad"), n_img)
+        cam = {"metric": "cam_infer_imgs_per_sec", "value": n_img * world / (ms_cam / 1e3), "unit": "img/s", "ms_per_image": ms_cam / n_img,
+               "workload": "infer_cam.py: ViT-B/16 448x448, 2 flips, 3 present classes, GETAM start_layer=10 + affinity refine, results copied to host"}
+
     if rank == 0:
         pk = peaks()
         imgs = B * world * args.steps
@@ -210,7 +227,7 @@ def run_ours(args):
                        "precision": precision, "l2": "inputs larger than L2: each step streams 2 x 237 MB attention stacks + gradients"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(img_h.numel() * 4 + lab_h.numel() * 4) * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cam_infer": cam,
         }
         if world == 1 and not args.no_cpu_baseline:
             v, sec, cores = cpu_reference_step_time(2, 1)
@@ -230,6 +247,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cam", action="store_true", help="skip the secondary CAM-inference measurement")
     ap.add_argument("--profile-range", action="store_true", help="wrap one extra step in cudaProfilerStart/Stop (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -232,7 +232,7 @@ def test_affinity_refine_matches_oracle(dev, t, normalize):
     assert rel_err(t2n(got1), t2n(ref[..., 0])) < 1e-4
 
 
-def _infer_check(dev, name, precision, tol):
+def _infer_check(dev, name, precision, tol, truncate=True):
     from acr_wsss_b200 import infer_cam_image, pseudo_label, synth
     g = load_golden(name)
     C, S = int(g["C"]), int(g["S"])
@@ -243,7 +243,8 @@ def _infer_check(dev, name, precision, tol):
     label = synth.labels(1, C, present=present).to(dev)
     cam_dict, patch_dict, norm_cam = infer_cam_image(m, img, label, tuple(int(v) for v in g["out_size"]),
                                                      scales=tuple(float(s) for s in g["scales"]),
-                                                     start_layer=int(g["start_layer"]), getam_func=str(g["func"]))
+                                                     start_layer=int(g["start_layer"]), getam_func=str(g["func"]),
+                                                     truncate_backward=truncate)
     assert sorted(cam_dict) == present and cam_dict[present[0]].dtype == np.float32
     assert rel_err(np.stack([cam_dict[c] for c in present]), g["norm_cam"]) < tol
     assert rel_err(np.stack([patch_dict[c] for c in present]), g["patch_norm_cam"]) < tol
@@ -267,12 +268,34 @@ def test_infer_cam_fp32_448(dev):
         m.zero_grad()
         cls_pred[0, ci].backward(retain_graph=True)
         cam, attn_list, cam_list = m.getam(0, start_layer=10, func="grad")
-        assert cam.shape == (1, 784) and len(attn_list) == 12 and len(cam_list) == 2
+        assert cam.shape == (1, 784) and len(attn_list) == 12 and len(cam_list) == 2 and cam_list[0].shape == (1, 1, 785)
         assert rel_err(t2n(cam), g[f"getam_{ci}"]) < FP32_TOL
 
 
 def test_infer_cam_fp32_multiscale(dev):
     _infer_check(dev, "infer_vitb_128_ms.npz", "fp32", FP32_TOL)
+
+
+def test_infer_cam_fp32_multiscale_full_backward(dev):
+    _infer_check(dev, "infer_vitb_128_ms.npz", "fp32", FP32_TOL, truncate=False)
+
+
+def test_infer_cam_bf16_448(dev):
+    # fused path end to end: CAMs within the bf16 tolerance band of the fp32 reference, labels >= 99% (bf16 logits)
+    from acr_wsss_b200 import infer_cam_image, pseudo_label, synth
+    g = load_golden("infer_vitb_448.npz")
+    present = [int(c) for c in g["present"]]
+    m, _ = _build(dev, 20, "vitb", "bf16", 2.0)
+    m32, _ = _build(dev, 20, "vitb", "fp32", 2.0)
+    m.eval(); m32.eval()
+    img = synth.images(1, 448, seed=3).to(dev)
+    label = synth.labels(1, 20, present=present).to(dev)
+    a, _, _ = infer_cam_image(m, img, label, (60, 80), start_layer=10, getam_func="grad")
+    b, _, _ = infer_cam_image(m32, img, label, (60, 80), start_layer=10, getam_func="grad")
+    err = rel_err(np.stack([a[c] for c in present]), np.stack([b[c] for c in present]))
+    assert err < 5 * BF16_TOL, err
+    agree = (pseudo_label(a, 20, 0.4) == pseudo_label(b, 20, 0.4)).mean()
+    assert agree >= 0.98, agree
 
 
 # ------------------------------------------------------------------ (a10) PAMR
