@@ -1,0 +1,212 @@
+// LayerNorm forward / backward around the attention block (the glue either side of a1).
+// Reference: the nn.LayerNorm(eps=1e-6) calls of Block.forward, models/vision_transformer.py:230-233 (:299 for eps).
+//
+// HBM-bound.  Forward reads the fp32 residual stream once and writes the normalised rows directly in the GEMM's
+// operand type (bf16 on the fused path -- no separate cast kernel), plus mean / rstd per row.  Backward is a single
+// pass over (dy, x): one warp per row computes dx with warp-shuffle row reductions while every lane accumulates the
+// d-gamma / d-beta partial sums of the columns it owns in registers; CTAs write one partial row each and a second tiny
+// kernel folds them in a fixed order (deterministic, no atomics).  Stock PyTorch spends 105 us per call in its
+// gamma/beta backward at [12560, 768]; the whole backward here is bounded by ~130 MB of traffic.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+
+template <int VEC, bool OUT_BF16>      // VEC float4 per lane: E = 128 * VEC
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int M, float eps,
+                     void* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+  constexpr int E = 128 * VEC;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * E);
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = __ldg(xr + i * 32 + lane);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mu = acr::warp_sum(s) * (1.f / E);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float a = v[i].x - mu, b = v[i].y - mu, c = v[i].z - mu, d = v[i].w - mu;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rs = rsqrtf(acr::warp_sum(ss) * (1.f / E) + eps);
+  if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+    const float o0 = (v[i].x - mu) * rs * g.x + bb.x, o1 = (v[i].y - mu) * rs * g.y + bb.y;
+    const float o2 = (v[i].z - mu) * rs * g.z + bb.z, o3 = (v[i].w - mu) * rs * g.w + bb.w;
+    if (OUT_BF16) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0);
+      u.y = *reinterpret_cast<uint32_t*>(&p1);
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + row * E)[i * 32 + lane] = u;
+    } else {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * E)[i * 32 + lane] = make_float4(o0, o1, o2, o3);
+    }
+  }
+}
+
+template <int VEC, bool DY_BF16>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, int M, int rows_per_cta,
+                     float* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b) {
+  constexpr int E = 128 * VEC;
+  __shared__ float red[kWarpsPerCta][32 * 4 + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 g[VEC], ag[VEC], ab[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min((long long)M, r0 + rows_per_cta);
+  for (long long row = r0 + warp; row < r1; row += kWarpsPerCta) {
+    const float mu = __ldg(mean + row), rs = __ldg(rstd + row);
+    float4 d[VEC], xh[VEC];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      if (DY_BF16) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + row * E) + i * 32 + lane);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        d[i] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        d[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * E) + i * 32 + lane);
+      }
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * E) + i * 32 + lane);
+      xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
+      ag[i].x += d[i].x * xh[i].x; ag[i].y += d[i].y * xh[i].y; ag[i].z += d[i].z * xh[i].z; ag[i].w += d[i].w * xh[i].w;
+      d[i].x *= g[i].x; d[i].y *= g[i].y; d[i].z *= g[i].z; d[i].w *= g[i].w;       // dy * gamma
+      s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
+    }
+    s1 = acr::warp_sum(s1) * (1.f / E);
+    s2 = acr::warp_sum(s2) * (1.f / E);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float4 o;
+      o.x = rs * (d[i].x - s1 - xh[i].x * s2); o.y = rs * (d[i].y - s1 - xh[i].y * s2);
+      o.z = rs * (d[i].z - s1 - xh[i].z * s2); o.w = rs * (d[i].w - s1 - xh[i].w * s2);
+      reinterpret_cast<float4*>(dx + row * E)[i * 32 + lane] = o;
+    }
+  }
+  // fold the CTA's warps: column-owned partial sums -> one partial row per CTA
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const float4 v = pass ? ab[i] : ag[i];
+      red[warp][lane * 4 + 0] = v.x; red[warp][lane * 4 + 1] = v.y; red[warp][lane * 4 + 2] = v.z; red[warp][lane * 4 + 3] = v.w;
+      __syncthreads();
+      if (warp == 0) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; ++w) {
+          t.x += red[w][lane * 4 + 0]; t.y += red[w][lane * 4 + 1]; t.z += red[w][lane * 4 + 2]; t.w += red[w][lane * 4 + 3];
+        }
+        float* dst = (pass ? part_b : part_g) + (long long)blockIdx.x * E;
+        reinterpret_cast<float4*>(dst)[i * 32 + lane] = t;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_bwd_finish_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b, int nparts, int E,
+                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= E) return;
+  float sg = 0.f, sb = 0.f;
+  for (int p = 0; p < nparts; ++p) { sg += part_g[(long long)p * E + c]; sb += part_b[(long long)p * E + c]; }
+  dgamma[c] = sg;
+  dbeta[c] = sb;
+}
+
+constexpr int kBwdCtas = 296;     // 2 per SM
+
+template <int VEC>
+int launch_fwd(const float* x, const float* gamma, const float* beta, int M, float eps, void* y, int y_bf16, float* mean, float* rstd,
+               cudaStream_t st) {
+  const unsigned grid = (unsigned)((M + kWarpsPerCta - 1) / kWarpsPerCta);
+  if (y_bf16) layernorm_fwd_kernel<VEC, true><<<grid, kWarpsPerCta * 32, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
+  else layernorm_fwd_kernel<VEC, false><<<grid, kWarpsPerCta * 32, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
+  return acr::check_launch("layernorm_fwd_kernel");
+}
+template <int VEC>
+int launch_bwd(const void* dy, int dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
+               float* dx, float* dgamma, float* dbeta, float* parts, cudaStream_t st) {
+  constexpr int E = 128 * VEC;
+  const int ctas = M < kBwdCtas * kWarpsPerCta ? (M + kWarpsPerCta - 1) / kWarpsPerCta : kBwdCtas;
+  const int rows_per_cta = (M + ctas - 1) / ctas;
+  float* pg = parts;
+  float* pb = parts + (size_t)kBwdCtas * E;
+  if (dy_bf16) layernorm_bwd_kernel<VEC, true><<<ctas, kWarpsPerCta * 32, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
+  else layernorm_bwd_kernel<VEC, false><<<ctas, kWarpsPerCta * 32, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
+  if (int e = acr::check_launch("layernorm_bwd_kernel")) return e;
+  layernorm_bwd_finish_kernel<<<(E + 255) / 256, 256, 0, st>>>(pg, pb, ctas, E, dgamma, dbeta);
+  return acr::check_launch("layernorm_bwd_finish_kernel");
+}
+
+}  // namespace
+
+extern "C" size_t acr_layernorm_bwd_workspace(int E) { return E > 0 ? (size_t)2 * kBwdCtas * E * sizeof(float) : 0; }
+
+extern "C" int acr_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int E, float eps,
+                                 void* y, int y_is_bf16, float* mean, float* rstd, void* stream) {
+  ACR_REQUIRE(x && gamma && beta && y && mean && rstd, ACR_E_INVAL, "acr_layernorm_fwd: null pointer");
+  ACR_REQUIRE(M > 0 && E > 0 && E % 128 == 0 && E <= 2048, ACR_E_INVAL, "acr_layernorm_fwd: E=%d must be a multiple of 128, <= 2048", E);
+  ACR_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, ACR_E_ALIGN, "acr_layernorm_fwd: 16-byte alignment required");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (E / 128) {
+    case 1: return launch_fwd<1>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 2: return launch_fwd<2>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 3: return launch_fwd<3>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 4: return launch_fwd<4>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 6: return launch_fwd<6>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 8: return launch_fwd<8>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 10: return launch_fwd<10>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 12: return launch_fwd<12>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 16: return launch_fwd<16>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    default: acr::set_error("acr_layernorm_fwd: E=%d unsupported (128*{1,2,3,4,6,8,10,12,16})", E); return ACR_E_INVAL;
+  }
+}
+
+extern "C" int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
+                                 const float* gamma, int M, int E, float* dx, float* dgamma, float* dbeta,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  ACR_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, ACR_E_INVAL, "acr_layernorm_bwd: null pointer");
+  ACR_REQUIRE(M > 0 && E > 0 && E % 128 == 0 && E <= 2048, ACR_E_INVAL, "acr_layernorm_bwd: E=%d must be a multiple of 128, <= 2048", E);
+  ACR_REQUIRE(workspace_bytes >= acr_layernorm_bwd_workspace(E), ACR_E_NOMEM, "acr_layernorm_bwd: workspace too small");
+  ACR_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma | (uintptr_t)workspace) & 15) == 0, ACR_E_ALIGN,
+              "acr_layernorm_bwd: 16-byte alignment required");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* parts = (float*)workspace;
+  switch (E / 128) {
+    case 1: return launch_bwd<1>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 2: return launch_bwd<2>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 3: return launch_bwd<3>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 4: return launch_bwd<4>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 6: return launch_bwd<6>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 8: return launch_bwd<8>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 10: return launch_bwd<10>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 12: return launch_bwd<12>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 16: return launch_bwd<16>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    default: acr::set_error("acr_layernorm_bwd: E=%d unsupported (128*{1,2,3,4,6,8,10,12,16})", E); return ACR_E_INVAL;
+  }
+}

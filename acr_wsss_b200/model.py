@@ -115,9 +115,16 @@ class Block(nn.Module):
         self.norm2 = nn.LayerNorm(dim, eps=1e-6)
         self.mlp = Mlp(dim, int(dim * mlp_ratio))
 
+    def _norm(self, ln, x):
+        # bf16 path: this repo's LayerNorm kernel writes the Linear's bf16 operand directly (no cast kernel, and a
+        # single-pass backward); fp32 path: stock nn.LayerNorm, exactly the reference's call
+        if self.attn.precision == "bf16" and x.is_cuda and x.dtype == torch.float32 and x.shape[-1] % 128 == 0:
+            return ops.layer_norm(x, ln.weight, ln.bias, ln.eps, out_bf16=True)
+        return ln(x)
+
     def forward(self, x):
-        x = x + self.attn(self.norm1(x))
-        x = x + self.mlp(self.norm2(x))
+        x = x + self.attn(self._norm(self.norm1, x))
+        x = x + self.mlp(self._norm(self.norm2, x))
         return x
 
 

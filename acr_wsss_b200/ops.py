@@ -255,6 +255,47 @@ def stack_views(stack, maps, states=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# LayerNorm around the attention core (writes the following Linear's bf16 operand directly)
+# ----------------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, out_bf16):
+        _need_cuda(x)
+        E = x.shape[-1]
+        x2 = x.contiguous().float().view(-1, E)
+        M = x2.shape[0]
+        y = torch.empty(M, E, device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        w, b = weight.contiguous().float(), bias.contiguous().float()
+        _call("acr_layernorm_fwd", 1, _p(x2), _p(w), _p(b), M, E, float(eps), _p(y), int(out_bf16), _p(mean), _p(rstd), _stream())
+        ctx.save_for_backward(x2, mean, rstd, w)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, w = ctx.saved_tensors
+        M, E = x2.shape
+        dy2 = dy.contiguous().view(M, E)
+        if dy2.dtype not in (torch.bfloat16, torch.float32):
+            dy2 = dy2.float()
+        dx = torch.empty_like(x2)
+        dg = torch.empty(E, device=x2.device, dtype=torch.float32)
+        db = torch.empty(E, device=x2.device, dtype=torch.float32)
+        wsb = _lib.lib().acr_layernorm_bwd_workspace(E)
+        ws = torch.empty(wsb, device=x2.device, dtype=torch.uint8)
+        _call("acr_layernorm_bwd", 2, _p(dy2), int(dy2.dtype == torch.bfloat16), _p(x2), _p(mean), _p(rstd), _p(w), M, E,
+              _p(dx), _p(dg), _p(db), _p(ws), wsb, _stream())
+        return dx.view(ctx.shape), dg, db, None, None
+
+
+def layer_norm(x, weight, bias, eps=1e-6, out_bf16=False):
+    """nn.LayerNorm(eps) over the last dimension of an fp32 tensor; output fp32 or (out_bf16) bf16."""
+    return _LayerNorm.apply(x, weight, bias, eps, out_bf16)
+
+
+# ----------------------------------------------------------------------------------------------
 # (a7) consistency loss
 # ----------------------------------------------------------------------------------------------
 def consistency_codes(attn1, attn2, p, one_buffer=False):

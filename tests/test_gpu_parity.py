@@ -457,3 +457,27 @@ def test_sign_code_gradient_path_matches_dense_path(dev):
     assert torch.equal(l_a, l_b)
     for a, b_ in zip(g_a, g_b):
         assert rel_err(t2n(a), t2n(b_)) < 2e-3
+
+
+@pytest.mark.parametrize("M,E,bf16", [(1, 128, False), (37, 768, True), (12560, 768, True), (4100, 1024, False)])
+def test_layernorm_kernel_vs_torch_reference(dev, M, E, bf16):
+    """Floating-point kernel: compared with the plain PyTorch fp32 op (F.layer_norm), fwd and bwd."""
+    from acr_wsss_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(E + M)
+    x = (torch.randn(M, E, generator=g) * 2 + 0.5).to(dev).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(E, generator=g)).to(dev).requires_grad_(True)
+    b = (0.1 * torch.randn(E, generator=g)).to(dev).requires_grad_(True)
+    dy = torch.randn(M, E, generator=g).to(dev)
+    if bf16:
+        dy = dy.to(torch.bfloat16)
+    y = ops.layer_norm(x, w, b, 1e-6, out_bf16=bf16)
+    y.backward(dy)
+    got = (y.detach().float(), x.grad.clone(), w.grad.clone(), b.grad.clone())
+    x.grad = w.grad = b.grad = None
+    yr = F.layer_norm(x, (E,), w, b, 1e-6)
+    yr.backward(dy.float())
+    ref = (yr.detach(), x.grad, w.grad, b.grad)
+    tols = (BF16_TOL if bf16 else 1e-5, 1e-4, 1e-4, 1e-4)
+    for a, r, tol in zip(got, ref, tols):
+        assert rel_err(t2n(a), t2n(r)) < tol
