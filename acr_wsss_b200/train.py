@@ -3,8 +3,14 @@
 PolyOptimizer mirrors tool/torchutils.py:10-31 INCLUDING its argument slip: the reference passes
 weight_decay positionally into SGD's momentum slot, so the effective optimiser is SGD(momentum=wt_dec, weight_decay=0)
 with lr_t = lr * (1 - t/max_step)^0.9.
+
+Trainer runs the step either eagerly or -- the default on a GPU -- as two CUDA graphs (forward+backward, optimiser
+update) around one NCCL all-reduce of the flat gradient buffer: after the kernels were fused the step became CPU-launch
+bound (~950 launches), and a graph replay removes that.  The optimiser in graph mode is the same SGD written on flat
+buffers with the learning rate in a device scalar (so the poly schedule keeps working across replays).
 """
 import torch
+import torch.distributed as dist
 
 from .losses import acr_total_loss
 from .parallel import GradBuckets
@@ -27,39 +33,118 @@ class PolyOptimizer(torch.optim.SGD):
         self.global_step += 1
 
 
+class _FlatPolySGD:
+    """PolyOptimizer's arithmetic on flat buffers: buf = m*buf + g ; p -= lr_t*buf, m = wt_dec, lr_t on device."""
+
+    def __init__(self, params, flat_grad, lr, wt_dec, max_step, poly=0.9):
+        self.params = params
+        dev = flat_grad.device
+        self.flat_grad = flat_grad
+        self.flat_param = torch.empty_like(flat_grad)
+        off = 0
+        for p in reversed(params):                              # same order as GradBuckets' flat gradient buffer
+            n = p.numel()
+            self.flat_param[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat_param[off:off + n].view_as(p)
+            off += n
+        self.buf = torch.zeros_like(flat_grad)
+        self.lr0, self.mom, self.max_step, self.poly = lr, wt_dec, max_step, poly
+        self.global_step = 0
+        self.neg_lr = torch.zeros((), device=dev, dtype=torch.float32)
+        self.param_groups = [{"lr": lr}]
+
+    def set_lr_for_step(self):
+        mult = (1 - self.global_step / self.max_step) ** self.poly if self.global_step < self.max_step else 0.0
+        if self.global_step >= self.max_step:
+            mult = (1 - (self.max_step - 1) / self.max_step) ** self.poly      # the reference stops updating lr there
+        self.param_groups[0]["lr"] = self.lr0 * mult
+        self.neg_lr.fill_(-self.lr0 * mult)
+        self.global_step += 1
+
+    def update(self):           # graph-capturable
+        self.buf.mul_(self.mom).add_(self.flat_grad)
+        self.flat_param.addcmul_(self.buf, self.neg_lr)
+
+
 class Trainer:
     """One object = one rank.  `step(img, label)` takes HOST (pinned) or device tensors and returns the loss tensor
     (device, detached); gradients are averaged across ranks when torch.distributed is initialised."""
 
-    def __init__(self, model, lr=0.01, wt_dec=5e-4, max_step=100000, alpha=100.0, bucket_bytes=64 << 20):
+    def __init__(self, model, lr=0.01, wt_dec=5e-4, max_step=100000, alpha=100.0, bucket_bytes=64 << 20, cuda_graph=None):
         self.model = model
         self.alpha = alpha
         model.train()
         model.set_capture_grad(False)
-        # parameters the ACR path never reaches get no gradient in the reference either (SURVEY Q4)
-        self.buckets = GradBuckets(list(model.parameters()), bucket_bytes)
-        self.opt = PolyOptimizer(model.parameters(), lr=lr, weight_decay=wt_dec, max_step=max_step)
         self.dev = next(model.parameters()).device
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.graph = (self.dev.type == "cuda") if cuda_graph is None else bool(cuda_graph)
+        # parameters the ACR path never reaches get no gradient in the reference either (SURVEY Q4)
+        self.buckets = GradBuckets(list(model.parameters()), bucket_bytes, hooks=not self.graph)
+        if self.graph:
+            self.opt = _FlatPolySGD(self.buckets.params, self.buckets.flat, lr, wt_dec, max_step)
+        else:
+            self.opt = PolyOptimizer(model.parameters(), lr=lr, weight_decay=wt_dec, max_step=max_step)
         self._img = None
         self._label = None
+        self._g_fb = None
+        self._g_opt = None
+        self._loss = None
+        self._eager_steps = 0
+        self._side = None
 
     def _stage(self, img, label):
-        if img.is_cuda:
-            return img, label
         if self._img is None or self._img.shape != img.shape:
+            if self._g_fb is not None:
+                raise RuntimeError("Trainer: input shape changed after CUDA-graph capture")
             self._img = torch.empty(img.shape, device=self.dev, dtype=img.dtype)
             self._label = torch.empty(label.shape, device=self.dev, dtype=label.dtype)
         self._img.copy_(img, non_blocking=True)
         self._label.copy_(label, non_blocking=True)
         return self._img, self._label
 
-    def step(self, img, label):
-        img, label = self._stage(img, label)
+    def _forward_backward(self, img, label):
         img2 = img.flip(-1)                                   # transforms.RandomHorizontalFlip(p=1), train_acr.py:135
         cls_list, (attn1, attn2) = self.model.forward_mirror(img, img2)
         loss, parts = acr_total_loss(cls_list[0], cls_list[1], label, attn1, attn2, img.shape[2] // 16, self.alpha)
         self.buckets.zero()
         loss.backward()
-        self.buckets.finish()
-        self.opt.step()
         return loss.detach()
+
+    def step(self, img, label):
+        if not self.graph:
+            if not img.is_cuda:
+                img, label = self._stage(img, label)
+            loss = self._forward_backward(img, label)
+            self.buckets.finish()
+            self.opt.step()
+            return loss
+        img, label = self._stage(img, label)
+        if self._g_fb is None and self._eager_steps < 2:
+            # warm-up eagerly (lazy initialisation inside the kernels' host code, cuBLAS workspaces, autotuning) on the
+            # SAME side stream the capture will use, so autograd's gradient-accumulation nodes are bound to it
+            self._eager_steps += 1
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                loss = self._forward_backward(img, label)
+            torch.cuda.current_stream().wait_stream(self._side)
+            self.buckets.reduce_all()
+            self.opt.set_lr_for_step()
+            self.opt.update()
+            return loss
+        if self._g_fb is None:
+            torch.cuda.synchronize()
+            self._g_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g_fb, stream=self._side):
+                self._loss = self._forward_backward(img, label)
+            self._g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g_opt, stream=self._side):
+                self.opt.update()
+            self._g_fb.replay()              # the capture itself did not execute the step
+        else:
+            self._g_fb.replay()
+        self.buckets.reduce_all()
+        self.opt.set_lr_for_step()
+        self._g_opt.replay()
+        return self._loss

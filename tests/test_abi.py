@@ -50,7 +50,7 @@ def test_product_never_imports_the_oracle():
 def test_invalid_arguments_are_rejected_before_any_launch():
     from acr_wsss_b200 import _lib
     L = _lib.lib()
-    assert L.acr_consistency_fwd_bwd(None, None, 1, 1, 5, 2, 1.0, 1.0, None, None, None, 0, None, 0, None) == -1
+    assert L.acr_consistency_fwd_bwd(None, None, 1, 1, 5, 2, 1.0, 1.0, None, None, None, 0, None, None, 0, None, 0, None) == -1
     assert b"null" in L.acr_last_error_string()
     assert L.acr_consistency_workspace(8, 12, 785) >= 8 * 12 * 785 * 4
     assert L.acr_bilateral_workspace(1, 21, 224, 224) > 0

@@ -481,3 +481,28 @@ def test_layernorm_kernel_vs_torch_reference(dev, M, E, bf16):
     tols = (BF16_TOL if bf16 else 1e-5, 1e-4, 1e-4, 1e-4)
     for a, r, tol in zip(got, ref, tols):
         assert rel_err(t2n(a), t2n(r)) < tol
+
+
+def test_trainer_cuda_graph_matches_eager(dev):
+    """Trainer's CUDA-graph step (flat SGD, device-side lr) == the eager step with the PolyOptimizer mirror."""
+    from acr_wsss_b200 import ACR, Trainer, synth
+    orc = _orc()
+    S, B, C = 64, 2, 20
+    sd = orc.synth_state_dict(orc.vit_shapes(768, 12, C), qkv_gain=2.0)
+    img, label = synth.images(B, S), synth.labels(B, C)
+    losses, finals = [], []
+    for graph in (True, False):
+        m = ACR(C, "vitb", precision="bf16").to(dev)
+        m.load_state_dict(sd)
+        for n, p in m.named_parameters():
+            if n.startswith(("pretrained.model.norm.", "pretrained.model.head.", "scratch.")) or n.endswith("bkg_token"):
+                p.requires_grad_(False)
+        tr = Trainer(m, lr=0.01, max_step=50, alpha=100.0, cuda_graph=graph)
+        ls = [float(tr.step(img.pin_memory(), label.pin_memory())) for _ in range(5)]     # 2 eager warm-ups, capture, 2 replays
+        losses.append(ls)
+        finals.append(m.cls_head.weight.detach().float().cpu().clone())
+        assert abs(tr.opt.param_groups[0]["lr"] - 0.01 * (1 - 4 / 50) ** 0.9) < 1e-9
+    assert losses[0][0] > losses[0][-1]                       # it trains
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 2e-3 * abs(b), (losses)
+    assert rel_err(t2n(finals[0]), t2n(finals[1])) < 2e-3
