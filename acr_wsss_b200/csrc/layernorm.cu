@@ -14,20 +14,43 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 
-template <int VEC, bool OUT_BF16>      // VEC float4 per lane: E = 128 * VEC
+// four consecutive elements of a row, fp32 or bf16 storage
+template <bool BF16>
+__device__ __forceinline__ float4 load4(const void* __restrict__ base, long long idx4) {
+  if (BF16) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(base) + idx4);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return __ldg(reinterpret_cast<const float4*>(base) + idx4);
+}
+template <bool BF16>
+__device__ __forceinline__ void store4(void* __restrict__ base, long long idx4, float4 v) {
+  if (BF16) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0);
+    u.y = *reinterpret_cast<uint32_t*>(&p1);
+    reinterpret_cast<uint2*>(base)[idx4] = u;
+  } else {
+    reinterpret_cast<float4*>(base)[idx4] = v;
+  }
+}
+
+template <int VEC, bool OUT_BF16, bool X_BF16>      // VEC float4 per lane: E = 128 * VEC
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int M, float eps,
+layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int M, float eps,
                      void* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
   constexpr int E = 128 * VEC;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (row >= M) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * E);
   float4 v[VEC];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    v[i] = __ldg(xr + i * 32 + lane);
+    v[i] = load4<X_BF16>(x, row * (E / 4) + i * 32 + lane);
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mu = acr::warp_sum(s) * (1.f / E);
@@ -45,23 +68,15 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
     const float o0 = (v[i].x - mu) * rs * g.x + bb.x, o1 = (v[i].y - mu) * rs * g.y + bb.y;
     const float o2 = (v[i].z - mu) * rs * g.z + bb.z, o3 = (v[i].w - mu) * rs * g.w + bb.w;
-    if (OUT_BF16) {
-      __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&p0);
-      u.y = *reinterpret_cast<uint32_t*>(&p1);
-      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + row * E)[i * 32 + lane] = u;
-    } else {
-      reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + row * E)[i * 32 + lane] = make_float4(o0, o1, o2, o3);
-    }
+    store4<OUT_BF16>(y, row * (E / 4) + i * 32 + lane, make_float4(o0, o1, o2, o3));
   }
 }
 
-template <int VEC, bool DY_BF16>
+template <int VEC, bool DY_BF16, bool X_BF16>      // X_BF16: x is bf16 and dx is written as bf16
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, int M, int rows_per_cta,
-                     float* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b) {
+                     void* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b) {
   constexpr int E = 128 * VEC;
   __shared__ float red[kWarpsPerCta][32 * 4 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -80,15 +95,8 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, c
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      if (DY_BF16) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + row * E) + i * 32 + lane);
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-        d[i] = make_float4(a.x, a.y, b.x, b.y);
-      } else {
-        d[i] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * E) + i * 32 + lane);
-      }
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * E) + i * 32 + lane);
+      d[i] = load4<DY_BF16>(dy, row * (E / 4) + i * 32 + lane);
+      const float4 xv = load4<X_BF16>(x, row * (E / 4) + i * 32 + lane);
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
       ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
       ag[i].x += d[i].x * xh[i].x; ag[i].y += d[i].y * xh[i].y; ag[i].z += d[i].z * xh[i].z; ag[i].w += d[i].w * xh[i].w;
@@ -103,7 +111,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const float* __restrict__ x, c
       float4 o;
       o.x = rs * (d[i].x - s1 - xh[i].x * s2); o.y = rs * (d[i].y - s1 - xh[i].y * s2);
       o.z = rs * (d[i].z - s1 - xh[i].z * s2); o.w = rs * (d[i].w - s1 - xh[i].w * s2);
-      reinterpret_cast<float4*>(dx + row * E)[i * 32 + lane] = o;
+      store4<X_BF16>(dx, row * (E / 4) + i * 32 + lane, o);
     }
   }
   // fold the CTA's warps: column-owned partial sums -> one partial row per CTA
@@ -141,23 +149,35 @@ layernorm_bwd_finish_kernel(const float* __restrict__ part_g, const float* __res
 constexpr int kBwdCtas = 296;     // 2 per SM
 
 template <int VEC>
-int launch_fwd(const float* x, const float* gamma, const float* beta, int M, float eps, void* y, int y_bf16, float* mean, float* rstd,
-               cudaStream_t st) {
+int launch_fwd(const void* x, int x_bf16, const float* gamma, const float* beta, int M, float eps, void* y, int y_bf16, float* mean,
+               float* rstd, cudaStream_t st) {
   const unsigned grid = (unsigned)((M + kWarpsPerCta - 1) / kWarpsPerCta);
-  if (y_bf16) layernorm_fwd_kernel<VEC, true><<<grid, kWarpsPerCta * 32, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
-  else layernorm_fwd_kernel<VEC, false><<<grid, kWarpsPerCta * 32, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
+  const int T = kWarpsPerCta * 32;
+  if (x_bf16) {
+    if (y_bf16) layernorm_fwd_kernel<VEC, true, true><<<grid, T, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
+    else layernorm_fwd_kernel<VEC, false, true><<<grid, T, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
+  } else {
+    if (y_bf16) layernorm_fwd_kernel<VEC, true, false><<<grid, T, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
+    else layernorm_fwd_kernel<VEC, false, false><<<grid, T, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
+  }
   return acr::check_launch("layernorm_fwd_kernel");
 }
 template <int VEC>
-int launch_bwd(const void* dy, int dy_bf16, const float* x, const float* mean, const float* rstd, const float* gamma, int M,
-               float* dx, float* dgamma, float* dbeta, float* parts, cudaStream_t st) {
+int launch_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, const float* mean, const float* rstd, const float* gamma, int M,
+               void* dx, float* dgamma, float* dbeta, float* parts, cudaStream_t st) {
   constexpr int E = 128 * VEC;
   const int ctas = M < kBwdCtas * kWarpsPerCta ? (M + kWarpsPerCta - 1) / kWarpsPerCta : kBwdCtas;
   const int rows_per_cta = (M + ctas - 1) / ctas;
   float* pg = parts;
   float* pb = parts + (size_t)kBwdCtas * E;
-  if (dy_bf16) layernorm_bwd_kernel<VEC, true><<<ctas, kWarpsPerCta * 32, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
-  else layernorm_bwd_kernel<VEC, false><<<ctas, kWarpsPerCta * 32, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
+  const int T = kWarpsPerCta * 32;
+  if (x_bf16) {
+    if (dy_bf16) layernorm_bwd_kernel<VEC, true, true><<<ctas, T, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
+    else layernorm_bwd_kernel<VEC, false, true><<<ctas, T, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
+  } else {
+    if (dy_bf16) layernorm_bwd_kernel<VEC, true, false><<<ctas, T, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
+    else layernorm_bwd_kernel<VEC, false, false><<<ctas, T, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
+  }
   if (int e = acr::check_launch("layernorm_bwd_kernel")) return e;
   layernorm_bwd_finish_kernel<<<(E + 255) / 256, 256, 0, st>>>(pg, pb, ctas, E, dgamma, dbeta);
   return acr::check_launch("layernorm_bwd_finish_kernel");
@@ -167,28 +187,28 @@ int launch_bwd(const void* dy, int dy_bf16, const float* x, const float* mean, c
 
 extern "C" size_t acr_layernorm_bwd_workspace(int E) { return E > 0 ? (size_t)2 * kBwdCtas * E * sizeof(float) : 0; }
 
-extern "C" int acr_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int E, float eps,
+extern "C" int acr_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const float* beta, int M, int E, float eps,
                                  void* y, int y_is_bf16, float* mean, float* rstd, void* stream) {
   ACR_REQUIRE(x && gamma && beta && y && mean && rstd, ACR_E_INVAL, "acr_layernorm_fwd: null pointer");
   ACR_REQUIRE(M > 0 && E > 0 && E % 128 == 0 && E <= 2048, ACR_E_INVAL, "acr_layernorm_fwd: E=%d must be a multiple of 128, <= 2048", E);
   ACR_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, ACR_E_ALIGN, "acr_layernorm_fwd: 16-byte alignment required");
   cudaStream_t st = (cudaStream_t)stream;
   switch (E / 128) {
-    case 1: return launch_fwd<1>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 2: return launch_fwd<2>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 3: return launch_fwd<3>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 4: return launch_fwd<4>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 6: return launch_fwd<6>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 8: return launch_fwd<8>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 10: return launch_fwd<10>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 12: return launch_fwd<12>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 16: return launch_fwd<16>(x, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 1: return launch_fwd<1>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 2: return launch_fwd<2>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 3: return launch_fwd<3>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 4: return launch_fwd<4>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 6: return launch_fwd<6>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 8: return launch_fwd<8>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 10: return launch_fwd<10>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 12: return launch_fwd<12>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 16: return launch_fwd<16>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
     default: acr::set_error("acr_layernorm_fwd: E=%d unsupported (128*{1,2,3,4,6,8,10,12,16})", E); return ACR_E_INVAL;
   }
 }
 
-extern "C" int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
-                                 const float* gamma, int M, int E, float* dx, float* dgamma, float* dbeta,
+extern "C" int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* mean, const float* rstd,
+                                 const float* gamma, int M, int E, void* dx, float* dgamma, float* dbeta,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   ACR_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, ACR_E_INVAL, "acr_layernorm_bwd: null pointer");
   ACR_REQUIRE(M > 0 && E > 0 && E % 128 == 0 && E <= 2048, ACR_E_INVAL, "acr_layernorm_bwd: E=%d must be a multiple of 128, <= 2048", E);
@@ -198,15 +218,15 @@ extern "C" int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
   cudaStream_t st = (cudaStream_t)stream;
   float* parts = (float*)workspace;
   switch (E / 128) {
-    case 1: return launch_bwd<1>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 2: return launch_bwd<2>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 3: return launch_bwd<3>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 4: return launch_bwd<4>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 6: return launch_bwd<6>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 8: return launch_bwd<8>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 10: return launch_bwd<10>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 12: return launch_bwd<12>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 16: return launch_bwd<16>(dy, dy_is_bf16, x, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 1: return launch_bwd<1>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 2: return launch_bwd<2>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 3: return launch_bwd<3>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 4: return launch_bwd<4>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 6: return launch_bwd<6>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 8: return launch_bwd<8>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 10: return launch_bwd<10>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 12: return launch_bwd<12>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 16: return launch_bwd<16>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
     default: acr::set_error("acr_layernorm_bwd: E=%d unsupported (128*{1,2,3,4,6,8,10,12,16})", E); return ACR_E_INVAL;
   }
 }

@@ -25,6 +25,14 @@ _BACKBONES = {
 _BACKBONE_ALIASES = {"vitb": "vitb16_384", "deit": "deitb16_384", "vitl": "vitl16_384"}
 
 
+def _lin(mod, x):
+    """nn.Linear call; uses the module's cached bf16 weight copy (set by Trainer) when there is one."""
+    w16 = getattr(mod, "_w16", None)
+    if w16 is not None and x.dtype == torch.bfloat16 and torch.is_grad_enabled():
+        return ops.linear_cached_bf16(x, mod.weight, mod.bias, w16, getattr(mod, "_b16", None))
+    return mod(x)
+
+
 class Attention(nn.Module):
     """Drop-in for models/vision_transformer.py:167-214.
 
@@ -79,7 +87,7 @@ class Attention(nn.Module):
 
     def forward(self, x):
         B, N, C = x.shape
-        qkv = self.qkv(x)
+        qkv = _lin(self.qkv, x)
         # The reference refreshes its saved map only when x.requires_grad (vision_transformer.py:207-209).
         record = x.requires_grad
         state = None
@@ -91,7 +99,7 @@ class Attention(nn.Module):
             self._state = state
             self.attn_mean = mean
         out = out.to(x.dtype) if out.dtype != x.dtype and not torch.is_autocast_enabled() else out
-        return self.proj(out)
+        return _lin(self.proj, out)
 
 
 class Mlp(nn.Module):
@@ -104,7 +112,7 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden_features, out_features)
 
     def forward(self, x):
-        return self.fc2(self.act(self.fc1(x)))
+        return _lin(self.fc2, self.act(_lin(self.fc1, x)))
 
 
 class Block(nn.Module):
@@ -118,7 +126,7 @@ class Block(nn.Module):
     def _norm(self, ln, x):
         # bf16 path: this repo's LayerNorm kernel writes the Linear's bf16 operand directly (no cast kernel, and a
         # single-pass backward); fp32 path: stock nn.LayerNorm, exactly the reference's call
-        if self.attn.precision == "bf16" and x.is_cuda and x.dtype == torch.float32 and x.shape[-1] % 128 == 0:
+        if self.attn.precision == "bf16" and x.is_cuda and x.shape[-1] % 128 == 0:
             return ops.layer_norm(x, ln.weight, ln.bias, ln.eps, out_bf16=True)
         return ln(x)
 

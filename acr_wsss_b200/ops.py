@@ -255,6 +255,48 @@ def stack_views(stack, maps, states=None):
 
 
 # ----------------------------------------------------------------------------------------------
+# Linear with a cached bf16 copy of the fp32 master weight (library GEMM; only the cast / accumulate traffic changes)
+# ----------------------------------------------------------------------------------------------
+class _LinearCachedBF16(torch.autograd.Function):
+    """y = x W^T + b with bf16 operands taken from a persistent bf16 copy of the master weights (refreshed once per
+    optimiser step) instead of autocast's per-call casts; the weight / bias gradients are accumulated straight into the
+    fp32 .grad buffers (one mixed-precision add instead of cast + add).  The GEMMs themselves stay cuBLAS."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w16, b16):
+        x2 = x.reshape(-1, x.shape[-1])
+        y = torch.nn.functional.linear(x2, w16, b16)      # (torch.addmm with a 1-D bf16 bias takes a 60x slower path)
+        ctx.save_for_backward(x2, w16)
+        ctx.params = (weight, bias)
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], w16.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w16 = ctx.saved_tensors
+        weight, bias = ctx.params
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dx = (dy2 @ w16).view(ctx.in_shape) if ctx.needs_input_grad[0] else None
+        dw = dy2.t() @ x2
+        gw = gb = None
+        if weight.grad is not None:
+            weight.grad.add_(dw)                    # fp32 += bf16, one kernel
+        else:
+            gw = dw.float()
+        if bias is not None:
+            db = dy2.sum(0, dtype=torch.float32)
+            if bias.grad is not None:
+                bias.grad.add_(db)
+            else:
+                gb = db
+        return dx, gw, gb, None, None
+
+
+def linear_cached_bf16(x, weight, bias, w16, b16):
+    return _LinearCachedBF16.apply(x, weight, bias, w16, b16)
+
+
+# ----------------------------------------------------------------------------------------------
 # LayerNorm around the attention core (writes the following Linear's bf16 operand directly)
 # ----------------------------------------------------------------------------------------------
 class _LayerNorm(torch.autograd.Function):
@@ -262,13 +304,16 @@ class _LayerNorm(torch.autograd.Function):
     def forward(ctx, x, weight, bias, eps, out_bf16):
         _need_cuda(x)
         E = x.shape[-1]
-        x2 = x.contiguous().float().view(-1, E)
+        x2 = x.contiguous().view(-1, E)
+        if x2.dtype not in (torch.bfloat16, torch.float32):
+            x2 = x2.float()
+        xb = int(x2.dtype == torch.bfloat16)
         M = x2.shape[0]
         y = torch.empty(M, E, device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
         mean = torch.empty(M, device=x.device, dtype=torch.float32)
         rstd = torch.empty(M, device=x.device, dtype=torch.float32)
         w, b = weight.contiguous().float(), bias.contiguous().float()
-        _call("acr_layernorm_fwd", 1, _p(x2), _p(w), _p(b), M, E, float(eps), _p(y), int(out_bf16), _p(mean), _p(rstd), _stream())
+        _call("acr_layernorm_fwd", 1, _p(x2), xb, _p(w), _p(b), M, E, float(eps), _p(y), int(out_bf16), _p(mean), _p(rstd), _stream())
         ctx.save_for_backward(x2, mean, rstd, w)
         ctx.shape = x.shape
         return y.view(x.shape)
@@ -285,13 +330,13 @@ class _LayerNorm(torch.autograd.Function):
         db = torch.empty(E, device=x2.device, dtype=torch.float32)
         wsb = _lib.lib().acr_layernorm_bwd_workspace(E)
         ws = torch.empty(wsb, device=x2.device, dtype=torch.uint8)
-        _call("acr_layernorm_bwd", 2, _p(dy2), int(dy2.dtype == torch.bfloat16), _p(x2), _p(mean), _p(rstd), _p(w), M, E,
+        _call("acr_layernorm_bwd", 2, _p(dy2), int(dy2.dtype == torch.bfloat16), _p(x2), int(x2.dtype == torch.bfloat16), _p(mean), _p(rstd), _p(w), M, E,
               _p(dx), _p(dg), _p(db), _p(ws), wsb, _stream())
         return dx.view(ctx.shape), dg, db, None, None
 
 
 def layer_norm(x, weight, bias, eps=1e-6, out_bf16=False):
-    """nn.LayerNorm(eps) over the last dimension of an fp32 tensor; output fp32 or (out_bf16) bf16."""
+    """nn.LayerNorm(eps) over the last dimension of an fp32 or bf16 tensor; output fp32 or (out_bf16) bf16."""
     return _LayerNorm.apply(x, weight, bias, eps, out_bf16)
 
 

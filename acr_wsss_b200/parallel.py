@@ -24,7 +24,13 @@ class GradBuckets:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         order = list(reversed(self.params))
-        total = sum(p.numel() for p in order)
+        # every tensor starts at a multiple of 128 elements: 16-byte alignment of fp32 AND bf16 views of the same layout
+        # (cuBLAS drops to much slower kernels for unaligned operands)
+        self.offsets = {}
+        total = 0
+        for p in order:
+            self.offsets[p] = total
+            total += (p.numel() + 127) // 128 * 128
         dev = order[0].device
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.buckets = []            # (start, end, n_params)
@@ -32,9 +38,10 @@ class GradBuckets:
         off, start, count = 0, 0, 0
         for p in order:
             n = p.numel()
+            off = self.offsets[p]
             p.grad = self.flat[off:off + n].view_as(p)
             self._bucket_of[p] = len(self.buckets)
-            off += n
+            off += (n + 127) // 128 * 128
             count += 1
             if (off - start) * 4 >= bucket_bytes:
                 self.buckets.append([start, off, count])

@@ -36,18 +36,19 @@ class PolyOptimizer(torch.optim.SGD):
 class _FlatPolySGD:
     """PolyOptimizer's arithmetic on flat buffers: buf = m*buf + g ; p -= lr_t*buf, m = wt_dec, lr_t on device."""
 
-    def __init__(self, params, flat_grad, lr, wt_dec, max_step, poly=0.9):
+    def __init__(self, params, flat_grad, offsets, lr, wt_dec, max_step, poly=0.9):
         self.params = params
+        self.offsets = offsets                                  # same (128-element aligned) layout as the gradient buffer
         dev = flat_grad.device
         self.flat_grad = flat_grad
-        self.flat_param = torch.empty_like(flat_grad)
-        off = 0
-        for p in reversed(params):                              # same order as GradBuckets' flat gradient buffer
-            n = p.numel()
+        self.flat_param = torch.zeros_like(flat_grad)
+        for p in params:
+            off, n = offsets[p], p.numel()
             self.flat_param[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat_param[off:off + n].view_as(p)
-            off += n
         self.buf = torch.zeros_like(flat_grad)
+        # persistent bf16 copy of the master weights for the trunk's Linear layers (refreshed inside update())
+        self.flat_param16 = self.flat_param.to(torch.bfloat16)
         self.lr0, self.mom, self.max_step, self.poly = lr, wt_dec, max_step, poly
         self.global_step = 0
         self.neg_lr = torch.zeros((), device=dev, dtype=torch.float32)
@@ -64,6 +65,18 @@ class _FlatPolySGD:
     def update(self):           # graph-capturable
         self.buf.mul_(self.mom).add_(self.flat_grad)
         self.flat_param.addcmul_(self.buf, self.neg_lr)
+        self.flat_param16.copy_(self.flat_param)
+
+    def attach_bf16_views(self, model):
+        """Give every trunk Linear a bf16 view (`_w16`, `_b16`) of its master parameters."""
+        off = self.offsets
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Linear) and mod.weight in off and getattr(mod, "weight").requires_grad:
+                w = mod.weight
+                mod._w16 = self.flat_param16[off[w]:off[w] + w.numel()].view_as(w)
+                if mod.bias is not None and mod.bias in off:
+                    b = mod.bias
+                    mod._b16 = self.flat_param16[off[b]:off[b] + b.numel()].view_as(b)
 
 
 class Trainer:
@@ -81,7 +94,9 @@ class Trainer:
         # parameters the ACR path never reaches get no gradient in the reference either
         self.buckets = GradBuckets(list(model.parameters()), bucket_bytes, hooks=not self.graph)
         if self.graph:
-            self.opt = _FlatPolySGD(self.buckets.params, self.buckets.flat, lr, wt_dec, max_step)
+            self.opt = _FlatPolySGD(self.buckets.params, self.buckets.flat, self.buckets.offsets, lr, wt_dec, max_step)
+            if getattr(model, "precision", "fp32") == "bf16":
+                self.opt.attach_bf16_views(model.pretrained.model.blocks)
         else:
             self.opt = PolyOptimizer(model.parameters(), lr=lr, weight_decay=wt_dec, max_step=max_step)
         self._img = None

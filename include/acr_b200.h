@@ -88,15 +88,15 @@ int acr_attn_bwd_f32(const float* qkv, const float* P, const float* d_out,
 
 /* ------------------------------------------------------------------------------------------
  * LayerNorm either side of the attention core.  Replaces the nn.LayerNorm(eps=1e-6) calls of
- * Block.forward, models/vision_transformer.py:230-233.  x [M,E] fp32 (E a multiple of 128, <= 2048); y [M,E] in fp32 or,
+ * Block.forward, models/vision_transformer.py:230-233.  x [M,E] fp32 or bf16 (E a multiple of 128, <= 2048; dx has x's type); y [M,E] in fp32 or,
  * with y_is_bf16, directly in the bf16 operand type of the following Linear; mean/rstd [M] fp32 are kept for backward.
  * Backward: dy [M,E] fp32 or bf16 -> dx [M,E] fp32, dgamma/dbeta [E] fp32 (deterministic two-level reduction).
  * ------------------------------------------------------------------------------------------ */
-int acr_layernorm_fwd(const float* x, const float* gamma, const float* beta, int M, int E, float eps,
+int acr_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const float* beta, int M, int E, float eps,
                       void* y, int y_is_bf16, float* mean, float* rstd, void* stream);
 size_t acr_layernorm_bwd_workspace(int E);
-int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* mean, const float* rstd,
-                      const float* gamma, int M, int E, float* dx, float* dgamma, float* dbeta,
+int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* mean, const float* rstd,
+                      const float* gamma, int M, int E, void* dx, float* dgamma, float* dbeta,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
