@@ -135,15 +135,26 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
   }
 }
 
+// 32 columns per CTA, 8 groups of partial rows per column, folded through shared memory (fixed order -> deterministic)
 __global__ void __launch_bounds__(256)
 layernorm_bwd_finish_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b, int nparts, int E,
                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= E) return;
-  float sg = 0.f, sb = 0.f;
-  for (int p = 0; p < nparts; ++p) { sg += part_g[(long long)p * E + c]; sb += part_b[(long long)p * E + c]; }
-  dgamma[c] = sg;
-  dbeta[c] = sb;
+  __shared__ float sg[8][33], sb[8][33];
+  const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float ag = 0.f, ab = 0.f;
+  if (c < E)
+    for (int p = grp; p < nparts; p += 8) { ag += part_g[(long long)p * E + c]; ab += part_b[(long long)p * E + c]; }
+  sg[grp][cl] = ag;
+  sb[grp][cl] = ab;
+  __syncthreads();
+  if (grp == 0 && c < E) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { tg += sg[k][cl]; tb += sb[k][cl]; }
+    dgamma[c] = tg;
+    dbeta[c] = tb;
+  }
 }
 
 constexpr int kBwdCtas = 296;     // 2 per SM
@@ -179,7 +190,7 @@ int launch_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, const flo
     else layernorm_bwd_kernel<VEC, false, false><<<ctas, T, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
   }
   if (int e = acr::check_launch("layernorm_bwd_kernel")) return e;
-  layernorm_bwd_finish_kernel<<<(E + 255) / 256, 256, 0, st>>>(pg, pb, ctas, E, dgamma, dbeta);
+  layernorm_bwd_finish_kernel<<<(E + 31) / 32, 256, 0, st>>>(pg, pb, ctas, E, dgamma, dbeta);
   return acr::check_launch("layernorm_bwd_finish_kernel");
 }
 
