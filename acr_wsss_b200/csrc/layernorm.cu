@@ -157,6 +157,45 @@ layernorm_bwd_finish_kernel(const float* __restrict__ part_g, const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Column sums of a bf16 matrix (bias gradients of the Linear layers): x [M,F] bf16 -> out[F] (+)= sum_m x[m,:].
+// Stage 1: CTA (column block of 64, row chunk r) -> fp32 partial [R][F]; stage 2 folds the R partials in a fixed order.
+constexpr int kColsumChunks = 64;
+
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int F, int rows_per_chunk, float* __restrict__ partial) {
+  __shared__ float2 red[8][33];
+  const int cp = threadIdx.x & 31, grp = threadIdx.x >> 5;      // 32 column pairs x 8 row groups
+  const int c = blockIdx.x * 64 + cp * 2;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(M, r0 + rows_per_chunk);
+  float2 acc = make_float2(0.f, 0.f);
+  if (c < F) {
+    for (int r = r0 + grp; r < r1; r += 8) {
+      const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + (size_t)r * F + c));
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+  }
+  red[grp][cp] = acc;
+  __syncthreads();
+  if (grp == 0 && c < F) {
+    float2 t = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { t.x += red[k][cp].x; t.y += red[k][cp].y; }
+    *reinterpret_cast<float2*>(partial + (size_t)blockIdx.y * F + c) = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ partial, int nparts, int F, float* __restrict__ out, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= F) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * F + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
 constexpr int kBwdCtas = 296;     // 2 per SM
 
 template <int VEC>
@@ -240,4 +279,22 @@ extern "C" int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, 
     case 16: return launch_bwd<16>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
     default: acr::set_error("acr_layernorm_bwd: E=%d unsupported (128*{1,2,3,4,6,8,10,12,16})", E); return ACR_E_INVAL;
   }
+}
+
+extern "C" size_t acr_colsum_workspace(int F) { return F > 0 ? (size_t)kColsumChunks * F * sizeof(float) : 0; }
+
+extern "C" int acr_colsum_bf16(const void* x, int M, int F, float* out, int accumulate, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+  ACR_REQUIRE(x && out && workspace, ACR_E_INVAL, "acr_colsum_bf16: null pointer");
+  ACR_REQUIRE(M > 0 && F > 0 && F % 2 == 0, ACR_E_INVAL, "acr_colsum_bf16: F must be even");
+  ACR_REQUIRE(workspace_bytes >= acr_colsum_workspace(F), ACR_E_NOMEM, "acr_colsum_bf16: workspace too small");
+  ACR_REQUIRE(((uintptr_t)x & 3) == 0 && ((uintptr_t)workspace & 7) == 0, ACR_E_ALIGN, "acr_colsum_bf16: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = M < kColsumChunks * 8 ? 1 : kColsumChunks;
+  const int rows_per_chunk = (M + chunks - 1) / chunks;
+  dim3 grid((F + 63) / 64, chunks);
+  colsum_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, M, F, rows_per_chunk, (float*)workspace);
+  if (int e = acr::check_launch("colsum_bf16_kernel")) return e;
+  colsum_finish_kernel<<<(F + 255) / 256, 256, 0, st>>>((const float*)workspace, chunks, F, out, accumulate);
+  return acr::check_launch("colsum_finish_kernel");
 }

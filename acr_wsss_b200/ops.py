@@ -284,12 +284,24 @@ class _LinearCachedBF16(torch.autograd.Function):
         else:
             gw = dw.float()
         if bias is not None:
-            db = dy2.sum(0, dtype=torch.float32)
-            if bias.grad is not None:
-                bias.grad.add_(db)
+            if bias.grad is not None and dy2.is_cuda and dy2.dtype == torch.bfloat16 and dy2.is_contiguous() and dy2.shape[1] % 2 == 0:
+                colsum_bf16(dy2, bias.grad, accumulate=True)       # db accumulated straight into the fp32 .grad
             else:
-                gb = db
+                db = dy2.sum(0, dtype=torch.float32)
+                if bias.grad is not None:
+                    bias.grad.add_(db)
+                else:
+                    gb = db
         return dx, gw, gb, None, None
+
+
+def colsum_bf16(x, out, accumulate=False):
+    """out[F] (+)= x.sum(0) for a contiguous bf16 [M,F] matrix; fp32 accumulation, deterministic."""
+    M, F = x.shape
+    wsb = _lib.lib().acr_colsum_workspace(F)
+    ws = torch.empty(wsb, device=x.device, dtype=torch.uint8)
+    _call("acr_colsum_bf16", 2, _p(x), M, F, _p(out), int(accumulate), _p(ws), wsb, _stream())
+    return out
 
 
 def linear_cached_bf16(x, weight, bias, w16, b16):

@@ -99,6 +99,12 @@ int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf
                       const float* gamma, int M, int E, void* dx, float* dgamma, float* dbeta,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Column sums of a bf16 matrix: out[F] (+)= sum_m x[m,:]  (bias gradients of the Linear layers around the attention core;
+ * deterministic two-stage reduction, fp32 accumulation).  workspace: acr_colsum_workspace(F) bytes. */
+size_t acr_colsum_workspace(int F);
+int acr_colsum_bf16(const void* x_bf16, int M, int F, float* out, int accumulate, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (a7) All-pairs consistency loss, forward and gradient in one pass.
  * Replaces train_acr.py:143-161 (= train_acr_coco.py:140-158): the slicing, the 3*p in-place

@@ -50,7 +50,9 @@ t2 = timeit(lambda: fwd(True)); res["fwd_with_mean_us"] = t2; res["mean_kernel_u
 t = timeit(lambda: bwd(0)); res["bwd_noG_us"] = t; res["bwd_noG_TFLOPs"] = 2 * f_core / t / 1e6
 t = timeit(lambda: bwd(1)); res["bwd_withG_us"] = t; res["bwd_withG_TFLOPs"] = 2 * f_core / t / 1e6
 t = timeit(lambda: bwd(2)); res["bwd_codes_us"] = t; res["bwd_codes_TFLOPs"] = 2 * f_core / t / 1e6
-a1 = torch.softmax(torch.randn(B, 12, N, N, device=dev, generator=g), -1); a2 = torch.softmax(torch.randn(B, 12, N, N, device=dev, generator=g), -1)
-t = timeit(lambda: ops.consistency_fwd_bwd(a1, a2, int((N - 1) ** 0.5), 100.0, 100.0)); res["consistency_us"] = t; res["consistency_GBs"] = 16.0 * B * 12 * N * N / t / 1e3
-t = timeit(lambda: ops.consistency_codes(a1, a2, int((N - 1) ** 0.5))); res["consistency_codes_us"] = t
+pp = int(round((N - 1) ** 0.5))
+if pp * pp + 1 == N:
+    a1 = torch.softmax(torch.randn(B, 12, N, N, device=dev, generator=g), -1); a2 = torch.softmax(torch.randn(B, 12, N, N, device=dev, generator=g), -1)
+    t = timeit(lambda: ops.consistency_fwd_bwd(a1, a2, pp, 100.0, 100.0)); res["consistency_us"] = t; res["consistency_GBs"] = 16.0 * B * 12 * N * N / t / 1e3
+    t = timeit(lambda: ops.consistency_codes(a1, a2, pp)); res["consistency_codes_us"] = t
 print(json.dumps({k: round(v, 2) for k, v in res.items()}))

@@ -509,3 +509,14 @@ def test_trainer_cuda_graph_matches_eager(dev):
     for a, b in zip(*losses):
         assert abs(a - b) <= 3e-2 * abs(b), (losses)
     assert rel_err(t2n(finals[0]), t2n(finals[1])) < 5e-2
+
+
+@pytest.mark.parametrize("M,F", [(1, 2), (37, 768), (12560, 3072), (513, 20)])
+def test_colsum_bf16_vs_torch(dev, M, F):
+    from acr_wsss_b200 import ops
+    g = torch.Generator().manual_seed(M + F)
+    x = torch.randn(M, F, generator=g).to(torch.bfloat16).to(dev)
+    out = torch.full((F,), 3.0, device=dev)
+    ops.colsum_bf16(x, out, accumulate=True)
+    ref = 3.0 + x.float().sum(0)
+    assert rel_err(t2n(out), t2n(ref)) < 1e-5
