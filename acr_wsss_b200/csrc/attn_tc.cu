@@ -108,14 +108,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
 #pragma unroll
     for (int i = 0; i < HD; ++i) o[i] = 0.f;
     uint32_t r[32];
+    // N = p*p+1 leaves a thin last tile: warps whose 32 query rows all lie past N only keep the barrier protocol going
+    // (their TMEM lanes hold garbage that is never stored), and 32-column chunks past N are skipped in the key tail tile.
+    const bool rows_live = q0 + (warp & 3) * 32 < N;
     for (int j = 0; j < ntiles; ++j) {
       tc::mbar_wait(&s.s_full, j & 1);
       tc::tc_fence_after();
+      if (!rows_live) {
+        tc::tc_fence_before();
+        tc::mbar_arrive(&s.p_full);
+        tc::mbar_wait(&s.o_full, j & 1);
+        continue;
+      }
       const int col0 = j * BN;
       const bool tail = (col0 + BN > N);
       float mx = m;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        if (tail && col0 + c * 32 >= N) break;
         tc::tmem_ld32(tS + lane_off + c * 32, r);
         tc::tmem_ld_wait();
         if (!tail) {
@@ -132,9 +142,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
       float rowsum = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+        if (tail && col0 + c * 32 >= N) {          // keys past N: P = 0 (V rows there are zero-filled, 0 * garbage must stay finite)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          tc::tmem_st16(tP + lane_off + c * 16, pk);
+          continue;
+        }
         tc::tmem_ld32(tS + lane_off + c * 32, r);
         tc::tmem_ld_wait();
-        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float p0 = tc::fast_exp2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -ms));
@@ -302,6 +318,8 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const bool tail = (kv0 + BN > N);
     const bool row0_warp = (MODE == 0) && (p_row0 != nullptr) && (q0 == 0) && ((warp & 3) == 0);
+    // thin last tiles (N = p*p+1): warps whose 32 rows or 64 columns all lie past N only keep the barrier protocol going
+    const bool live = (q0 + (warp & 3) * 32 < N) && (kv0 + half * 64 < N);
     uint32_t r[32];
     for (int h = 0; h < H; ++h) {
       const int ab = h & 1;
@@ -311,9 +329,10 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
       float part = 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        const int colbase = kv0 + half * 64 + c * 32;
+        if (!live || (tail && colbase >= N)) break;
         tc::tmem_ld32(tmem + ab * 128 + lane_off + half * 64 + c * 32, r);
         tc::tmem_ld_wait();
-        const int colbase = kv0 + half * 64 + c * 32;
         if (!tail) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -337,7 +356,7 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&s.t_empty[ab]);
-      if (MODE == 1 && row_ok) atomicAdd(p_row0 + ((size_t)b * H + h) * N + q0 + row, part);
+      if (MODE == 1 && row_ok && live) atomicAdd(p_row0 + ((size_t)b * H + h) * N + q0 + row, part);
     }
     if (MODE == 0) {
     // All MMAs have completed (the last t_full was observed) and every TMA load was consumed: the pipeline
@@ -512,6 +531,15 @@ struct BwdSmem {
 // grow == nullptr <=> no affinity gradient was given (warp-uniform).
 // GMODE: 0 no affinity gradient, 1 fp32 rows (scalar loads), 2 fp32 rows (128-bit loads), 3 sign codes (`grow` then points
 // at bytes and `invH` carries 2*w*scale/H of this row).
+// zero `n` 16-byte chunks (from chunk c0) of this thread's row in the swizzled P and dS tiles
+__device__ __forceinline__ void bwd_zero_chunks(uint8_t* prow, uint8_t* drow, int row, int c0, int n) {
+  for (int cc = c0; cc < c0 + n; ++cc) {
+    const int pos = (cc ^ (row & 7)) << 4;
+    *reinterpret_cast<uint4*>(prow + pos) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(drow + pos) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 template <int GMODE, bool TAIL>
 __device__ __forceinline__ void bwd_tile_body(BwdSmem& s, int buf, uint32_t tS, uint32_t tDP, uint32_t lane_off, int half, int row,
                                               int colbase, int N, const float* __restrict__ grow, float invH, float scale_log2,
@@ -520,6 +548,10 @@ __device__ __forceinline__ void bwd_tile_body(BwdSmem& s, int buf, uint32_t tS, 
   uint32_t rs[32], rd[32];
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
+    if (TAIL && colbase + c * 32 >= N) {             // 32 key columns entirely past N (uniform over the warp): P = dS = 0
+      bwd_zero_chunks(s.p[buf][half] + row * 128, s.ds[buf][half] + row * 128, row, c * 4, 4);
+      continue;
+    }
     tc::tmem_ld32(tS + lane_off + half * 64 + c * 32, rs);
     tc::tmem_ld32(tDP + lane_off + half * 64 + c * 32, rd);
     float g[32];
@@ -698,7 +730,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     for (int i = 0; i < ntiles; ++i) {
       const int q0 = i * BM;
       const int qi = q0 + row;
-      const bool q_ok = qi < N;
       const float lse2 = lse_n * kLog2e, dlt = dlt_n;
       if (i + 1 < ntiles) {                          // row statistics of the next tile, off the critical path
         const int qn = qi + BM;
@@ -713,7 +744,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       tc::mbar_wait(&s.sdp_full, i & 1);
       tc::tc_fence_after();
       // specialised bodies (uniform branches): affinity gradient present / key tail tile
-      if (crow != nullptr) {
+      if (q0 + (warp & 3) * 32 >= N) {
+        // all 32 query rows of this warp lie past N (last query tile): nothing to compute, the tiles just need finite
+        // values there (they meet zero-filled dO / Q rows in the gradient MMAs)
+        bwd_zero_chunks(s.p[i & 1][half] + row * 128, s.ds[i & 1][half] + row * 128, row, 0, 8);
+      } else if (crow != nullptr) {
         const float w2 = gcode_weight(gc, qi, invH);
         const float* cp = reinterpret_cast<const float*>(crow);
         if (!tail) bwd_tile_body<3, false>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, cp, w2, scale_log2, lse2, dlt, rd_row0);

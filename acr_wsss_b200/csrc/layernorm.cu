@@ -135,23 +135,33 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
   }
 }
 
-// 32 columns per CTA, 8 groups of partial rows per column, folded through shared memory (fixed order -> deterministic)
-__global__ void __launch_bounds__(256)
+// 32 columns per CTA, 32 groups of partial rows per column (4 independent accumulators each), folded through shared
+// memory in a fixed order -> deterministic
+__global__ void __launch_bounds__(1024)
 layernorm_bwd_finish_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b, int nparts, int E,
                             float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float sg[8][33], sb[8][33];
+  __shared__ float sg[32][33], sb[32][33];
   const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  float ag = 0.f, ab = 0.f;
-  if (c < E)
-    for (int p = grp; p < nparts; p += 8) { ag += part_g[(long long)p * E + c]; ab += part_b[(long long)p * E + c]; }
-  sg[grp][cl] = ag;
-  sb[grp][cl] = ab;
+  float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < E) {
+    int p = grp;
+    for (; p + 96 < nparts; p += 128) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ag[u] += __ldg(part_g + (long long)(p + 32 * u) * E + c);
+        ab[u] += __ldg(part_b + (long long)(p + 32 * u) * E + c);
+      }
+    }
+    for (; p < nparts; p += 32) { ag[0] += __ldg(part_g + (long long)p * E + c); ab[0] += __ldg(part_b + (long long)p * E + c); }
+  }
+  sg[grp][cl] = (ag[0] + ag[1]) + (ag[2] + ag[3]);
+  sb[grp][cl] = (ab[0] + ab[1]) + (ab[2] + ab[3]);
   __syncthreads();
   if (grp == 0 && c < E) {
     float tg = 0.f, tb = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { tg += sg[k][cl]; tb += sb[k][cl]; }
+    for (int k = 0; k < 32; ++k) { tg += sg[k][cl]; tb += sb[k][cl]; }
     dgamma[c] = tg;
     dbeta[c] = tb;
   }
@@ -229,7 +239,7 @@ int launch_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, const flo
     else layernorm_bwd_kernel<VEC, false, false><<<ctas, T, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
   }
   if (int e = acr::check_launch("layernorm_bwd_kernel")) return e;
-  layernorm_bwd_finish_kernel<<<(E + 31) / 32, 256, 0, st>>>(pg, pb, ctas, E, dgamma, dbeta);
+  layernorm_bwd_finish_kernel<<<(E + 31) / 32, 1024, 0, st>>>(pg, pb, ctas, E, dgamma, dbeta);
   return acr::check_launch("layernorm_bwd_finish_kernel");
 }
 
