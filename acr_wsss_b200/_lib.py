@@ -27,12 +27,16 @@ SIGNATURES = {
                                  c_void_p, c_longlong, c_void_p]),
     "acr_attn_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                  c_void_p, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "acr_layernorm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "acr_layernorm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_int, c_void_p, c_void_p,
+                                  c_void_p]),
     "acr_layernorm_bwd_workspace": (c_size_t, [c_int]),
-    "acr_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                  c_void_p, c_size_t, c_void_p]),
+    "acr_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "acr_colsum_workspace": (c_size_t, [c_int]),
     "acr_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "acr_gelu_fwd_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
+    "acr_gelu_bwd_workspace": (c_size_t, [c_int]),
+    "acr_gelu_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "acr_consistency_workspace": (c_size_t, [c_int, c_int, c_int]),
     "acr_consistency_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
                                         c_void_p, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong,

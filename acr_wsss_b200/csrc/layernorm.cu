@@ -40,8 +40,8 @@ __device__ __forceinline__ void store4(void* __restrict__ base, long long idx4, 
 
 template <int VEC, bool OUT_BF16, bool X_BF16>      // VEC float4 per lane: E = 128 * VEC
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int M, float eps,
-                     void* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
+layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ res, void* __restrict__ sum_out, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, int M, float eps, void* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
   constexpr int E = 128 * VEC;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -51,6 +51,15 @@ layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     v[i] = load4<X_BF16>(x, row * (E / 4) + i * 32 + lane);
+    if (res != nullptr) {       // residual add fused in: s = x + res is stored (rounded to the stream's type) and normalised
+      const float4 r = load4<X_BF16>(res, row * (E / 4) + i * 32 + lane);
+      v[i] = make_float4(v[i].x + r.x, v[i].y + r.y, v[i].z + r.z, v[i].w + r.w);
+      if (X_BF16) {
+        v[i].x = __bfloat162float(__float2bfloat16(v[i].x)); v[i].y = __bfloat162float(__float2bfloat16(v[i].y));
+        v[i].z = __bfloat162float(__float2bfloat16(v[i].z)); v[i].w = __bfloat162float(__float2bfloat16(v[i].w));
+      }
+      store4<X_BF16>(sum_out, row * (E / 4) + i * 32 + lane, v[i]);
+    }
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mu = acr::warp_sum(s) * (1.f / E);
@@ -72,20 +81,21 @@ layernorm_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma
   }
 }
 
-template <int VEC, bool DY_BF16, bool X_BF16>      // X_BF16: x is bf16 and dx is written as bf16
+template <int VEC, bool DY_BF16, bool X_BF16, bool COLSUM = false>      // X_BF16: x is bf16 and dx is written as bf16
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ mean,
+layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ dres, const void* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, int M, int rows_per_cta,
-                     void* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b) {
+                     void* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b, float* __restrict__ part_c) {
   constexpr int E = 128 * VEC;
   __shared__ float red[kWarpsPerCta][32 * 4 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 g[VEC], ag[VEC], ab[VEC];
+  float4 g[VEC], ag[VEC], ab[VEC], ac[COLSUM ? VEC : 1];      // ac: column sums of dx
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
     ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (COLSUM) ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min((long long)M, r0 + rows_per_cta);
@@ -111,14 +121,25 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
       float4 o;
       o.x = rs * (d[i].x - s1 - xh[i].x * s2); o.y = rs * (d[i].y - s1 - xh[i].y * s2);
       o.z = rs * (d[i].z - s1 - xh[i].z * s2); o.w = rs * (d[i].w - s1 - xh[i].w * s2);
+      if (dres != nullptr) {    // gradient arriving over the residual connection, added before the single rounding
+        const float4 r = load4<X_BF16>(dres, row * (E / 4) + i * 32 + lane);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
       store4<X_BF16>(dx, row * (E / 4) + i * 32 + lane, o);
+      if (COLSUM) {                  // sums what was stored (rounded when the stream is bf16), like a separate column sum would
+        if (X_BF16) {
+          o.x = __bfloat162float(__float2bfloat16(o.x)); o.y = __bfloat162float(__float2bfloat16(o.y));
+          o.z = __bfloat162float(__float2bfloat16(o.z)); o.w = __bfloat162float(__float2bfloat16(o.w));
+        }
+        ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;
+      }
     }
   }
   // fold the CTA's warps: column-owned partial sums -> one partial row per CTA
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    for (int pass = 0; pass < 2; ++pass) {
-      const float4 v = pass ? ab[i] : ag[i];
+    for (int pass = 0; pass < (COLSUM ? 3 : 2); ++pass) {
+      const float4 v = pass == 0 ? ag[i] : (pass == 1 ? ab[i] : ac[COLSUM ? i : 0]);
       red[warp][lane * 4 + 0] = v.x; red[warp][lane * 4 + 1] = v.y; red[warp][lane * 4 + 2] = v.z; red[warp][lane * 4 + 3] = v.w;
       __syncthreads();
       if (warp == 0) {
@@ -127,7 +148,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
         for (int w = 0; w < kWarpsPerCta; ++w) {
           t.x += red[w][lane * 4 + 0]; t.y += red[w][lane * 4 + 1]; t.z += red[w][lane * 4 + 2]; t.w += red[w][lane * 4 + 3];
         }
-        float* dst = (pass ? part_b : part_g) + (long long)blockIdx.x * E;
+        float* dst = (pass == 0 ? part_g : (pass == 1 ? part_b : part_c)) + (long long)blockIdx.x * E;
         reinterpret_cast<float4*>(dst)[i * 32 + lane] = t;
       }
       __syncthreads();
@@ -138,12 +159,12 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ x, co
 // 32 columns per CTA, 32 groups of partial rows per column (4 independent accumulators each), folded through shared
 // memory in a fixed order -> deterministic
 __global__ void __launch_bounds__(1024)
-layernorm_bwd_finish_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b, int nparts, int E,
-                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ float sg[32][33], sb[32][33];
+layernorm_bwd_finish_kernel(const float* __restrict__ part_g, const float* __restrict__ part_b, const float* __restrict__ part_c, int nparts,
+                            int E, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dx_colsum, int accumulate) {
+  __shared__ float sg[32][33], sb[32][33], sc[32][33];
   const int cl = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+  float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f}, ac[4] = {0.f, 0.f, 0.f, 0.f};
   if (c < E) {
     int p = grp;
     for (; p + 96 < nparts; p += 128) {
@@ -151,19 +172,26 @@ layernorm_bwd_finish_kernel(const float* __restrict__ part_g, const float* __res
       for (int u = 0; u < 4; ++u) {
         ag[u] += __ldg(part_g + (long long)(p + 32 * u) * E + c);
         ab[u] += __ldg(part_b + (long long)(p + 32 * u) * E + c);
+        if (part_c != nullptr) ac[u] += __ldg(part_c + (long long)(p + 32 * u) * E + c);
       }
     }
-    for (; p < nparts; p += 32) { ag[0] += __ldg(part_g + (long long)p * E + c); ab[0] += __ldg(part_b + (long long)p * E + c); }
+    for (; p < nparts; p += 32) {
+      ag[0] += __ldg(part_g + (long long)p * E + c);
+      ab[0] += __ldg(part_b + (long long)p * E + c);
+      if (part_c != nullptr) ac[0] += __ldg(part_c + (long long)p * E + c);
+    }
   }
   sg[grp][cl] = (ag[0] + ag[1]) + (ag[2] + ag[3]);
   sb[grp][cl] = (ab[0] + ab[1]) + (ab[2] + ab[3]);
+  sc[grp][cl] = (ac[0] + ac[1]) + (ac[2] + ac[3]);
   __syncthreads();
   if (grp == 0 && c < E) {
-    float tg = 0.f, tb = 0.f;
+    float tg = 0.f, tb = 0.f, tcs = 0.f;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) { tg += sg[k][cl]; tb += sb[k][cl]; }
+    for (int k = 0; k < 32; ++k) { tg += sg[k][cl]; tb += sb[k][cl]; tcs += sc[k][cl]; }
     dgamma[c] = tg;
     dbeta[c] = tb;
+    if (dx_colsum != nullptr) dx_colsum[c] = accumulate ? dx_colsum[c] + tcs : tcs;
   }
 }
 
@@ -209,84 +237,90 @@ colsum_finish_kernel(const float* __restrict__ partial, int nparts, int F, float
 constexpr int kBwdCtas = 296;     // 2 per SM
 
 template <int VEC>
-int launch_fwd(const void* x, int x_bf16, const float* gamma, const float* beta, int M, float eps, void* y, int y_bf16, float* mean,
+int launch_fwd(const void* x, int x_bf16, const void* res, void* sum_out, const float* gamma, const float* beta, int M, float eps, void* y, int y_bf16, float* mean,
                float* rstd, cudaStream_t st) {
   const unsigned grid = (unsigned)((M + kWarpsPerCta - 1) / kWarpsPerCta);
   const int T = kWarpsPerCta * 32;
   if (x_bf16) {
-    if (y_bf16) layernorm_fwd_kernel<VEC, true, true><<<grid, T, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
-    else layernorm_fwd_kernel<VEC, false, true><<<grid, T, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
+    if (y_bf16) layernorm_fwd_kernel<VEC, true, true><<<grid, T, 0, st>>>(x, res, sum_out, gamma, beta, M, eps, y, mean, rstd);
+    else layernorm_fwd_kernel<VEC, false, true><<<grid, T, 0, st>>>(x, res, sum_out, gamma, beta, M, eps, y, mean, rstd);
   } else {
-    if (y_bf16) layernorm_fwd_kernel<VEC, true, false><<<grid, T, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
-    else layernorm_fwd_kernel<VEC, false, false><<<grid, T, 0, st>>>(x, gamma, beta, M, eps, y, mean, rstd);
+    if (y_bf16) layernorm_fwd_kernel<VEC, true, false><<<grid, T, 0, st>>>(x, res, sum_out, gamma, beta, M, eps, y, mean, rstd);
+    else layernorm_fwd_kernel<VEC, false, false><<<grid, T, 0, st>>>(x, res, sum_out, gamma, beta, M, eps, y, mean, rstd);
   }
   return acr::check_launch("layernorm_fwd_kernel");
 }
 template <int VEC>
-int launch_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, const float* mean, const float* rstd, const float* gamma, int M,
-               void* dx, float* dgamma, float* dbeta, float* parts, cudaStream_t st) {
+int launch_bwd(const void* dy, int dy_bf16, const void* dres, const void* x, int x_bf16, const float* mean, const float* rstd, const float* gamma, int M,
+               void* dx, float* dgamma, float* dbeta, float* dx_colsum, int accumulate, float* parts, cudaStream_t st) {
   constexpr int E = 128 * VEC;
   const int ctas = M < kBwdCtas * kWarpsPerCta ? (M + kWarpsPerCta - 1) / kWarpsPerCta : kBwdCtas;
   const int rows_per_cta = (M + ctas - 1) / ctas;
   float* pg = parts;
   float* pb = parts + (size_t)kBwdCtas * E;
+  float* pc = dx_colsum ? parts + (size_t)2 * kBwdCtas * E : nullptr;
   const int T = kWarpsPerCta * 32;
-  if (x_bf16) {
-    if (dy_bf16) layernorm_bwd_kernel<VEC, true, true><<<ctas, T, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
-    else layernorm_bwd_kernel<VEC, false, true><<<ctas, T, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
+  if (pc != nullptr) {          // column sums of dx: bf16 stream only (the trunk's residual path)
+    ACR_REQUIRE(x_bf16 && dy_bf16, ACR_E_INVAL, "acr_layernorm_bwd: dx_colsum needs bf16 x and dy");
+    layernorm_bwd_kernel<VEC, true, true, true><<<ctas, T, 0, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);
+  } else if (x_bf16) {
+    if (dy_bf16) layernorm_bwd_kernel<VEC, true, true><<<ctas, T, 0, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);
+    else layernorm_bwd_kernel<VEC, false, true><<<ctas, T, 0, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);
   } else {
-    if (dy_bf16) layernorm_bwd_kernel<VEC, true, false><<<ctas, T, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
-    else layernorm_bwd_kernel<VEC, false, false><<<ctas, T, 0, st>>>(dy, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb);
+    if (dy_bf16) layernorm_bwd_kernel<VEC, true, false><<<ctas, T, 0, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);
+    else layernorm_bwd_kernel<VEC, false, false><<<ctas, T, 0, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);
   }
   if (int e = acr::check_launch("layernorm_bwd_kernel")) return e;
-  layernorm_bwd_finish_kernel<<<(E + 31) / 32, 1024, 0, st>>>(pg, pb, ctas, E, dgamma, dbeta);
+  layernorm_bwd_finish_kernel<<<(E + 31) / 32, 1024, 0, st>>>(pg, pb, pc, ctas, E, dgamma, dbeta, dx_colsum, accumulate);
   return acr::check_launch("layernorm_bwd_finish_kernel");
 }
 
 }  // namespace
 
-extern "C" size_t acr_layernorm_bwd_workspace(int E) { return E > 0 ? (size_t)2 * kBwdCtas * E * sizeof(float) : 0; }
+extern "C" size_t acr_layernorm_bwd_workspace(int E) { return E > 0 ? (size_t)3 * kBwdCtas * E * sizeof(float) : 0; }
 
-extern "C" int acr_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const float* beta, int M, int E, float eps,
-                                 void* y, int y_is_bf16, float* mean, float* rstd, void* stream) {
+extern "C" int acr_layernorm_fwd(const void* x, int x_is_bf16, const void* residual, void* sum_out, const float* gamma, const float* beta,
+                                 int M, int E, float eps, void* y, int y_is_bf16, float* mean, float* rstd, void* stream) {
   ACR_REQUIRE(x && gamma && beta && y && mean && rstd, ACR_E_INVAL, "acr_layernorm_fwd: null pointer");
   ACR_REQUIRE(M > 0 && E > 0 && E % 128 == 0 && E <= 2048, ACR_E_INVAL, "acr_layernorm_fwd: E=%d must be a multiple of 128, <= 2048", E);
-  ACR_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, ACR_E_ALIGN, "acr_layernorm_fwd: 16-byte alignment required");
+  ACR_REQUIRE((residual == nullptr) == (sum_out == nullptr), ACR_E_INVAL, "acr_layernorm_fwd: residual and sum_out go together");
+  ACR_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)residual | (uintptr_t)sum_out) & 15) == 0, ACR_E_ALIGN,
+              "acr_layernorm_fwd: 16-byte alignment required");
   cudaStream_t st = (cudaStream_t)stream;
   switch (E / 128) {
-    case 1: return launch_fwd<1>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 2: return launch_fwd<2>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 3: return launch_fwd<3>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 4: return launch_fwd<4>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 6: return launch_fwd<6>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 8: return launch_fwd<8>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 10: return launch_fwd<10>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 12: return launch_fwd<12>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
-    case 16: return launch_fwd<16>(x, x_is_bf16, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 1: return launch_fwd<1>(x, x_is_bf16, residual, sum_out, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 2: return launch_fwd<2>(x, x_is_bf16, residual, sum_out, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 3: return launch_fwd<3>(x, x_is_bf16, residual, sum_out, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 4: return launch_fwd<4>(x, x_is_bf16, residual, sum_out, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 6: return launch_fwd<6>(x, x_is_bf16, residual, sum_out, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 8: return launch_fwd<8>(x, x_is_bf16, residual, sum_out, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 10: return launch_fwd<10>(x, x_is_bf16, residual, sum_out, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 12: return launch_fwd<12>(x, x_is_bf16, residual, sum_out, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
+    case 16: return launch_fwd<16>(x, x_is_bf16, residual, sum_out, gamma, beta, M, eps, y, y_is_bf16, mean, rstd, st);
     default: acr::set_error("acr_layernorm_fwd: E=%d unsupported (128*{1,2,3,4,6,8,10,12,16})", E); return ACR_E_INVAL;
   }
 }
 
-extern "C" int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* mean, const float* rstd,
-                                 const float* gamma, int M, int E, void* dx, float* dgamma, float* dbeta,
+extern "C" int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const void* d_residual, const void* x, int x_is_bf16, const float* mean, const float* rstd,
+                                 const float* gamma, int M, int E, void* dx, float* dgamma, float* dbeta, float* dx_colsum, int accumulate,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   ACR_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && workspace, ACR_E_INVAL, "acr_layernorm_bwd: null pointer");
   ACR_REQUIRE(M > 0 && E > 0 && E % 128 == 0 && E <= 2048, ACR_E_INVAL, "acr_layernorm_bwd: E=%d must be a multiple of 128, <= 2048", E);
   ACR_REQUIRE(workspace_bytes >= acr_layernorm_bwd_workspace(E), ACR_E_NOMEM, "acr_layernorm_bwd: workspace too small");
-  ACR_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma | (uintptr_t)workspace) & 15) == 0, ACR_E_ALIGN,
+  ACR_REQUIRE((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)gamma | (uintptr_t)workspace | (uintptr_t)d_residual) & 15) == 0, ACR_E_ALIGN,
               "acr_layernorm_bwd: 16-byte alignment required");
   cudaStream_t st = (cudaStream_t)stream;
   float* parts = (float*)workspace;
   switch (E / 128) {
-    case 1: return launch_bwd<1>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 2: return launch_bwd<2>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 3: return launch_bwd<3>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 4: return launch_bwd<4>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 6: return launch_bwd<6>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 8: return launch_bwd<8>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 10: return launch_bwd<10>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 12: return launch_bwd<12>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
-    case 16: return launch_bwd<16>(dy, dy_is_bf16, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, parts, st);
+    case 1: return launch_bwd<1>(dy, dy_is_bf16, d_residual, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, dx_colsum, accumulate, parts, st);
+    case 2: return launch_bwd<2>(dy, dy_is_bf16, d_residual, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, dx_colsum, accumulate, parts, st);
+    case 3: return launch_bwd<3>(dy, dy_is_bf16, d_residual, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, dx_colsum, accumulate, parts, st);
+    case 4: return launch_bwd<4>(dy, dy_is_bf16, d_residual, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, dx_colsum, accumulate, parts, st);
+    case 6: return launch_bwd<6>(dy, dy_is_bf16, d_residual, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, dx_colsum, accumulate, parts, st);
+    case 8: return launch_bwd<8>(dy, dy_is_bf16, d_residual, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, dx_colsum, accumulate, parts, st);
+    case 10: return launch_bwd<10>(dy, dy_is_bf16, d_residual, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, dx_colsum, accumulate, parts, st);
+    case 12: return launch_bwd<12>(dy, dy_is_bf16, d_residual, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, dx_colsum, accumulate, parts, st);
+    case 16: return launch_bwd<16>(dy, dy_is_bf16, d_residual, x, x_is_bf16, mean, rstd, gamma, M, dx, dgamma, dbeta, dx_colsum, accumulate, parts, st);
     default: acr::set_error("acr_layernorm_bwd: E=%d unsupported (128*{1,2,3,4,6,8,10,12,16})", E); return ACR_E_INVAL;
   }
 }

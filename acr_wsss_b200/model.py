@@ -25,12 +25,25 @@ _BACKBONES = {
 _BACKBONE_ALIASES = {"vitb": "vitb16_384", "deit": "deitb16_384", "vitl": "vitl16_384"}
 
 
-def _lin(mod, x):
-    """nn.Linear call; uses the module's cached bf16 weight copy (set by Trainer) when there is one."""
-    w16 = getattr(mod, "_w16", None)
-    if w16 is not None and x.dtype == torch.bfloat16 and torch.is_grad_enabled():
-        return ops.linear_cached_bf16(x, mod.weight, mod.bias, w16, getattr(mod, "_b16", None))
+def _cached(mod, x):
+    return getattr(mod, "_w16", None) is not None and x.dtype == torch.bfloat16 and torch.is_grad_enabled()
+
+
+def _lin(mod, x, skip_bias_grad=False):
+    """nn.Linear call; uses the module's cached bf16 weight copy (set by Trainer) when there is one.
+    skip_bias_grad: the caller folds this layer's bias gradient into the following add_layer_norm (cached path only)."""
+    if _cached(mod, x):
+        return ops.linear_cached_bf16(x, mod.weight, mod.bias, mod._w16, getattr(mod, "_b16", None), skip_bias_grad)
+    assert not skip_bias_grad
     return mod(x)
+
+
+def _fold_bias(mod, x):
+    """The bias Parameter whose gradient add_layer_norm's backward can take over (cached bf16 path with fp32 .grad), or None."""
+    b = mod.bias
+    if b is not None and _cached(mod, x) and b.requires_grad and b.grad is not None and b.grad.dtype == torch.float32:
+        return b
+    return None
 
 
 class Attention(nn.Module):
@@ -85,7 +98,7 @@ class Attention(nn.Module):
             return st["grad_row0"]
         return st["attn_grad"][:, :, 0, :] if st.get("attn_grad") is not None else None
 
-    def forward(self, x):
+    def forward(self, x, skip_bias_grad=False):
         B, N, C = x.shape
         qkv = _lin(self.qkv, x)
         # The reference refreshes its saved map only when x.requires_grad (vision_transformer.py:207-209).
@@ -99,7 +112,7 @@ class Attention(nn.Module):
             self._state = state
             self.attn_mean = mean
         out = out.to(x.dtype) if out.dtype != x.dtype and not torch.is_autocast_enabled() else out
-        return _lin(self.proj, out)
+        return _lin(self.proj, out, skip_bias_grad)
 
 
 class Mlp(nn.Module):
@@ -111,8 +124,13 @@ class Mlp(nn.Module):
         self.act = nn.GELU()
         self.fc2 = nn.Linear(hidden_features, out_features)
 
-    def forward(self, x):
-        return _lin(self.fc2, self.act(_lin(self.fc1, x)))
+    def forward(self, x, skip_bias_grad=False):
+        w16 = getattr(self.fc1, "_w16", None)
+        if w16 is not None and x.dtype == torch.bfloat16 and x.is_cuda and torch.is_grad_enabled():
+            h = ops.linear_gelu_cached_bf16(x, self.fc1.weight, self.fc1.bias, w16, getattr(self.fc1, "_b16", None))
+        else:
+            h = self.act(_lin(self.fc1, x))
+        return _lin(self.fc2, h, skip_bias_grad)
 
 
 class Block(nn.Module):
@@ -134,6 +152,24 @@ class Block(nn.Module):
         x = x + self.attn(self._norm(self.norm1, x))
         x = x + self.mlp(self._norm(self.norm2, x))
         return x
+
+    def fused_ok(self, x):
+        return self.attn.precision == "bf16" and x.is_cuda and x.dtype == torch.bfloat16 and x.shape[-1] % 128 == 0
+
+    def forward_stream(self, x, pending, pending_bias=None, fold_out=True):
+        """Same arithmetic as forward() with the residual adds folded into the LayerNorm kernels.  The residual stream
+        travels as (x, pending) with the true value x + pending.  Returns (stream, pending branch, bias Parameter whose
+        gradient the NEXT add_layer_norm must produce (or None), this block's input)."""
+        if pending is None:
+            s, h = x, self._norm(self.norm1, x)
+        else:
+            s, h = ops.add_layer_norm(x, pending, self.norm1.weight, self.norm1.bias, self.norm1.eps, out_bf16=True,
+                                      branch_bias=pending_bias)
+        pb = _fold_bias(self.attn.proj, h)
+        s2, h2 = ops.add_layer_norm(s, self.attn(h, pb is not None), self.norm2.weight, self.norm2.bias, self.norm2.eps,
+                                    out_bf16=True, branch_bias=pb)
+        fb = _fold_bias(self.mlp.fc2, h2) if fold_out else None
+        return s2, self.mlp(h2, fb is not None), fb, s
 
 
 class PatchEmbed(nn.Module):
@@ -204,9 +240,16 @@ class VisionTransformer(nn.Module):
         x = torch.cat((cls_tokens.to(x.dtype), x), dim=1)
         x = x + pos_embed.to(x.dtype)
         self._block_in = []            # input of every block (references): lets GETAM stop its backward at start_layer
-        for blk in self.blocks:
-            self._block_in.append(x)
-            x = blk(x)
+        if len(self.blocks) and self.blocks[0].fused_ok(x):
+            pending = pbias = None
+            for i, blk in enumerate(self.blocks):        # the last block's branch meets a plain add: it keeps its own bias gradient
+                x, pending, pbias, blk_in = blk.forward_stream(x, pending, pbias, fold_out=i + 1 < len(self.blocks))
+                self._block_in.append(blk_in)
+            x = x + pending
+        else:
+            for blk in self.blocks:
+                self._block_in.append(x)
+                x = blk(x)
         if last_block_out is not None:
             last_block_out.append(x)
         return self.norm(x), None

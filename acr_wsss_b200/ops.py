@@ -263,11 +263,11 @@ class _LinearCachedBF16(torch.autograd.Function):
     fp32 .grad buffers (one mixed-precision add instead of cast + add).  The GEMMs themselves stay cuBLAS."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, w16, b16):
+    def forward(ctx, x, weight, bias, w16, b16, skip_bias_grad=False):
         x2 = x.reshape(-1, x.shape[-1])
         y = torch.nn.functional.linear(x2, w16, b16)      # (torch.addmm with a 1-D bf16 bias takes a 60x slower path)
         ctx.save_for_backward(x2, w16)
-        ctx.params = (weight, bias)
+        ctx.params = (weight, None if skip_bias_grad else bias)      # skipped: add_layer_norm's backward owns the bias gradient
         ctx.in_shape = x.shape
         return y.view(*x.shape[:-1], w16.shape[0])
 
@@ -277,12 +277,14 @@ class _LinearCachedBF16(torch.autograd.Function):
         weight, bias = ctx.params
         dy2 = dy.reshape(-1, dy.shape[-1])
         dx = (dy2 @ w16).view(ctx.in_shape) if ctx.needs_input_grad[0] else None
-        dw = dy2.t() @ x2
         gw = gb = None
-        if weight.grad is not None:
-            weight.grad.add_(dw)                    # fp32 += bf16, one kernel
+        if weight.grad is not None and weight.grad.dtype == torch.float32 and dy2.is_cuda and dy2.dtype == torch.bfloat16:
+            # dW accumulated by the GEMM itself: bf16 operands, fp32 accumulator written in place (no bf16 dW, no add kernel)
+            torch.addmm(weight.grad, dy2.t(), x2, out_dtype=torch.float32, out=weight.grad)
+        elif weight.grad is not None:
+            weight.grad.add_(dy2.t() @ x2)
         else:
-            gw = dw.float()
+            gw = (dy2.t() @ x2).float()
         if bias is not None:
             if bias.grad is not None and dy2.is_cuda and dy2.dtype == torch.bfloat16 and dy2.is_contiguous() and dy2.shape[1] % 2 == 0:
                 colsum_bf16(dy2, bias.grad, accumulate=True)       # db accumulated straight into the fp32 .grad
@@ -292,7 +294,7 @@ class _LinearCachedBF16(torch.autograd.Function):
                     bias.grad.add_(db)
                 else:
                     gb = db
-        return dx, gw, gb, None, None
+        return dx, gw, gb, None, None, None
 
 
 def colsum_bf16(x, out, accumulate=False):
@@ -304,8 +306,54 @@ def colsum_bf16(x, out, accumulate=False):
     return out
 
 
-def linear_cached_bf16(x, weight, bias, w16, b16):
-    return _LinearCachedBF16.apply(x, weight, bias, w16, b16)
+def linear_cached_bf16(x, weight, bias, w16, b16, skip_bias_grad=False):
+    return _LinearCachedBF16.apply(x, weight, bias, w16, b16, skip_bias_grad)
+
+
+class _LinearGeluCachedBF16(torch.autograd.Function):
+    """fc1 + exact GELU of the MLP (models/vision_transformer.py:158-160) on the cached-bf16 path: the GELU runs in this
+    repo's kernels and its backward also produces fc1's bias gradient, so the [M,4E] gradient is read once."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w16, b16):
+        x2 = x.reshape(-1, x.shape[-1])
+        f = torch.nn.functional.linear(x2, w16, b16)
+        y = torch.empty_like(f)
+        _call("acr_gelu_fwd_bf16", 1, _p(f), _p(y), f.numel(), _stream())
+        ctx.save_for_backward(x2, w16, f)
+        ctx.params = (weight, bias)
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], w16.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w16, f = ctx.saved_tensors
+        weight, bias = ctx.params
+        M, F = f.shape
+        dy2 = dy.reshape(M, F).contiguous()
+        df = torch.empty_like(f)
+        fused_bias = bias is not None and bias.grad is not None and bias.grad.dtype == torch.float32
+        gb = None
+        if fused_bias:
+            wsb = _lib.lib().acr_gelu_bwd_workspace(F)
+            ws = torch.empty(wsb, device=f.device, dtype=torch.uint8)
+            _call("acr_gelu_bwd_bf16", 2, _p(f), _p(dy2), _p(df), M, F, _p(bias.grad), 1, _p(ws), wsb, _stream())
+        else:
+            _call("acr_gelu_bwd_bf16", 1, _p(f), _p(dy2), _p(df), M, F, None, 0, None, 0, _stream())
+            if bias is not None:
+                gb = df.sum(0, dtype=torch.float32)
+        dx = (df @ w16).view(ctx.in_shape) if ctx.needs_input_grad[0] else None
+        gw = None
+        if weight.grad is not None and weight.grad.dtype == torch.float32:
+            torch.addmm(weight.grad, df.t(), x2, out_dtype=torch.float32, out=weight.grad)
+        else:
+            gw = (df.t() @ x2).float()
+        return dx, gw, gb, None, None
+
+
+def linear_gelu_cached_bf16(x, weight, bias, w16, b16):
+    _need_cuda(x)
+    return _LinearGeluCachedBF16.apply(x, weight, bias, w16, b16)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -325,7 +373,7 @@ class _LayerNorm(torch.autograd.Function):
         mean = torch.empty(M, device=x.device, dtype=torch.float32)
         rstd = torch.empty(M, device=x.device, dtype=torch.float32)
         w, b = weight.contiguous().float(), bias.contiguous().float()
-        _call("acr_layernorm_fwd", 1, _p(x2), xb, _p(w), _p(b), M, E, float(eps), _p(y), int(out_bf16), _p(mean), _p(rstd), _stream())
+        _call("acr_layernorm_fwd", 1, _p(x2), xb, None, None, _p(w), _p(b), M, E, float(eps), _p(y), int(out_bf16), _p(mean), _p(rstd), _stream())
         ctx.save_for_backward(x2, mean, rstd, w)
         ctx.shape = x.shape
         return y.view(x.shape)
@@ -342,9 +390,75 @@ class _LayerNorm(torch.autograd.Function):
         db = torch.empty(E, device=x2.device, dtype=torch.float32)
         wsb = _lib.lib().acr_layernorm_bwd_workspace(E)
         ws = torch.empty(wsb, device=x2.device, dtype=torch.uint8)
-        _call("acr_layernorm_bwd", 2, _p(dy2), int(dy2.dtype == torch.bfloat16), _p(x2), int(x2.dtype == torch.bfloat16), _p(mean), _p(rstd), _p(w), M, E,
-              _p(dx), _p(dg), _p(db), _p(ws), wsb, _stream())
+        _call("acr_layernorm_bwd", 2, _p(dy2), int(dy2.dtype == torch.bfloat16), None, _p(x2), int(x2.dtype == torch.bfloat16), _p(mean), _p(rstd), _p(w), M, E,
+              _p(dx), _p(dg), _p(db), None, 0, _p(ws), wsb, _stream())
         return dx.view(ctx.shape), dg, db, None, None
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """s = x + branch ; y = LayerNorm(s)  (Block.forward, models/vision_transformer.py:230-233: the residual add and the norm
+    that follows it) in one pass over the residual stream; returns (s, y).  Backward adds the gradient arriving at s over
+    the skip connection to the LayerNorm input gradient inside the kernel (no separate accumulation pass)."""
+
+    @staticmethod
+    def forward(ctx, x, branch, weight, bias, eps, out_bf16, branch_bias):
+        _need_cuda(x, branch)
+        ctx.branch_bias = branch_bias
+        E = x.shape[-1]
+        x2 = x.contiguous().view(-1, E)
+        r2 = branch.contiguous().view(-1, E)
+        if r2.dtype != x2.dtype:
+            r2 = r2.to(x2.dtype)
+        xb = int(x2.dtype == torch.bfloat16)
+        M = x2.shape[0]
+        ssum = torch.empty_like(x2)
+        y = torch.empty(M, E, device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(M, device=x.device, dtype=torch.float32)
+        w, b = weight.contiguous().float(), bias.contiguous().float()
+        _call("acr_layernorm_fwd", 1, _p(x2), xb, _p(r2), _p(ssum), _p(w), _p(b), M, E, float(eps), _p(y), int(out_bf16), _p(mean), _p(rstd), _stream())
+        ctx.save_for_backward(ssum, mean, rstd, w)
+        ctx.shape = x.shape
+        return ssum.view(x.shape), y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, ds, dy):
+        s2, mean, rstd, w = ctx.saved_tensors
+        M, E = s2.shape
+        bb = ctx.branch_bias
+        if dy is None:
+            if bb is not None:
+                raise RuntimeError("add_layer_norm: branch_bias given but the normalised output received no gradient")
+            return ds, ds, None, None, None, None, None
+        dy2 = dy.contiguous().view(M, E)
+        if dy2.dtype not in (torch.bfloat16, torch.float32):
+            dy2 = dy2.float()
+        ds2 = None
+        if ds is not None:
+            ds2 = ds.contiguous().view(M, E)
+            if ds2.dtype != s2.dtype:
+                ds2 = ds2.to(s2.dtype)
+        dx = torch.empty_like(s2)
+        dg = torch.empty(E, device=s2.device, dtype=torch.float32)
+        db = torch.empty(E, device=s2.device, dtype=torch.float32)
+        wsb = _lib.lib().acr_layernorm_bwd_workspace(E)
+        ws = torch.empty(wsb, device=s2.device, dtype=torch.uint8)
+        # bias gradient of the Linear that produced `branch` = column sums of dx, taken in the same pass
+        col = bb.grad if bb is not None else None
+        _call("acr_layernorm_bwd", 2, _p(dy2), int(dy2.dtype == torch.bfloat16), _p(ds2), _p(s2), int(s2.dtype == torch.bfloat16), _p(mean), _p(rstd),
+              _p(w), M, E, _p(dx), _p(dg), _p(db), _p(col), 1, _p(ws), wsb, _stream())
+        dx = dx.view(ctx.shape)
+        return dx, dx, dg, db, None, None, None
+
+
+def add_layer_norm(x, branch, weight, bias, eps=1e-6, out_bf16=False, branch_bias=None):
+    """(x + branch, LayerNorm(x + branch)) with the add fused into the LayerNorm kernels (forward and backward).
+    branch_bias: the bias Parameter of the Linear that produced `branch` (via linear_cached_bf16(..., skip_bias_grad=True));
+    its fp32 .grad is incremented by the column sums of the branch gradient inside the backward kernel."""
+    if branch_bias is not None and not (branch_bias.grad is not None and branch_bias.grad.dtype == torch.float32
+                                        and x.dtype == torch.bfloat16 and out_bf16):
+        raise RuntimeError("add_layer_norm: branch_bias needs a preallocated fp32 .grad and the bf16 stream")
+    return _AddLayerNorm.apply(x, branch, weight, bias, eps, out_bf16, branch_bias)
 
 
 def layer_norm(x, weight, bias, eps=1e-6, out_bf16=False):

@@ -91,12 +91,17 @@ int acr_attn_bwd_f32(const float* qkv, const float* P, const float* d_out,
  * Block.forward, models/vision_transformer.py:230-233.  x [M,E] fp32 or bf16 (E a multiple of 128, <= 2048; dx has x's type); y [M,E] in fp32 or,
  * with y_is_bf16, directly in the bf16 operand type of the following Linear; mean/rstd [M] fp32 are kept for backward.
  * Backward: dy [M,E] fp32 or bf16 -> dx [M,E] fp32, dgamma/dbeta [E] fp32 (deterministic two-level reduction).
+ * Residual fusion (Block.forward's `x = x + branch(x)` followed by the next norm): with `residual` (x's type) the kernel
+ * normalises s = x + residual and also stores s in `sum_out`; in backward `d_residual` (dx's type, may be NULL) is the
+ * gradient arriving over the skip connection and is added to dx before the single rounding; `dx_colsum` [E] (may be NULL)
+ * receives (or, with accumulate, is incremented by) the column sums of dx = the bias gradient of the Linear whose output
+ * was the residual branch.
  * ------------------------------------------------------------------------------------------ */
-int acr_layernorm_fwd(const void* x, int x_is_bf16, const float* gamma, const float* beta, int M, int E, float eps,
-                      void* y, int y_is_bf16, float* mean, float* rstd, void* stream);
+int acr_layernorm_fwd(const void* x, int x_is_bf16, const void* residual, void* sum_out, const float* gamma, const float* beta,
+                      int M, int E, float eps, void* y, int y_is_bf16, float* mean, float* rstd, void* stream);
 size_t acr_layernorm_bwd_workspace(int E);
-int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf16, const float* mean, const float* rstd,
-                      const float* gamma, int M, int E, void* dx, float* dgamma, float* dbeta,
+int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const void* d_residual, const void* x, int x_is_bf16, const float* mean, const float* rstd,
+                      const float* gamma, int M, int E, void* dx, float* dgamma, float* dbeta, float* dx_colsum, int accumulate,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Column sums of a bf16 matrix: out[F] (+)= sum_m x[m,:]  (bias gradients of the Linear layers around the attention core;
@@ -104,6 +109,14 @@ int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const void* x, int x_is_bf
 size_t acr_colsum_workspace(int F);
 int acr_colsum_bf16(const void* x_bf16, int M, int F, float* out, int accumulate, void* workspace, size_t workspace_bytes,
                     void* stream);
+
+/* Exact (erf) GELU of the ViT MLP (Mlp.act = nn.GELU, models/vision_transformer.py:148-164) on bf16 activations, fp32 math.
+ * Forward: y[n] = gelu(x[n]).  Backward: dx[M,F] = dy * gelu'(x) and, when `colsum` is given, colsum[F] (+)= sum_m dx[m,:]
+ * (the bias gradient of fc1) from the same pass.  F a multiple of 8; workspace: acr_gelu_bwd_workspace(F) bytes. */
+int acr_gelu_fwd_bf16(const void* x_bf16, void* y_bf16, long long n, void* stream);
+size_t acr_gelu_bwd_workspace(int F);
+int acr_gelu_bwd_bf16(const void* x_bf16, const void* dy_bf16, void* dx_bf16, int M, int F, float* colsum, int accumulate,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (a7) All-pairs consistency loss, forward and gradient in one pass.

@@ -520,3 +520,66 @@ def test_colsum_bf16_vs_torch(dev, M, F):
     ops.colsum_bf16(x, out, accumulate=True)
     ref = 3.0 + x.float().sum(0)
     assert rel_err(t2n(out), t2n(ref)) < 1e-5
+
+
+@pytest.mark.parametrize("M,E", [(37, 768), (12560, 768), (300, 1024)])
+def test_add_layernorm_kernel_vs_torch_reference(dev, M, E):
+    """Residual add fused into LayerNorm (bf16 stream): (s, y) and the gradients against plain PyTorch fp32 math on the
+    same bf16 inputs; the skip-connection gradient ds is added inside the backward kernel."""
+    from acr_wsss_b200 import ops
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(E + M)
+    x = (torch.randn(M, E, generator=g) * 2 + 0.5).to(torch.bfloat16).to(dev).requires_grad_(True)
+    r = torch.randn(M, E, generator=g).to(torch.bfloat16).to(dev).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(E, generator=g)).to(dev).requires_grad_(True)
+    b = (0.1 * torch.randn(E, generator=g)).to(dev).requires_grad_(True)
+    dy = torch.randn(M, E, generator=g).to(torch.bfloat16).to(dev)
+    ds = torch.randn(M, E, generator=g).to(torch.bfloat16).to(dev)
+    bb = torch.zeros(E, device=dev, requires_grad=True)              # stands for the bias of the Linear that produced r
+    bb.grad = torch.full((E,), 0.25, device=dev)
+    s, y = ops.add_layer_norm(x, r, w, b, 1e-6, out_bf16=True, branch_bias=bb)
+    torch.autograd.backward([s, y], [ds, dy])
+    got = (s.detach().float(), y.detach().float(), x.grad.float(), r.grad.float(), w.grad.clone(), b.grad.clone())
+    assert rel_err(t2n(bb.grad), t2n(0.25 + r.grad.float().sum(0))) < 1e-5      # column sums of exactly the stored gradient
+    x.grad = r.grad = w.grad = b.grad = None
+    sr = (x.float() + r.float()).to(torch.bfloat16).float()          # the stream is stored in bf16
+    sr.retain_grad()
+    yr = F.layer_norm(sr, (E,), w, b, 1e-6)
+    torch.autograd.backward([sr, yr], [ds.float(), dy.float()])
+    ref = (sr.detach(), yr.detach(), x.grad.float(), r.grad.float(), w.grad, b.grad)
+    assert torch.equal(got[0], ref[0])                               # the add itself is exact (one rounding)
+    for a, rr, tol in zip(got[1:], ref[1:], (BF16_TOL, BF16_TOL, BF16_TOL, 1e-4, 1e-4)):
+        assert rel_err(t2n(a), t2n(rr)) < tol
+
+
+@pytest.mark.parametrize("M,F", [(1, 8), (37, 3072), (12560, 3072), (515, 40)])
+def test_gelu_kernels_vs_torch_reference(dev, M, F):
+    """Exact-erf GELU forward / backward (+ fused column sum = fc1 bias gradient) against PyTorch fp32 math."""
+    from acr_wsss_b200 import ops, _lib
+    import ctypes
+    import torch.nn.functional as Fn
+    g = torch.Generator().manual_seed(M + F)
+    x = (torch.randn(M, F, generator=g) * 2).to(torch.bfloat16).to(dev)
+    dy = torch.randn(M, F, generator=g).to(torch.bfloat16).to(dev)
+    L = _lib.lib()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    y = torch.empty_like(x)
+    assert L.acr_gelu_fwd_bf16(p(x), p(y), x.numel(), st) == 0, _lib.last_error()
+    xr = x.float().requires_grad_(True)
+    yr = Fn.gelu(xr)
+    assert rel_err(t2n(y.float()), t2n(yr.detach())) < BF16_TOL
+    # elementwise: within one bf16 ulp of the fp32 result everywhere (the erf approximation is good to 1.5e-7 absolute)
+    assert bool(((y.float() - yr.detach()).abs() <= 2.0 ** -7 * yr.detach().abs() + 1e-6).all())
+    yr.backward(dy.float())
+    dx = torch.empty_like(x)
+    col = torch.full((F,), 2.0, device=dev)
+    wsb = L.acr_gelu_bwd_workspace(F)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    assert L.acr_gelu_bwd_bf16(p(x), p(dy), p(dx), M, F, p(col), 1, p(ws), wsb, st) == 0, _lib.last_error()
+    assert rel_err(t2n(dx.float()), t2n(xr.grad)) < BF16_TOL
+    assert bool(((dx.float() - xr.grad).abs() <= 2.0 ** -7 * xr.grad.abs() + 1e-6).all())
+    assert rel_err(t2n(col), t2n(2.0 + dx.float().sum(0))) < 1e-5    # column sum of exactly the values written
+    dx2 = torch.empty_like(x)
+    assert L.acr_gelu_bwd_bf16(p(x), p(dy), p(dx2), M, F, None, 0, None, 0, st) == 0, _lib.last_error()
+    assert torch.equal(dx, dx2)
