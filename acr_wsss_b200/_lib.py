@@ -34,6 +34,7 @@ SIGNATURES = {
                                   c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "acr_colsum_workspace": (c_size_t, [c_int]),
     "acr_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "acr_sgd_momentum_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_void_p, c_void_p]),
     "acr_gelu_fwd_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "acr_gelu_bwd_workspace": (c_size_t, [c_int]),
     "acr_gelu_bwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),

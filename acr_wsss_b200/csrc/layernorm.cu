@@ -189,8 +189,8 @@ layernorm_bwd_finish_kernel(const float* __restrict__ part_g, const float* __res
     float tg = 0.f, tb = 0.f, tcs = 0.f;
 #pragma unroll
     for (int k = 0; k < 32; ++k) { tg += sg[k][cl]; tb += sb[k][cl]; tcs += sc[k][cl]; }
-    dgamma[c] = tg;
-    dbeta[c] = tb;
+    dgamma[c] = accumulate ? dgamma[c] + tg : tg;
+    dbeta[c] = accumulate ? dbeta[c] + tb : tb;
     if (dx_colsum != nullptr) dx_colsum[c] = accumulate ? dx_colsum[c] + tcs : tcs;
   }
 }

@@ -297,6 +297,13 @@ class _LinearCachedBF16(torch.autograd.Function):
         return dx, gw, gb, None, None, None
 
 
+def sgd_momentum_step(param, grad, buf, param_bf16, momentum, neg_lr):
+    """buf = momentum*buf + grad ; param += neg_lr*buf ; param_bf16 = bf16(param) on flat fp32 buffers, one pass
+    (neg_lr: device scalar).  tool/torchutils.py:10-31 as it really runs."""
+    _need_cuda(param, grad, buf, neg_lr)
+    _call("acr_sgd_momentum_step", 1, _p(param), _p(grad), _p(buf), _p(param_bf16), param.numel(), float(momentum), _p(neg_lr), _stream())
+
+
 def colsum_bf16(x, out, accumulate=False):
     """out[F] (+)= x.sum(0) for a contiguous bf16 [M,F] matrix; fp32 accumulation, deterministic."""
     M, F = x.shape
@@ -417,6 +424,7 @@ class _AddLayerNorm(torch.autograd.Function):
         rstd = torch.empty(M, device=x.device, dtype=torch.float32)
         w, b = weight.contiguous().float(), bias.contiguous().float()
         _call("acr_layernorm_fwd", 1, _p(x2), xb, _p(r2), _p(ssum), _p(w), _p(b), M, E, float(eps), _p(y), int(out_bf16), _p(mean), _p(rstd), _stream())
+        ctx.norm_params = (weight, bias)
         ctx.save_for_backward(ssum, mean, rstd, w)
         ctx.shape = x.shape
         return ssum.view(x.shape), y.view(x.shape)
@@ -439,15 +447,26 @@ class _AddLayerNorm(torch.autograd.Function):
             if ds2.dtype != s2.dtype:
                 ds2 = ds2.to(s2.dtype)
         dx = torch.empty_like(s2)
-        dg = torch.empty(E, device=s2.device, dtype=torch.float32)
-        db = torch.empty(E, device=s2.device, dtype=torch.float32)
         wsb = _lib.lib().acr_layernorm_bwd_workspace(E)
         ws = torch.empty(wsb, device=s2.device, dtype=torch.uint8)
         # bias gradient of the Linear that produced `branch` = column sums of dx, taken in the same pass
         col = bb.grad if bb is not None else None
+        nw, nb = ctx.norm_params
+        direct = all(p_.grad is not None and p_.grad.dtype == torch.float32 and p_.grad.is_contiguous() for p_ in (nw, nb))
+        if direct:          # d-gamma / d-beta added straight into the fp32 .grad buffers by the finish kernel
+            dg, db = nw.grad, nb.grad
+        else:
+            dg = torch.empty(E, device=s2.device, dtype=torch.float32)
+            db = torch.empty(E, device=s2.device, dtype=torch.float32)
+            if col is not None:
+                dg.zero_()
+                db.zero_()
+        acc = int(direct or col is not None)
         _call("acr_layernorm_bwd", 2, _p(dy2), int(dy2.dtype == torch.bfloat16), _p(ds2), _p(s2), int(s2.dtype == torch.bfloat16), _p(mean), _p(rstd),
-              _p(w), M, E, _p(dx), _p(dg), _p(db), _p(col), 1, _p(ws), wsb, _stream())
+              _p(w), M, E, _p(dx), _p(dg), _p(db), _p(col), acc, _p(ws), wsb, _stream())
         dx = dx.view(ctx.shape)
+        if direct:
+            return dx, dx, None, None, None, None, None
         return dx, dx, dg, db, None, None, None
 
 

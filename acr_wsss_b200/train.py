@@ -12,6 +12,7 @@ buffers with the learning rate in a device scalar (so the poly schedule keeps wo
 import torch
 import torch.distributed as dist
 
+from . import ops
 from .losses import acr_total_loss
 from .parallel import GradBuckets
 
@@ -63,9 +64,12 @@ class _FlatPolySGD:
         self.global_step += 1
 
     def update(self):           # graph-capturable
-        self.buf.mul_(self.mom).add_(self.flat_grad)
-        self.flat_param.addcmul_(self.buf, self.neg_lr)
-        self.flat_param16.copy_(self.flat_param)
+        if self.flat_param.is_cuda:
+            ops.sgd_momentum_step(self.flat_param, self.flat_grad, self.buf, self.flat_param16, self.mom, self.neg_lr)
+        else:                   # CPU unit tests of the host logic (gloo)
+            self.buf.mul_(self.mom).add_(self.flat_grad)
+            self.flat_param.addcmul_(self.buf, self.neg_lr)
+            self.flat_param16.copy_(self.flat_param)
 
     def attach_bf16_views(self, model):
         """Give every trunk Linear a bf16 view (`_w16`, `_b16`) of its master parameters."""

@@ -94,8 +94,9 @@ int acr_attn_bwd_f32(const float* qkv, const float* P, const float* d_out,
  * Residual fusion (Block.forward's `x = x + branch(x)` followed by the next norm): with `residual` (x's type) the kernel
  * normalises s = x + residual and also stores s in `sum_out`; in backward `d_residual` (dx's type, may be NULL) is the
  * gradient arriving over the skip connection and is added to dx before the single rounding; `dx_colsum` [E] (may be NULL)
- * receives (or, with accumulate, is incremented by) the column sums of dx = the bias gradient of the Linear whose output
- * was the residual branch.
+ * receives the column sums of dx = the bias gradient of the Linear whose output was the residual branch.  With
+ * `accumulate` != 0 all three [E] outputs (dgamma, dbeta, dx_colsum) are incremented instead of overwritten, so they can
+ * point straight at fp32 .grad buffers.
  * ------------------------------------------------------------------------------------------ */
 int acr_layernorm_fwd(const void* x, int x_is_bf16, const void* residual, void* sum_out, const float* gamma, const float* beta,
                       int M, int E, float eps, void* y, int y_is_bf16, float* mean, float* rstd, void* stream);
@@ -109,6 +110,13 @@ int acr_layernorm_bwd(const void* dy, int dy_is_bf16, const void* d_residual, co
 size_t acr_colsum_workspace(int F);
 int acr_colsum_bf16(const void* x_bf16, int M, int F, float* out, int accumulate, void* workspace, size_t workspace_bytes,
                     void* stream);
+
+/* Optimiser update of the step on flat fp32 buffers (PolyOptimizer, tool/torchutils.py:10-31, as it really runs: SGD with
+ * momentum = the weight-decay value): buf = momentum*buf + grad ; param += (*neg_lr)*buf ; param_bf16 = bf16(param)
+ * (param_bf16 may be NULL).  neg_lr is a DEVICE scalar (-lr_t), so the poly schedule works across CUDA-graph replays.
+ * n a multiple of 4. */
+int acr_sgd_momentum_step(float* param, const float* grad, float* momentum_buf, void* param_bf16, long long n,
+                          float momentum, const float* neg_lr, void* stream);
 
 /* Exact (erf) GELU of the ViT MLP (Mlp.act = nn.GELU, models/vision_transformer.py:148-164) on bf16 activations, fp32 math.
  * Forward: y[n] = gelu(x[n]).  Backward: dx[M,F] = dy * gelu'(x) and, when `colsum` is given, colsum[F] (+)= sum_m dx[m,:]

@@ -583,3 +583,22 @@ def test_gelu_kernels_vs_torch_reference(dev, M, F):
     dx2 = torch.empty_like(x)
     assert L.acr_gelu_bwd_bf16(p(x), p(dy), p(dx2), M, F, None, 0, None, 0, st) == 0, _lib.last_error()
     assert torch.equal(dx, dx2)
+
+
+def test_sgd_momentum_step_vs_torch(dev):
+    """Fused optimiser update == buf.mul_(m).add_(g); p.addcmul_(buf, -lr); p16.copy_(p) (tool/torchutils.py:10-31 arithmetic)."""
+    from acr_wsss_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    n = 128 * 1001
+    p = torch.randn(n, generator=g).to(dev)
+    gr = torch.randn(n, generator=g).to(dev) * 1e-2
+    buf = torch.randn(n, generator=g).to(dev) * 1e-2
+    p16 = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    neg_lr = torch.tensor(-0.0123, device=dev)
+    pr, br = p.clone(), buf.clone()
+    br.mul_(5e-4).add_(gr)
+    pr.addcmul_(br, neg_lr)
+    ops.sgd_momentum_step(p, gr, buf, p16, 5e-4, neg_lr)
+    assert torch.equal(buf, br)
+    assert rel_err(t2n(p), t2n(pr)) < 1e-6
+    assert torch.equal(p16, p.to(torch.bfloat16))
