@@ -43,13 +43,15 @@ def pseudo_label(cam_dict, num_classes, threshold):
 
 
 def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, getam_func="cam_grad_s",
-                    aff=True, t=1, normalize=False, truncate_backward=True):
+                    aff=True, t=1, normalize=False, truncate_backward=True, batch_classes=True, max_replicas=8):
     """One image of the infer_cam.py loop body (:145-215).
 
     img [1,3,h,w] (normalised), label [1,C] multi-hot, out_size = (rows, cols) of the original image (the
     reference calls these W,H at infer_cam.py:136).  Returns (cam_dict, patch_cam_dict, norm_cam [C,rows,cols])
     with {class_index: float32 [rows,cols]} dicts as saved by np.save at :227-228.
     truncate_backward: stop each per-class backward at block `start_layer` (identical GETAM).
+    batch_classes (needs truncate_backward): the blocks >= start_layer run on one copy of the token stream per present
+    class (at most max_replicas per pass) and ONE backward delivers every class's attention gradients.
     """
     assert img.shape[0] == 1, "the reference infers one image at a time (infer_cam.py:122)"
     C = label.shape[1]
@@ -64,7 +66,18 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
             if hflip % 2 == 1:
                 inp = inp.flip(-1)
             ph, pw = int((h * scale) // 16), int((w * scale) // 16)
-            cls_pred, _, attn, patch_cam = model.forward_cam(inp)
+            batched = truncate_backward and batch_classes and len(present) > 0 and 0 < start_layer < len(model.pretrained.model.blocks)
+            rows0 = []
+            if batched:
+                for c0 in range(0, len(present), max_replicas):
+                    chunk = present[c0:c0 + max_replicas]
+                    cls_rep, _, attn, patch_cam = model.forward_cam_batched(inp, len(chunk), start_layer)
+                    model.backward_for_getam_batched(cls_rep, chunk)
+                    for k in range(len(chunk)):
+                        cam, _, _ = model.getam(k, start_layer=start_layer, func=getam_func)
+                        rows0.append(cam[0])
+            else:
+                cls_pred, _, attn, patch_cam = model.forward_cam(inp)
             patch_cam = patch_cam.permute(0, 2, 1).reshape(1, C, ph, pw)
             patch_cam = F.interpolate(patch_cam, [rows, cols], mode="bilinear", align_corners=False)[0]
             patch_cam = patch_cam.detach() * label[0, :].view(C, 1, 1)
@@ -72,9 +85,8 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
                 patch_cam = patch_cam.flip(-1)
             patch_cam_list.append(patch_cam)
 
-            output = cls_pred[0, :]
-            rows0 = []
-            for ci in present:
+            output = None if batched else cls_pred[0, :]
+            for ci in ([] if batched else present):
                 if truncate_backward:
                     model.backward_for_getam(output[ci], start_layer)
                 else:

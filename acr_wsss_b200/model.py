@@ -224,9 +224,12 @@ class VisionTransformer(nn.Module):
         posemb_grid = posemb_grid.permute(0, 2, 3, 1).reshape(1, gs_h * gs_w, -1)
         return torch.cat([posemb_tok, posemb_grid], dim=1)
 
-    def forward_flex(self, x, last_block_out=None):
+    def forward_flex(self, x, last_block_out=None, replicate_at=None, replicas=1):
         """vision_transformer.py:449-486.  Returns (norm(x), None); `last_block_out`, if a list, receives the
-        un-normalised output of the last block (what the reference reads through its forward hook, Q4)."""
+        un-normalised output of the last block (what the reference reads through its forward hook, Q4).
+        replicate_at / replicas: batched GETAM -- the input of block `replicate_at` is detached and
+        repeated `replicas` times along the batch, so ONE backward with one one-hot cotangent per replica yields the
+        per-class attention gradients of blocks >= replicate_at; the replicated leaf is kept in self._rep_in."""
         b, c, h, w = x.shape
         pos_embed = self._resize_pos_embed(self.pos_embed, h // self.patch_size[1], w // self.patch_size[0])
         # patch_embed.proj is a stride-16 16x16 convolution (vision_transformer.py:463-464) == one GEMM over
@@ -240,14 +243,26 @@ class VisionTransformer(nn.Module):
         x = torch.cat((cls_tokens.to(x.dtype), x), dim=1)
         x = x + pos_embed.to(x.dtype)
         self._block_in = []            # input of every block (references): lets GETAM stop its backward at start_layer
+        self._rep_in = None
+
+        def replicate(t):
+            t = t.detach().expand(replicas, -1, -1).contiguous().requires_grad_(True)
+            self._rep_in = t
+            return t
+
         if len(self.blocks) and self.blocks[0].fused_ok(x):
             pending = pbias = None
             for i, blk in enumerate(self.blocks):        # the last block's branch meets a plain add: it keeps its own bias gradient
+                if i == replicate_at:
+                    assert pbias is None, "batched GETAM runs outside the training path"
+                    x, pending = replicate(x if pending is None else x + pending), None
                 x, pending, pbias, blk_in = blk.forward_stream(x, pending, pbias, fold_out=i + 1 < len(self.blocks))
                 self._block_in.append(blk_in)
             x = x + pending
         else:
-            for blk in self.blocks:
+            for i, blk in enumerate(self.blocks):
+                if i == replicate_at:
+                    x = replicate(x)
                 self._block_in.append(x)
                 x = blk(x)
         if last_block_out is not None:
@@ -358,6 +373,45 @@ class ACR(nn.Module):
         x_patch_cls = self.cls_head(x_patch.mean(dim=1))
         x_patch_cam = F.relu(self.cls_head(x_patch))
         return x_cls, x_patch_cls, attn, x_patch_cam
+
+    def forward_cam_batched(self, x, replicas, start_layer):
+        """forward_cam for ONE image with the blocks >= start_layer run on `replicas` identical copies (batched GETAM,
+        SURVEY 8f rank 1).  Returns (x_cls [replicas,C] -- one row per copy, all equal up to rounding --, x_patch_cls [1,C],
+        attn [1,L,N,N], x_patch_cam [1,N-1,C]); follow with backward_for_getam_batched(x_cls, classes)."""
+        assert x.shape[0] == 1 and replicas >= 1
+        vit = self.pretrained.model
+        p_h, p_w = x.shape[2] // 16, x.shape[3] // 16
+        N = p_h * p_w + 1
+        L = len(vit.blocks)
+        stack = torch.empty(1, L, N, N, device=x.device, dtype=torch.float32)
+        rep = torch.empty(replicas, L - start_layer, N, N, device=x.device, dtype=torch.float32)
+        for l, blk in enumerate(vit.blocks):
+            blk.attn._slot = stack[:, l] if l < start_layer else rep[:, l - start_layer]
+        last = []
+        with torch.enable_grad():
+            if self.precision == "bf16":
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    vit.forward_flex(x, last, replicate_at=start_layer, replicas=replicas)
+            else:
+                vit.forward_flex(x, last, replicate_at=start_layer, replicas=replicas)
+            layer_4 = last[0].float()
+            x_cls = self.cls_head(layer_4[:, 0, :])
+        for blk in vit.blocks:
+            blk.attn._slot = None
+        stack[0, start_layer:] = rep[0]
+        self.pretrained.activations["4"] = layer_4
+        with torch.no_grad():
+            x_patch = layer_4[:1, 1:, :]
+            x_patch_cls = self.cls_head(x_patch.mean(dim=1))
+            x_patch_cam = F.relu(self.cls_head(x_patch))
+        return x_cls, x_patch_cls, stack, x_patch_cam
+
+    def backward_for_getam_batched(self, x_cls, classes):
+        """One backward for all classes: copy k receives the one-hot cotangent of classes[k] (infer_cam.py:173-179 runs
+        one full backward per class).  Afterwards getam(k, start_layer, ...) is the GETAM of classes[k]."""
+        idx = torch.as_tensor(list(classes), device=x_cls.device)
+        sel = x_cls[torch.arange(len(classes), device=x_cls.device), idx].sum()
+        torch.autograd.grad(sel, self.pretrained.model._rep_in)
 
     def forward_mirror(self, x1, x2):
         """DPT/ACR.py:170-174.  The reference runs the two views one after the other; nothing on the path couples

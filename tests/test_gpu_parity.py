@@ -232,7 +232,7 @@ def test_affinity_refine_matches_oracle(dev, t, normalize):
     assert rel_err(t2n(got1), t2n(ref[..., 0])) < 1e-4
 
 
-def _infer_check(dev, name, precision, tol, truncate=True):
+def _infer_check(dev, name, precision, tol, truncate=True, batch_classes=True):
     from acr_wsss_b200 import infer_cam_image, pseudo_label, synth
     g = load_golden(name)
     C, S = int(g["C"]), int(g["S"])
@@ -244,7 +244,7 @@ def _infer_check(dev, name, precision, tol, truncate=True):
     cam_dict, patch_dict, norm_cam = infer_cam_image(m, img, label, tuple(int(v) for v in g["out_size"]),
                                                      scales=tuple(float(s) for s in g["scales"]),
                                                      start_layer=int(g["start_layer"]), getam_func=str(g["func"]),
-                                                     truncate_backward=truncate)
+                                                     truncate_backward=truncate, batch_classes=batch_classes)
     assert sorted(cam_dict) == present and cam_dict[present[0]].dtype == np.float32
     assert rel_err(np.stack([cam_dict[c] for c in present]), g["norm_cam"]) < tol
     assert rel_err(np.stack([patch_dict[c] for c in present]), g["patch_norm_cam"]) < tol
@@ -274,6 +274,11 @@ def test_infer_cam_fp32_448(dev):
 
 def test_infer_cam_fp32_multiscale(dev):
     _infer_check(dev, "infer_vitb_128_ms.npz", "fp32", FP32_TOL)
+
+
+def test_infer_cam_fp32_per_class_truncated_backward(dev):
+    """One truncated backward per class (the batched-GETAM default is covered by the tests above)."""
+    _infer_check(dev, "infer_vitb_128_ms.npz", "fp32", FP32_TOL, batch_classes=False)
 
 
 def test_infer_cam_fp32_multiscale_full_backward(dev):
