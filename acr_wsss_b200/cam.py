@@ -50,8 +50,9 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
     reference calls these W,H at infer_cam.py:136).  Returns (cam_dict, patch_cam_dict, norm_cam [C,rows,cols])
     with {class_index: float32 [rows,cols]} dicts as saved by np.save at :227-228.
     truncate_backward: stop each per-class backward at block `start_layer` (identical GETAM).
-    batch_classes (needs truncate_backward): the blocks >= start_layer run on one copy of the token stream per present
-    class (at most max_replicas per pass) and ONE backward delivers every class's attention gradients.
+    batch_classes (needs truncate_backward): both flips go through the trunk as one batch of 2, the blocks >= start_layer
+    run on one copy of the token stream per present class (at most max_replicas per pass) and ONE backward delivers every
+    class's attention gradients for both flips.
     """
     assert img.shape[0] == 1, "the reference infers one image at a time (infer_cam.py:122)"
     C = label.shape[1]
@@ -59,34 +60,56 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
     rows, cols = out_size
     present = [ci for ci in range(C) if float(label[0, ci]) > 1e-5]
     cam_list, patch_cam_list = [], []
+    nblocks = len(model.pretrained.model.blocks)
+    batched = truncate_backward and batch_classes and len(present) > 0 and 0 < start_layer < nblocks
+
+    def finish_view(attn, patch_cam, rows0, flipped, ph, pw):
+        """infer_cam.py:153-199 for one flip: patch CAM and (affinity-refined) GETAM maps at the original image size."""
+        patch_cam = patch_cam.permute(0, 2, 1).reshape(1, C, ph, pw)
+        patch_cam = F.interpolate(patch_cam, [rows, cols], mode="bilinear", align_corners=False)[0]
+        patch_cam = patch_cam.detach() * label[0, :].view(C, 1, 1)
+        if flipped:
+            patch_cam = patch_cam.flip(-1)
+        patch_cam_list.append(patch_cam)
+        cam_matrix = torch.zeros(C, rows, cols, device=img.device)
+        if present:
+            cams = torch.stack(rows0, dim=1).unsqueeze(0)        # [1,Np,C']
+            if aff:
+                cams = affinity_refine(attn.detach(), cams, t=t, normalize=normalize)
+            cams = cams[0].t().reshape(len(present), 1, ph, pw)
+            cams = F.interpolate(cams, (rows, cols), mode="bilinear", align_corners=True)[:, 0]
+            cam_matrix[present] = cams
+        if flipped:
+            cam_matrix = cam_matrix.flip(-1)
+        cam_list.append(cam_matrix)
+
     for scale in scales:
+        inp = F.interpolate(img, size=(int(h * scale), int(w * scale)), mode="bilinear", align_corners=False)
+        ph, pw = int((h * scale) // 16), int((w * scale) // 16)
+        model.zero_grad()
+        if batched:
+            # both flips as one batch of 2, every present class as a copy of the token stream from block start_layer on:
+            # one forward and ONE backward per scale (the reference: 2 forwards and 2*C' full backwards)
+            both = torch.cat([inp.flip(-1), inp], dim=0)          # hflip = 1 (flipped) first, then 2, as infer_cam.py:148-151
+            rows_v = [[], []]
+            for c0 in range(0, len(present), max_replicas):
+                chunk = present[c0:c0 + max_replicas]
+                cls_rep, _, attn, patch_cam = model.forward_cam_batched(both, len(chunk), start_layer)
+                model.backward_for_getam_batched(cls_rep, chunk * 2)
+                for v in range(2):
+                    for k in range(len(chunk)):
+                        cam, _, _ = model.getam(v * len(chunk) + k, start_layer=start_layer, func=getam_func)
+                        rows_v[v].append(cam[0])
+            for v in range(2):
+                finish_view(attn[v:v + 1], patch_cam[v:v + 1], rows_v[v], v == 0, ph, pw)
+            continue
         for hflip in (1, 2):
             model.zero_grad()
-            inp = F.interpolate(img, size=(int(h * scale), int(w * scale)), mode="bilinear", align_corners=False)
-            if hflip % 2 == 1:
-                inp = inp.flip(-1)
-            ph, pw = int((h * scale) // 16), int((w * scale) // 16)
-            batched = truncate_backward and batch_classes and len(present) > 0 and 0 < start_layer < len(model.pretrained.model.blocks)
+            view = inp.flip(-1) if hflip % 2 == 1 else inp
+            cls_pred, _, attn, patch_cam = model.forward_cam(view)
+            output = cls_pred[0, :]
             rows0 = []
-            if batched:
-                for c0 in range(0, len(present), max_replicas):
-                    chunk = present[c0:c0 + max_replicas]
-                    cls_rep, _, attn, patch_cam = model.forward_cam_batched(inp, len(chunk), start_layer)
-                    model.backward_for_getam_batched(cls_rep, chunk)
-                    for k in range(len(chunk)):
-                        cam, _, _ = model.getam(k, start_layer=start_layer, func=getam_func)
-                        rows0.append(cam[0])
-            else:
-                cls_pred, _, attn, patch_cam = model.forward_cam(inp)
-            patch_cam = patch_cam.permute(0, 2, 1).reshape(1, C, ph, pw)
-            patch_cam = F.interpolate(patch_cam, [rows, cols], mode="bilinear", align_corners=False)[0]
-            patch_cam = patch_cam.detach() * label[0, :].view(C, 1, 1)
-            if hflip % 2 == 1:
-                patch_cam = patch_cam.flip(-1)
-            patch_cam_list.append(patch_cam)
-
-            output = None if batched else cls_pred[0, :]
-            for ci in ([] if batched else present):
+            for ci in present:
                 if truncate_backward:
                     model.backward_for_getam(output[ci], start_layer)
                 else:
@@ -94,17 +117,7 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
                     output[ci].backward(retain_graph=True)      # one_hot * output, infer_cam.py:173-179
                 cam, _, _ = model.getam(0, start_layer=start_layer, func=getam_func)
                 rows0.append(cam[0])
-            cam_matrix = torch.zeros(C, rows, cols, device=img.device)
-            if present:
-                cams = torch.stack(rows0, dim=1).unsqueeze(0)        # [1,Np,C']
-                if aff:
-                    cams = affinity_refine(attn.detach(), cams, t=t, normalize=normalize)
-                cams = cams[0].t().reshape(len(present), 1, ph, pw)
-                cams = F.interpolate(cams, (rows, cols), mode="bilinear", align_corners=True)[:, 0]
-                cam_matrix[present] = cams
-            if hflip % 2 == 1:
-                cam_matrix = cam_matrix.flip(-1)
-            cam_list.append(cam_matrix)
+            finish_view(attn, patch_cam, rows0, hflip % 2 == 1, ph, pw)
     patch_sum = torch.stack(patch_cam_list).sum(0)
     patch_norm = normalize_cam(patch_sum, 1e-5)
     sum_cam = torch.stack(cam_list).sum(0)

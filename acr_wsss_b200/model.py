@@ -245,8 +245,8 @@ class VisionTransformer(nn.Module):
         self._block_in = []            # input of every block (references): lets GETAM stop its backward at start_layer
         self._rep_in = None
 
-        def replicate(t):
-            t = t.detach().expand(replicas, -1, -1).contiguous().requires_grad_(True)
+        def replicate(t):       # sample b -> copies b*replicas .. b*replicas + replicas - 1
+            t = t.detach().repeat_interleave(replicas, dim=0).requires_grad_(True)
             self._rep_in = t
             return t
 
@@ -375,16 +375,17 @@ class ACR(nn.Module):
         return x_cls, x_patch_cls, attn, x_patch_cam
 
     def forward_cam_batched(self, x, replicas, start_layer):
-        """forward_cam for ONE image with the blocks >= start_layer run on `replicas` identical copies (batched GETAM,
-        SURVEY 8f rank 1).  Returns (x_cls [replicas,C] -- one row per copy, all equal up to rounding --, x_patch_cls [1,C],
-        attn [1,L,N,N], x_patch_cam [1,N-1,C]); follow with backward_for_getam_batched(x_cls, classes)."""
-        assert x.shape[0] == 1 and replicas >= 1
+        """forward_cam with the blocks >= start_layer run on `replicas` identical copies of every sample (batched GETAM,
+        SURVEY 8f rank 1); copy k of sample b sits at batch index b*replicas + k.  Returns (x_cls [B*replicas,C],
+        x_patch_cls [B,C], attn [B,L,N,N], x_patch_cam [B,N-1,C]); follow with backward_for_getam_batched(x_cls, classes)."""
+        assert replicas >= 1
         vit = self.pretrained.model
+        B = x.shape[0]
         p_h, p_w = x.shape[2] // 16, x.shape[3] // 16
         N = p_h * p_w + 1
         L = len(vit.blocks)
-        stack = torch.empty(1, L, N, N, device=x.device, dtype=torch.float32)
-        rep = torch.empty(replicas, L - start_layer, N, N, device=x.device, dtype=torch.float32)
+        stack = torch.empty(B, L, N, N, device=x.device, dtype=torch.float32)
+        rep = torch.empty(B * replicas, L - start_layer, N, N, device=x.device, dtype=torch.float32)
         for l, blk in enumerate(vit.blocks):
             blk.attn._slot = stack[:, l] if l < start_layer else rep[:, l - start_layer]
         last = []
@@ -398,17 +399,17 @@ class ACR(nn.Module):
             x_cls = self.cls_head(layer_4[:, 0, :])
         for blk in vit.blocks:
             blk.attn._slot = None
-        stack[0, start_layer:] = rep[0]
+        stack[:, start_layer:] = rep[::replicas]
         self.pretrained.activations["4"] = layer_4
         with torch.no_grad():
-            x_patch = layer_4[:1, 1:, :]
+            x_patch = layer_4[::replicas, 1:, :]
             x_patch_cls = self.cls_head(x_patch.mean(dim=1))
             x_patch_cam = F.relu(self.cls_head(x_patch))
         return x_cls, x_patch_cls, stack, x_patch_cam
 
     def backward_for_getam_batched(self, x_cls, classes):
-        """One backward for all classes: copy k receives the one-hot cotangent of classes[k] (infer_cam.py:173-179 runs
-        one full backward per class).  Afterwards getam(k, start_layer, ...) is the GETAM of classes[k]."""
+        """One backward for all copies: batch index i receives the one-hot cotangent of classes[i] (infer_cam.py:173-179
+        runs one full backward per class).  Afterwards getam(i, start_layer, ...) is the GETAM of classes[i] for that copy."""
         idx = torch.as_tensor(list(classes), device=x_cls.device)
         sel = x_cls[torch.arange(len(classes), device=x_cls.device), idx].sum()
         torch.autograd.grad(sel, self.pretrained.model._rep_in)
