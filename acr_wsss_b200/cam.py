@@ -122,8 +122,26 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
     patch_norm = normalize_cam(patch_sum, 1e-5)
     sum_cam = torch.stack(cam_list).sum(0)
     norm_cam = normalize_cam(sum_cam, 1e-6)
-    norm_np = norm_cam.cpu().numpy()
-    patch_np = patch_norm.cpu().numpy()
-    cam_dict = {ci: norm_np[ci] for ci in present}
-    patch_cam_dict = {ci: patch_np[ci] for ci in present}
+    # only the present classes go to the host (what the reference keeps, infer_cam.py:217-228), through one pinned buffer
+    if present:
+        both = torch.stack([norm_cam[present], patch_norm[present]])           # [2,C',rows,cols]
+        host = _pinned(both.shape) if both.is_cuda else torch.empty(both.shape)
+        host.copy_(both, non_blocking=True)
+        if both.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        host_np = host.numpy().copy()
+    cam_dict = {ci: host_np[0, k] for k, ci in enumerate(present)}
+    patch_cam_dict = {ci: host_np[1, k] for k, ci in enumerate(present)}
     return cam_dict, patch_cam_dict, norm_cam
+
+
+_PINNED = {}
+
+
+def _pinned(shape):
+    key = tuple(shape)
+    if key not in _PINNED:
+        if len(_PINNED) > 8:
+            _PINNED.clear()
+        _PINNED[key] = torch.empty(key, dtype=torch.float32, pin_memory=True)
+    return _PINNED[key]
