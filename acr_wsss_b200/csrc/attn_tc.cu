@@ -440,6 +440,7 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
       attr_set = true;
     }
     dim3 grid(qt, H, B);
+    acr::KernelTimer kt_("attn_fwd_kernel", st);
     attn_fwd_kernel<<<grid, 256, smem, st>>>(tmap, (__nv_bfloat16*)out, lse, N, H, scale_log2);
     if (int e = acr::check_launch("attn_fwd_kernel")) return e;
   }
@@ -451,6 +452,7 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
       attr_set = true;
     }
     dim3 grid(kt, qt, B);
+    acr::KernelTimer kt_("attn_mean_kernel", st);
     attn_mean_kernel<0><<<grid, 384, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, (long long)N, GCode{}, p_row0, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel")) return e;
   }
@@ -862,6 +864,7 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
       attr_set = true;
     }
     dim3 grid(kt, qt, B);
+    acr::KernelTimer kt_("attn_delta_kernel", st);
     attn_mean_kernel<1><<<grid, 384, smem, st>>>(tmap_qkv, lse, const_cast<float*>(g_mean), g_batch_stride, g_row_stride, gc, delta, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel<1>")) return e;
   }
@@ -873,6 +876,7 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
       attr_set = true;
     }
     dim3 grid(kt, H, B);
+    acr::KernelTimer kt_("attn_bwd_kernel", st);
     attn_bwd_kernel<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, lse, delta, g_mean, g_batch_stride, g_row_stride, gc, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
                                              N, H, scale, scale_log2);
     if (int e = acr::check_launch("attn_bwd_kernel")) return e;

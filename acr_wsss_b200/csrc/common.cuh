@@ -44,6 +44,25 @@ int launch_sgemm(const float* A, Mat la, const float* B, Mat lb, float* C, Mat l
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Per-kernel device timing for bench.py's roofline (acr_profile_enable / acr_profile_read): while enabled, a KernelTimer
+// around a launch records a CUDA event pair on the launching stream.  Off by default and never on during graph capture.
+bool profiling_on();
+void profile_record(const char* kernel, cudaEvent_t a, cudaEvent_t b);
+struct KernelTimer {
+  const char* name;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  KernelTimer(const char* n, cudaStream_t s) : name(n), st(s) {
+    if (profiling_on() && cudaEventCreate(&a) == cudaSuccess && cudaEventCreate(&b) == cudaSuccess) cudaEventRecord(a, st);
+  }
+  ~KernelTimer() {
+    if (a && b) {
+      cudaEventRecord(b, st);
+      profile_record(name, a, b);
+    }
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -9,6 +9,7 @@ classes, B=8 per GPU), BCE + all-pairs consistency loss, backward, gradient all-
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -185,6 +186,8 @@ def run_ours(args):
     # recorded inside them); the same forward+backward is therefore run eagerly K more times with CUDA events around
     # every C-ABI call on the launching stream.  Identical kernels, shapes and launch counts.
     ops.PROFILE.reset(enabled=True)
+    L = _lib.lib()
+    L.acr_profile_enable(1)            # CUDA event pairs around the tensor-core attention kernels themselves (inside the C ABI)
     side = trainer._side if trainer._side is not None else torch.cuda.current_stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -193,6 +196,12 @@ def run_ours(args):
     torch.cuda.current_stream().wait_stream(side)
     prof = ops.PROFILE.summary()
     ops.PROFILE.reset(enabled=False)
+    kern = {}
+    for kname in ("attn_fwd_kernel", "attn_mean_kernel", "attn_delta_kernel", "attn_bwd_kernel"):
+        tot, cnt = ctypes.c_double(0.0), ctypes.c_longlong(0)
+        if L.acr_profile_read(kname.encode(), ctypes.byref(tot), ctypes.byref(cnt)) == 0 and cnt.value:
+            kern[kname] = {"ms": tot.value, "launches": cnt.value}
+    L.acr_profile_enable(0)
     launches = prof["launches"] // args.steps * args.steps
 
     # secondary metric: CAM inference (BASELINE.json configs[0]): forward_cam + GETAM over 3 present classes + affinity
@@ -217,18 +226,37 @@ def run_ours(args):
         imgs = B * world * args.steps
         value = imgs / (ms_dev / 1e3)
         e2e = imgs / (ms_e2e / 1e3)
-        # dominant kernel group: the fused attention backward (one C-ABI call per block and view)
-        dom = prof["kernels"].get("acr_attn_bwd_bf16" if precision == "bf16" else "acr_attn_bwd_f32", None)
-        # algorithmic FLOPs of one call (both views of the B images go through the trunk as one batch of 2B); recompute not counted
+        # dominant kernel: attn_bwd_kernel (one launch per block on the 2B images of both views), timed by CUDA events
+        # recorded around the launch itself inside the C ABI during the eager replay
+        dom = kern.get("attn_bwd_kernel") if precision == "bf16" else None
+        # algorithmic FLOPs of one launch: dP, dV, dK, dQ = 4 GEMMs of 2*N^2*D per head and image; the S recompute is not counted
         flops_bwd = 8.0 * (2 * B) * HEADS * N_TOK * N_TOK * HD
         roof = None
-        if dom and dom["calls"]:
-            avg_ms = dom["ms"] / dom["calls"]
+        if dom:
+            avg_ms = dom["ms"] / dom["launches"]
             ach = flops_bwd / (avg_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": dom["name"], "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tflops_sustained"], "traffic": None, "avg_launch_ms": avg_ms, "calls_per_step": dom["calls"] / args.steps,
-                    "peak_source": pk["src"] + " (sustained bf16 cuBLAS)",
-                    "share_of_step": dom["ms"] / ms_dev, "timing": "CUDA events around each call in an eager replay of the same steps (timed steps are CUDA graphs)", "per_kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof["kernels"].items()}}
+            traffic, traffic_src = None, None
+            tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "roofline_traffic.json")
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                if tj.get("kernel") == "attn_bwd_kernel":
+                    traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            roof = {"bound": "tensor", "kernel": "attn_bwd_kernel", "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tflops_sustained"], "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
+                    "avg_launch_ms": avg_ms, "launches_per_step": dom["launches"] / args.steps,
+                    "algorithmic_flop_per_launch": flops_bwd,
+                    "peak_source": pk["src"] + " (sustained bf16 cuBLAS; the kernel runs inside a long step)",
+                    "share_of_step": dom["ms"] / ms_dev,
+                    "timing": "CUDA events around the kernel launch on its stream, eager replay of the same steps (the timed steps are CUDA graphs)",
+                    "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in kern.items()},
+                    "entry_points_ms_per_step": {k: v["ms"] / args.steps for k, v in prof["kernels"].items()}}
+        elif precision != "bf16":
+            d32 = prof["kernels"].get("acr_attn_bwd_f32")
+            if d32 and d32["calls"]:
+                avg_ms = d32["ms"] / d32["calls"]
+                ach = flops_bwd / (avg_ms * 1e-3) / 1e12
+                roof = {"bound": "tensor", "kernel": d32["name"], "achieved": ach, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / pk["tflops_sustained"], "traffic": None, "avg_launch_ms": avg_ms, "peak_source": pk["src"]}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

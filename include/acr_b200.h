@@ -35,6 +35,13 @@ const char* acr_last_error_string(void);
 /* 1 when the current device is compute capability 10.x (tcgen05/TMEM/TMA kernels usable). */
 int acr_device_is_sm100(void);
 
+/* Per-kernel device timing (bench.py's roofline): while enabled, the tensor-core attention kernels are bracketed by CUDA
+ * event pairs on the launching stream.  acr_profile_read sums the elapsed time of every recorded launch of `kernel`
+ * ("attn_fwd_kernel", "attn_mean_kernel", "attn_delta_kernel", "attn_bwd_kernel") after synchronising its events;
+ * acr_profile_enable(0) drops the records.  Must be off during CUDA-graph capture. */
+void acr_profile_enable(int on);
+int acr_profile_read(const char* kernel, double* total_ms, long long* launches);
+
 /* ------------------------------------------------------------------------------------------
  * (a1) Attention core.  Replaces models/vision_transformer.py:198-214 (Attention.forward, the part
  * between the qkv Linear and the proj Linear) together with the head mean of DPT/ACR.py:107-112.
