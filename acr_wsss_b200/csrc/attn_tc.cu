@@ -620,7 +620,7 @@ __device__ __forceinline__ void bwd_tile_body(BwdSmem& s, int buf, uint32_t tS, 
 // i+1 only wait for 2 of the 5 MMAs; dQ tiles are reduced over key tiles with vectorised fp32 reductions.
 __global__ void __launch_bounds__(384, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                const float* __restrict__ lse, const float* __restrict__ delta, const float* __restrict__ g_mean, long long g_bs,
+                const __grid_constant__ CUtensorMap tmap_dq, const float* __restrict__ lse, const float* __restrict__ delta, const float* __restrict__ g_mean, long long g_bs,
                 long long g_ld, GCode gc, __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ dq_acc, float* __restrict__ g_row0,
                 int N, int H, float scale, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
@@ -632,6 +632,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_qkv);
     tc::prefetch_tmap(&tmap_do);
+    tc::prefetch_tmap(&tmap_dq);
     tc::mbar_init(&s.kv_full, 1);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.qdo_full[i], 1); tc::mbar_init(&s.qdo_empty[i], 1); }
     tc::mbar_init(&s.sdp_full, 1);
@@ -718,14 +719,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const float* stat_l = lse + ((size_t)b * H + h) * N;
     const float* stat_d = delta + ((size_t)b * H + h) * N;
     uint32_t rs[32];
-    // rows = queries (lanes), 64 columns = d; this thread reduces its 32 columns of query row q into the fp32 accumulator
-    auto reduce_dq = [&](int q) {
-      float* dqp = dq_acc + (((size_t)b * H + h) * N + q) * HD + half * 32;
+    // dQ of query tile t (rows = queries, this thread: 32 of the 64 d columns of one row) -> fp32 accumulator [B*H,N,64].
+    // Staged in the P tile of buffer t&1 -- free once the gradient MMAs of tile t have retired (dq_full(t)) and until the
+    // softmax of tile t+2 -- as two [128 x 32] fp32 SWIZZLE_128B tiles and added by two TMA reduce-adds
+    // (cp.reduce.async.bulk.tensor).  The 2048 scattered RED.128 per tile this replaces cost 13 % of the kernel (half-used
+    // L2 sectors); rows past N are clipped by the tensor map.
+    const bool dq_leader = (we == 0 && lane == 0);
+    auto push_dq = [&](int t) {
+      uint8_t* drow = s.p[t & 1][half] + row * 128;
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dqp + 4 * e), "f"(__uint_as_float(rs[4 * e])),
-                     "f"(__uint_as_float(rs[4 * e + 1])), "f"(__uint_as_float(rs[4 * e + 2])), "f"(__uint_as_float(rs[4 * e + 3]))
-                     : "memory");
+        *reinterpret_cast<uint4*>(drow + ((e ^ (row & 7)) << 4)) = make_uint4(rs[4 * e], rs[4 * e + 1], rs[4 * e + 2], rs[4 * e + 3]);
+      tc::fence_proxy_async_smem();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (dq_leader) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmap_dq)),
+                       "r"(tc::smem_u32(s.p[t & 1][hh])), "r"(hh * 32), "r"(t * BM), "r"(b * H + h)
+                       : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
     };
     float lse_n = (row < N) ? __ldg(stat_l + row) : INFINITY;   // natural-log LSE; scaled to log2 at use
     float dlt_n = (row < N) ? __ldg(stat_d + row) : 0.f;
@@ -745,6 +760,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       float* rd_row0 = (g_row0 != nullptr && qi == 0) ? g_row0 + ((size_t)b * H + h) * N + colbase : nullptr;
       tc::mbar_wait(&s.sdp_full, i & 1);
       tc::tc_fence_after();
+      if (i >= 2) {       // the TMA reduce of dQ(i-2) read its staging copy out of P[i&1]: it must be done before P(i) is written
+        if (dq_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+      }
       // specialised bodies (uniform branches): affinity gradient present / key tail tile
       if (q0 + (warp & 3) * 32 >= N) {
         // all 32 query rows of this warp lie past N (last query tile): nothing to compute, the tiles just need finite
@@ -773,13 +792,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&s.pds_full);
-      if (i > 0 && qi - BM < N) reduce_dq(qi - BM);
+      if (i > 0) push_dq(i - 1);
     }
     tc::mbar_wait(&s.dq_full, (ntiles - 1) & 1);
     tc::tc_fence_after();
     tc::tmem_ld32(tDQ + lane_off + half * 32, rs);
     tc::tmem_ld_wait();
-    if ((ntiles - 1) * BM + row < N) reduce_dq((ntiles - 1) * BM + row);
+    push_dq(ntiles - 1);
     // epilogue: dV, dK rows (lanes = keys) of this key tile; all MMAs are complete (the last dq_full covered them)
     const bool kv_ok = (kv0 + row) < N;
     uint32_t rd[32];
@@ -805,6 +824,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         reinterpret_cast<uint4*>(dkp)[c] = k;
       }
     }
+    // the TMA reduce-adds are asynchronous: they must complete before the CTA (and its shared memory) goes away
+    if (dq_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -847,9 +868,20 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
   const size_t rows = (size_t)B * H * N;
   float* delta = (float*)workspace;
   float* dq_acc = (float*)((char*)workspace + acr::align_up(rows * sizeof(float), 256));
-  CUtensorMap tmap_qkv, tmap_do;
+  CUtensorMap tmap_qkv, tmap_do, tmap_dq;
   if (int e = make_tmap(&tmap_qkv, qkv, B, N, 3 * H, D)) return e;
   if (int e = make_tmap(&tmap_do, d_out, B, N, H, D)) return e;
+  {   // fp32 dQ accumulator [B*H, N, 64] as (d, n, bh); box = 32 floats (128 B, SWIZZLE_128B) x 128 rows
+    EncodeTiledFn fn = get_encode_fn();
+    ACR_REQUIRE(fn != nullptr, ACR_E_NOSM100, "cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[3] = {(cuuint64_t)HD, (cuuint64_t)N, (cuuint64_t)B * H};
+    cuuint64_t strides[2] = {(cuuint64_t)HD * 4, (cuuint64_t)N * HD * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)BM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(&tmap_dq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dq_acc, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACR_REQUIRE(r == CUDA_SUCCESS, ACR_E_INVAL, "cuTensorMapEncodeTiled(dq) failed (%d)", (int)r);
+  }
   const float scale_log2 = scale * kLog2e;
   const int qt = (N + BM - 1) / BM, kt = (N + BN - 1) / BN;
 
@@ -877,7 +909,7 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
     }
     dim3 grid(kt, H, B);
     acr::KernelTimer kt_("attn_bwd_kernel", st);
-    attn_bwd_kernel<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, lse, delta, g_mean, g_batch_stride, g_row_stride, gc, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
+    attn_bwd_kernel<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, tmap_dq, lse, delta, g_mean, g_batch_stride, g_row_stride, gc, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
                                              N, H, scale, scale_log2);
     if (int e = acr::check_launch("attn_bwd_kernel")) return e;
   }
