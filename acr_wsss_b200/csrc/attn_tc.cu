@@ -310,10 +310,21 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
           }
       }
     }
-    // log2-domain LSE of this tile's rows for every head, staged once: s.lse2[h][row] (+inf for rows past N -> P = 0)
-    for (int e = we * 32 + lane; e < H * BM; e += 256) {
-      const int hh = e / BM, rr = e % BM;
-      s.lse2[hh][rr] = (q0 + rr < N) ? __ldg(lse + ((size_t)b * H + hh) * N + q0 + rr) * kLog2e : INFINITY;
+    // log2-domain LSE of this tile's rows for every head, staged once: s.lse2[h][row] (+inf for rows past N -> P = 0).
+    // Thread t owns row t & 127 for heads (t >> 7), +2, ...; the loads of a batch of 8 heads are issued before the first
+    // store so that their latencies overlap (this sits on the CTA's critical path before the first head).
+    {
+      const int t = we * 32 + lane, rr = t & (BM - 1);
+      const bool ok = (q0 + rr) < N;
+      const float* lp = lse + (size_t)b * H * N + q0 + rr;
+      for (int h0 = t >> 7; h0 < H; h0 += 16) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (ok && h0 + 2 * k < H) ? __ldg(lp + (size_t)(h0 + 2 * k) * N) : INFINITY;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (h0 + 2 * k < H) s.lse2[h0 + 2 * k][rr] = v[k] * kLog2e;
+      }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const bool tail = (kv0 + BN > N);
@@ -365,13 +376,25 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
 #pragma unroll
     for (int i = 0; i < 64; ++i) stage[row * STAGE_LD + half * 64 + i] = acc[i] * invH;
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    // each warp writes 16 rows, 4 at a time: 16 shared loads in flight before the 16 (row-contiguous, 128-byte) stores
     float* dst = mean + (size_t)b * mean_bs;
-    for (int rr = we * 16; rr < we * 16 + 16; ++rr) {
-      if (q0 + rr >= N) break;
+#pragma unroll 1
+    for (int r4 = we * 16; r4 < we * 16 + 16; r4 += 4) {
+      if (q0 + r4 >= N) break;
+      float v[4][4];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int col = cc * 32 + lane;
-        if (kv0 + col < N) dst[(size_t)(q0 + rr) * N + kv0 + col] = stage[rr * STAGE_LD + col];
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) v[u][cc] = stage[(r4 + u) * STAGE_LD + cc * 32 + lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (q0 + r4 + u < N) {
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int col = cc * 32 + lane;
+            if (kv0 + col < N) dst[(size_t)(q0 + r4 + u) * N + kv0 + col] = v[u][cc];
+          }
+        }
       }
     }
     }  // MODE == 0
