@@ -44,8 +44,8 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ res, v
                      const float* __restrict__ beta, int M, float eps, void* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
   constexpr int E = 128 * VEC;
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  if (row >= M) return;
+  // grid-stride over rows: the grid is sized to the resident warps of the device (no ragged last wave)
+  for (long long row = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * kWarpsPerCta) {
   float4 v[VEC];
   float s = 0.f;
 #pragma unroll
@@ -78,6 +78,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, const void* __restrict__ res, v
     const float o0 = (v[i].x - mu) * rs * g.x + bb.x, o1 = (v[i].y - mu) * rs * g.y + bb.y;
     const float o2 = (v[i].z - mu) * rs * g.z + bb.z, o3 = (v[i].w - mu) * rs * g.w + bb.w;
     store4<OUT_BF16>(y, row * (E / 4) + i * 32 + lane, make_float4(o0, o1, o2, o3));
+  }
   }
 }
 
@@ -239,7 +240,7 @@ constexpr int kBwdCtas = 296;     // 2 per SM
 template <int VEC>
 int launch_fwd(const void* x, int x_bf16, const void* res, void* sum_out, const float* gamma, const float* beta, int M, float eps, void* y, int y_bf16, float* mean,
                float* rstd, cudaStream_t st) {
-  const unsigned grid = (unsigned)((M + kWarpsPerCta - 1) / kWarpsPerCta);
+  const unsigned grid = (unsigned)std::min((M + kWarpsPerCta - 1) / kWarpsPerCta, 148 * 8);
   const int T = kWarpsPerCta * 32;
   if (x_bf16) {
     if (y_bf16) layernorm_fwd_kernel<VEC, true, true><<<grid, T, 0, st>>>(x, res, sum_out, gamma, beta, M, eps, y, mean, rstd);
