@@ -278,14 +278,16 @@ class _LinearCachedBF16(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         dx = (dy2 @ w16).view(ctx.in_shape) if ctx.needs_input_grad[0] else None
         gw = gb = None
-        if weight.grad is not None and weight.grad.dtype == torch.float32 and dy2.is_cuda and dy2.dtype == torch.bfloat16:
+        if not ctx.needs_input_grad[1]:
+            pass                                    # e.g. the truncated GETAM backward: only the activations' gradient is wanted
+        elif weight.grad is not None and weight.grad.dtype == torch.float32 and dy2.is_cuda and dy2.dtype == torch.bfloat16:
             # dW accumulated by the GEMM itself: bf16 operands, fp32 accumulator written in place (no bf16 dW, no add kernel)
             torch.addmm(weight.grad, dy2.t(), x2, out_dtype=torch.float32, out=weight.grad)
         elif weight.grad is not None:
             weight.grad.add_(dy2.t() @ x2)
         else:
             gw = (dy2.t() @ x2).float()
-        if bias is not None:
+        if bias is not None and ctx.needs_input_grad[2]:
             if bias.grad is not None and dy2.is_cuda and dy2.dtype == torch.bfloat16 and dy2.is_contiguous() and dy2.shape[1] % 2 == 0:
                 colsum_bf16(dy2, bias.grad, accumulate=True)       # db accumulated straight into the fp32 .grad
             else:
@@ -339,7 +341,8 @@ class _LinearGeluCachedBF16(torch.autograd.Function):
         M, F = f.shape
         dy2 = dy.reshape(M, F).contiguous()
         df = torch.empty_like(f)
-        fused_bias = bias is not None and bias.grad is not None and bias.grad.dtype == torch.float32
+        want_w, want_b = ctx.needs_input_grad[1], bias is not None and ctx.needs_input_grad[2]
+        fused_bias = want_b and bias.grad is not None and bias.grad.dtype == torch.float32
         gb = None
         if fused_bias:
             wsb = _lib.lib().acr_gelu_bwd_workspace(F)
@@ -347,11 +350,13 @@ class _LinearGeluCachedBF16(torch.autograd.Function):
             _call("acr_gelu_bwd_bf16", 2, _p(f), _p(dy2), _p(df), M, F, _p(bias.grad), 1, _p(ws), wsb, _stream())
         else:
             _call("acr_gelu_bwd_bf16", 1, _p(f), _p(dy2), _p(df), M, F, None, 0, None, 0, _stream())
-            if bias is not None:
+            if want_b:
                 gb = df.sum(0, dtype=torch.float32)
         dx = (df @ w16).view(ctx.in_shape) if ctx.needs_input_grad[0] else None
         gw = None
-        if weight.grad is not None and weight.grad.dtype == torch.float32:
+        if not want_w:
+            pass
+        elif weight.grad is not None and weight.grad.dtype == torch.float32:
             torch.addmm(weight.grad, df.t(), x2, out_dtype=torch.float32, out=weight.grad)
         else:
             gw = (df.t() @ x2).float()
