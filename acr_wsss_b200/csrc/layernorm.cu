@@ -88,15 +88,22 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ dres,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, int M, int rows_per_cta,
                      void* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b, float* __restrict__ part_c) {
   constexpr int E = 128 * VEC;
-  __shared__ float red[kWarpsPerCta][32 * 4 + 4];
+  constexpr int NARR = COLSUM ? 3 : 2;
+  // Column-owned partial sums (d-gamma, d-beta, column sums of dx) live in SHARED memory, one private strip per warp
+  // (float4 per lane -> conflict-free, no atomics): in registers they cost 72 registers per thread at E = 768 and held
+  // the kernel to 8 warps per SM; this way 2 CTAs (16 warps) are resident and the loads of more rows are in flight.
+  extern __shared__ float4 acc_sm[];          // [NARR][kWarpsPerCta][VEC * 32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 g[VEC], ag[VEC], ab[VEC], ac[COLSUM ? VEC : 1];      // ac: column sums of dx
+  float4* ag = acc_sm + (0 * kWarpsPerCta + warp) * (VEC * 32) + lane;
+  float4* ab = acc_sm + (1 * kWarpsPerCta + warp) * (VEC * 32) + lane;
+  float4* ac = acc_sm + ((COLSUM ? 2 : 1) * kWarpsPerCta + warp) * (VEC * 32) + lane;
+  float4 g[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
-    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (COLSUM) ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (COLSUM) ac[i * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min((long long)M, r0 + rows_per_cta);
@@ -109,8 +116,14 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ dres,
       d[i] = load4<DY_BF16>(dy, row * (E / 4) + i * 32 + lane);
       const float4 xv = load4<X_BF16>(x, row * (E / 4) + i * 32 + lane);
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-      ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
-      ag[i].x += d[i].x * xh[i].x; ag[i].y += d[i].y * xh[i].y; ag[i].z += d[i].z * xh[i].z; ag[i].w += d[i].w * xh[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float4 tb = ab[i * 32], tg = ag[i * 32];
+      tb.x += d[i].x; tb.y += d[i].y; tb.z += d[i].z; tb.w += d[i].w;
+      tg.x += d[i].x * xh[i].x; tg.y += d[i].y * xh[i].y; tg.z += d[i].z * xh[i].z; tg.w += d[i].w * xh[i].w;
+      ab[i * 32] = tb;
+      ag[i * 32] = tg;
       d[i].x *= g[i].x; d[i].y *= g[i].y; d[i].z *= g[i].z; d[i].w *= g[i].w;       // dy * gamma
       s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
       s2 += (d[i].x * xh[i].x + d[i].y * xh[i].y) + (d[i].z * xh[i].z + d[i].w * xh[i].w);
@@ -132,27 +145,22 @@ layernorm_bwd_kernel(const void* __restrict__ dy, const void* __restrict__ dres,
           o.x = __bfloat162float(__float2bfloat16(o.x)); o.y = __bfloat162float(__float2bfloat16(o.y));
           o.z = __bfloat162float(__float2bfloat16(o.z)); o.w = __bfloat162float(__float2bfloat16(o.w));
         }
-        ac[i].x += o.x; ac[i].y += o.y; ac[i].z += o.z; ac[i].w += o.w;
+        float4 tc_ = ac[i * 32];
+        tc_.x += o.x; tc_.y += o.y; tc_.z += o.z; tc_.w += o.w;
+        ac[i * 32] = tc_;
       }
     }
   }
-  // fold the CTA's warps: column-owned partial sums -> one partial row per CTA
+  // fold the CTA's warps in a fixed order: one partial row per CTA and array
+  __syncthreads();
+  const float* accf = reinterpret_cast<const float*>(acc_sm);
+  for (int a = 0; a < NARR; ++a) {
+    float* dst = (a == 0 ? part_g : (a == 1 ? part_b : part_c)) + (long long)blockIdx.x * E;
+    for (int c = threadIdx.x; c < E; c += kWarpsPerCta * 32) {
+      float t = 0.f;
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    for (int pass = 0; pass < (COLSUM ? 3 : 2); ++pass) {
-      const float4 v = pass == 0 ? ag[i] : (pass == 1 ? ab[i] : ac[COLSUM ? i : 0]);
-      red[warp][lane * 4 + 0] = v.x; red[warp][lane * 4 + 1] = v.y; red[warp][lane * 4 + 2] = v.z; red[warp][lane * 4 + 3] = v.w;
-      __syncthreads();
-      if (warp == 0) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int w = 0; w < kWarpsPerCta; ++w) {
-          t.x += red[w][lane * 4 + 0]; t.y += red[w][lane * 4 + 1]; t.z += red[w][lane * 4 + 2]; t.w += red[w][lane * 4 + 3];
-        }
-        float* dst = (pass == 0 ? part_g : (pass == 1 ? part_b : part_c)) + (long long)blockIdx.x * E;
-        reinterpret_cast<float4*>(dst)[i * 32 + lane] = t;
-      }
-      __syncthreads();
+      for (int w = 0; w < kWarpsPerCta; ++w) t += accf[(a * kWarpsPerCta + w) * E + c];
+      dst[c] = t;
     }
   }
 }
@@ -235,7 +243,7 @@ colsum_finish_kernel(const float* __restrict__ partial, int nparts, int F, float
   out[c] = accumulate ? out[c] + s : s;
 }
 
-constexpr int kBwdCtas = 296;     // 2 per SM
+constexpr int kBwdCtas = 296;     // 2 per SM (register limit: ~105 per thread at E = 768)
 
 template <int VEC>
 int launch_fwd(const void* x, int x_bf16, const void* res, void* sum_out, const float* gamma, const float* beta, int M, float eps, void* y, int y_bf16, float* mean,
@@ -261,16 +269,28 @@ int launch_bwd(const void* dy, int dy_bf16, const void* dres, const void* x, int
   float* pb = parts + (size_t)kBwdCtas * E;
   float* pc = dx_colsum ? parts + (size_t)2 * kBwdCtas * E : nullptr;
   const int T = kWarpsPerCta * 32;
+#define ACR_LN_BWD(DYB, XB, CS)                                                                                              \
+  do {                                                                                                                      \
+    auto kfn = layernorm_bwd_kernel<VEC, DYB, XB, CS>;                                                                      \
+    const size_t smem = (size_t)(CS ? 3 : 2) * kWarpsPerCta * E * sizeof(float);                                            \
+    static bool attr_set = false;                                                                                           \
+    if (!attr_set) {                                                                                                        \
+      ACR_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
+      attr_set = true;                                                                                                      \
+    }                                                                                                                       \
+    kfn<<<ctas, T, smem, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);                            \
+  } while (0)
   if (pc != nullptr) {          // column sums of dx: bf16 stream only (the trunk's residual path)
     ACR_REQUIRE(x_bf16 && dy_bf16, ACR_E_INVAL, "acr_layernorm_bwd: dx_colsum needs bf16 x and dy");
-    layernorm_bwd_kernel<VEC, true, true, true><<<ctas, T, 0, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);
+    ACR_LN_BWD(true, true, true);
   } else if (x_bf16) {
-    if (dy_bf16) layernorm_bwd_kernel<VEC, true, true><<<ctas, T, 0, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);
-    else layernorm_bwd_kernel<VEC, false, true><<<ctas, T, 0, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);
+    if (dy_bf16) ACR_LN_BWD(true, true, false);
+    else ACR_LN_BWD(false, true, false);
   } else {
-    if (dy_bf16) layernorm_bwd_kernel<VEC, true, false><<<ctas, T, 0, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);
-    else layernorm_bwd_kernel<VEC, false, false><<<ctas, T, 0, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);
+    if (dy_bf16) ACR_LN_BWD(true, false, false);
+    else ACR_LN_BWD(false, false, false);
   }
+#undef ACR_LN_BWD
   if (int e = acr::check_launch("layernorm_bwd_kernel")) return e;
   layernorm_bwd_finish_kernel<<<(E + 31) / 32, 1024, 0, st>>>(pg, pb, pc, ctas, E, dgamma, dbeta, dx_colsum, accumulate);
   return acr::check_launch("layernorm_bwd_finish_kernel");
