@@ -42,6 +42,34 @@ def pseudo_label(cam_dict, num_classes, threshold):
     return np.argmax(tensor, axis=0).astype(np.uint8)
 
 
+def save_cam_dict(path, cam_dict):
+    """Pseudo-label writer, infer_cam.py:227-228: `np.save(path, {class_index: float32 [rows,cols]})` -- the pickled-dict
+    .npy that evaluation.py:28-31 (and the downstream segmentation training) reads back with allow_pickle."""
+    np.save(path, {int(k): np.ascontiguousarray(v, dtype=np.float32) for k, v in cam_dict.items()})
+
+
+def load_cam_dict(path):
+    """evaluation.py:28-29."""
+    return np.load(path, allow_pickle=True).item()
+
+
+def label_iou(pred_labels, gt_labels, num_cls=21):
+    """evaluation.py:33-67 without its 8 worker processes: per-class IoU over a list of (prediction, ground truth) uint8
+    label maps (255 = ignore) and the mean.  Returns (iou [num_cls], miou)."""
+    P = np.zeros(num_cls, np.float64)
+    T = np.zeros(num_cls, np.float64)
+    TP = np.zeros(num_cls, np.float64)
+    for predict, gt in zip(pred_labels, gt_labels):
+        cal = gt < 255
+        mask = (predict == gt) * cal
+        for i in range(num_cls):
+            P[i] += np.sum((predict == i) * cal)
+            T[i] += np.sum((gt == i) * cal)
+            TP[i] += np.sum((gt == i) * mask)
+    iou = TP / (T + P - TP + 1e-10)
+    return iou, float(np.mean(iou))
+
+
 def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, getam_func="cam_grad_s",
                     aff=True, t=1, normalize=False, truncate_backward=True, batch_classes=True, max_replicas=8):
     """One image of the infer_cam.py loop body (:145-215).

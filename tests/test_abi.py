@@ -55,3 +55,27 @@ def test_invalid_arguments_are_rejected_before_any_launch():
     assert L.acr_consistency_workspace(8, 12, 785) >= 8 * 12 * 785 * 4
     assert L.acr_bilateral_workspace(1, 21, 224, 224) > 0
     assert L.acr_pamr_workspace(1, 3, 21, 448, 448, 6) > 0
+
+
+def test_pseudo_label_writer_roundtrip(tmp_path):
+    """The .npy dict format of infer_cam.py:227-228 as evaluation.py:28-36 reads it, and the IoU bookkeeping of :33-67."""
+    import numpy as np
+    from acr_wsss_b200 import save_cam_dict, load_cam_dict, pseudo_label, label_iou
+    rng = np.random.default_rng(0)
+    cam = {3: rng.random((5, 7), dtype=np.float32), 14: rng.random((5, 7), dtype=np.float32)}
+    f = tmp_path / "img.npy"
+    save_cam_dict(str(f), cam)
+    back = np.load(str(f), allow_pickle=True).item()          # exactly evaluation.py:29
+    assert sorted(back) == [3, 14] and back[3].dtype == np.float32 and np.array_equal(back[14], cam[14])
+    assert sorted(load_cam_dict(str(f))) == [3, 14]
+    lab = pseudo_label(back, 20, 0.4)
+    tensor = np.zeros((21, 5, 7), np.float32)                # evaluation.py:30-36 restated
+    for k in back:
+        tensor[k + 1] = back[k]
+    tensor[0] = 0.4
+    assert np.array_equal(lab, np.argmax(tensor, 0).astype(np.uint8))
+    gt = lab.copy()
+    gt[0, 0] = 255
+    gt[1, 1] = (gt[1, 1] + 1) % 21
+    iou, miou = label_iou([lab], [gt])
+    assert iou.shape == (21,) and 0.0 < miou < 1.0
