@@ -7,6 +7,7 @@ Public surface (mirrors the reference's names for this path):
     save_cam_dict, pseudo_label, label_iou     (cam.py      <- infer_cam.py:227-228, evaluation.py:28-67)
     PAMR                                       (pamr.py     <- pamr.py)
     bilateralfilter_batch                      (bilateralfilter.py <- wrapper/bilateralfilter)
+    GpuAugment, Prefetcher, augment_params     (data.py     <- myTool.py:1158-1199 get_data_from_chunk_v2)
 All compute goes through libacr_b200.so (csrc/, C ABI in include/acr_b200.h); there is no CPU fallback.
 """
 from . import _lib, ops  # noqa: F401
@@ -17,5 +18,6 @@ from .pamr import PAMR  # noqa: F401
 from .train import Trainer, PolyOptimizer  # noqa: F401
 from .parallel import GradBuckets, shard_indices  # noqa: F401
 from .bilateralfilter import bilateralfilter_batch, bilateralfilter  # noqa: F401
+from .data import GpuAugment, Prefetcher, augment_params  # noqa: F401
 
 __version__ = "0.1.0"

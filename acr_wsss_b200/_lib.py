@@ -36,6 +36,7 @@ SIGNATURES = {
     "acr_colsum_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "acr_profile_enable": (None, [c_int]),
     "acr_profile_read": (c_int, [c_char_p, POINTER(ctypes.c_double), POINTER(c_longlong)]),
+    "acr_augment_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "acr_sgd_momentum_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_void_p, c_void_p]),
     "acr_gelu_fwd_bf16": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "acr_gelu_bwd_workspace": (c_size_t, [c_int]),

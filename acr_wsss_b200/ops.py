@@ -299,6 +299,16 @@ class _LinearCachedBF16(torch.autograd.Function):
         return dx, gw, gb, None, None, None
 
 
+def augment_batch(src_u8, offsets, params, B, crop_size, want_ori=True):
+    """get_data_from_chunk_v2's per-image pixel work (myTool.py:1171-1196) for B decoded images packed in `src_u8`
+    (device uint8); params int32 [B,12] from data.augment_params.  Returns (images [B,3,dim,dim] fp32, ori uint8 or None)."""
+    _need_cuda(src_u8, offsets, params)
+    out = torch.empty(B, 3, crop_size, crop_size, device=src_u8.device, dtype=torch.float32)
+    ori = torch.empty(B, 3, crop_size, crop_size, device=src_u8.device, dtype=torch.uint8) if want_ori else None
+    _call("acr_augment_batch", 1, _p(src_u8), _p(offsets), _p(params), int(B), int(crop_size), _p(out), _p(ori), _stream())
+    return out, ori
+
+
 def sgd_momentum_step(param, grad, buf, param_bf16, momentum, neg_lr):
     """buf = momentum*buf + grad ; param += neg_lr*buf ; param_bf16 = bf16(param) on flat fp32 buffers, one pass
     (neg_lr: device scalar).  tool/torchutils.py:10-31 as it really runs."""

@@ -118,6 +118,16 @@ size_t acr_colsum_workspace(int F);
 int acr_colsum_bf16(const void* x_bf16, int M, int F, float* out, int accumulate, void* workspace, size_t workspace_bytes,
                     void* stream);
 
+/* Training-batch preparation on the GPU.  Replaces the per-image body of get_data_from_chunk_v2,
+ * myTool.py:1171-1196: RandomResizeLong (cv2.resize bilinear, :995-1008) -> flip (:895-899) -> ImageNet normalisation ->
+ * RandomCrop into a zero-filled crop_size x crop_size container (:923-955).  src: the decoded uint8 RGB images, HWC, packed
+ * back to back on the DEVICE; offsets[b]: byte offset of image b; params: 12 ints per image
+ *   {h, w, resized_h, resized_w, flip, img_top, img_left, cont_top, cont_left, ch, cw, 0}
+ * (the host draws them in the reference's RNG order: acr_wsss_b200/data.py).  out [B,3,crop,crop] fp32 normalised,
+ * ori_out [B,3,crop,crop] uint8 (the de-normalised copy the reference also returns; may be NULL). */
+int acr_augment_batch(const unsigned char* src, const long long* offsets, const int* params, int B, int crop_size,
+                      float* out, unsigned char* ori_out, void* stream);
+
 /* Optimiser update of the step on flat fp32 buffers (PolyOptimizer, tool/torchutils.py:10-31, as it really runs: SGD with
  * momentum = the weight-decay value): buf = momentum*buf + grad ; param += (*neg_lr)*buf ; param_bf16 = bf16(param)
  * (param_bf16 may be NULL).  neg_lr is a DEVICE scalar (-lr_t), so the poly schedule works across CUDA-graph replays.
