@@ -158,7 +158,8 @@ pamr_iter_kernel(const float* __restrict__ wgt, const float* __restrict__ min_, 
 //
 // (Round-1 experiments with 4-pixel "quad" threads and with channel-outer / register-resident weights were 1.1-5x SLOWER
 // than the scalar tap-outer kernel above -- low occupancy and L1 thrashing across channel planes; see DESIGN.md.  The
-// iteration is bound by L1/L2 gather bandwidth (48 taps per output), not HBM; a shared-memory tiled version is the next step.)
+// iteration is bound by gather bandwidth (48 taps per output), not HBM: pamr_iter_smem_kernel below serves the taps from
+// shared memory.)
 template <int ND>
 __global__ void __launch_bounds__(128)
 pamr_affinity_reg_kernel(const float* __restrict__ x, int K, int H, int W, Dil dil, float* __restrict__ wgt) {
@@ -214,6 +215,105 @@ pamr_affinity_reg_kernel(const float* __restrict__ x, int K, int H, int W, Dil d
   for (int n = 0; n < NN; ++n) wp[(long long)n * HW] = aff[n] * invs;
 }
 
+// Shared-memory tiled iteration.  48 taps per output make the iteration a gather problem (808 MB of tap reads per
+// iteration at cfg3, against 46 MB of compulsory HBM traffic), and through L1/L2 it ran at 128 us per iteration.  Here a
+// CTA owns a 32x32 output tile: the 8*ND weights of a thread's two pixels live in registers for the whole CTA, the
+// mask tile of CG channels with a halo of R = max dilation (borders replicated while filling, so the tap loop has no
+// clamps) lives in shared memory, and every tap is one conflict-free LDS + one FMA.  Tap order = the scalar kernel's
+// (bit-identical sums).  Bound: one warp-wide LDS per clock per SM.
+constexpr int kPamrTile = 32;
+constexpr int kPamrHalo = 24;                      // compile-time halo (largest dilation served): keeps every LDS address an
+constexpr int kPamrTS = kPamrTile + 2 * kPamrHalo; // immediate offset from one per-tap register (runtime strides cost 4 integer ops per tap)
+template <int ND, int CG>
+__global__ void __launch_bounds__(512, 1)
+pamr_iter_smem_kernel(const float* __restrict__ wgt, const float* __restrict__ min_, float* __restrict__ mout,
+                      int C, int H, int W, Dil dil, int groups) {
+  extern __shared__ float tile[];                 // [CG][TS][TS]
+  constexpr int TS = kPamrTS, R = kPamrHalo;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 16 threads, two rows per thread (ty, ty + 16)
+  const int x0 = blockIdx.x * kPamrTile, y0 = blockIdx.y * kPamrTile;
+  const int b = blockIdx.z / groups, g = blockIdx.z % groups;
+  const int c0 = g * CG;
+  const long long HW = (long long)H * W;
+  // fill: replicate-padded tile of CG channels
+  {   // one (channel, row) task per warp and step, lanes along the row: coalesced, 4 independent loads in flight per lane
+    const float* mb = min_ + ((long long)b * C + c0) * HW;
+    const int gx0 = clampi(x0 - R + tx, 0, W - 1), gx1 = clampi(x0 - R + tx + 32, 0, W - 1);
+    const int gx2 = clampi(x0 - R + tx + 64, 0, W - 1), gx3 = clampi(x0 - R + tx + 96, 0, W - 1);
+#pragma unroll 5
+    for (int task = ty; task < CG * TS; task += 16) {
+      const int c = task / TS, r = task - c * TS;
+      const int gy = clampi(y0 - R + r, 0, H - 1);
+      const bool cok = c0 + c < C;
+      const float* row = mb + (long long)c * HW + (long long)gy * W;
+      const float v0 = cok ? __ldg(row + gx0) : 0.f;
+      const float v1 = (cok && tx + 32 < TS) ? __ldg(row + gx1) : 0.f;
+      const float v2 = (cok && tx + 64 < TS) ? __ldg(row + gx2) : 0.f;
+      const float v3 = (cok && tx + 96 < TS) ? __ldg(row + gx3) : 0.f;
+      float* trow = tile + task * TS;
+      trow[tx] = v0;
+      if (tx + 32 < TS) trow[tx + 32] = v1;
+      if (tx + 64 < TS) trow[tx + 64] = v2;
+      if (tx + 96 < TS) trow[tx + 96] = v3;
+      for (int col = tx + 128; col < TS; col += 32) trow[col] = cok ? __ldg(row + clampi(x0 - R + col, 0, W - 1)) : 0.f;
+    }
+  }
+  const int px = x0 + tx, py0 = y0 + ty, py1 = y0 + ty + 16;
+  const bool ok0 = px < W && py0 < H, ok1 = px < W && py1 < H;
+  float w0[8 * ND], w1[8 * ND];
+  {
+    const float* wp = wgt + (long long)b * (8 * ND) * HW + px;
+#pragma unroll
+    for (int n = 0; n < 8 * ND; ++n) {
+      w0[n] = ok0 ? __ldg(wp + (long long)n * HW + (long long)py0 * W) : 0.f;
+      w1[n] = ok1 ? __ldg(wp + (long long)n * HW + (long long)py1 * W) : 0.f;
+    }
+  }
+  __syncthreads();
+  float a0[CG], a1[CG];
+#pragma unroll
+  for (int c = 0; c < CG; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
+  const int base = (ty + R) * TS + tx + R;
+  constexpr int per = TS * TS;
+#pragma unroll
+  for (int di = 0; di < ND; ++di) {
+    const int d = dil.d[di];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (t == 4) continue;
+      const int n = di * 8 + (t < 4 ? t : t - 1);
+      const int off = base + (t / 3 - 1) * d * TS + (t % 3 - 1) * d;
+#pragma unroll
+      for (int c = 0; c < CG; ++c) {
+        a0[c] = fmaf(w0[n], tile[c * per + off], a0[c]);
+        a1[c] = fmaf(w1[n], tile[c * per + off + 16 * TS], a1[c]);
+      }
+    }
+  }
+  float* op = mout + ((long long)b * C + c0) * HW + px;
+#pragma unroll
+  for (int c = 0; c < CG; ++c) {
+    if (c0 + c < C) {
+      if (ok0) op[c * HW + (long long)py0 * W] = a0[c];
+      if (ok1) op[c * HW + (long long)py1 * W] = a1[c];
+    }
+  }
+}
+
+template <int ND, int CG>
+int launch_iter_smem(const float* wgt, const float* cur, float* dst, int B, int C, int H, int W, const Dil& dil, cudaStream_t st) {
+  const int groups = (C + CG - 1) / CG;
+  const size_t smem = (size_t)CG * kPamrTS * kPamrTS * sizeof(float);
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    ACR_CUDA(cudaFuncSetAttribute(pamr_iter_smem_kernel<ND, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = smem;
+  }
+  dim3 grid((W + kPamrTile - 1) / kPamrTile, (H + kPamrTile - 1) / kPamrTile, B * groups);
+  pamr_iter_smem_kernel<ND, CG><<<grid, 512, smem, st>>>(wgt, cur, dst, C, H, W, dil, groups);
+  return acr::check_launch("pamr_iter_smem_kernel");
+}
+
 template <int ND>
 int launch_affinity_reg(const float* x, int B, int K, int H, int W, const Dil& dil, float* wgt, cudaStream_t st) {
   dim3 grid((W + 127) / 128, H, B);
@@ -233,12 +333,29 @@ int launch_iter(const float* wgt, const float* cur, float* dst, int B, int C, in
 int pamr_iterate(const float* wgt, float* ping, float* pong, float* out, int B, int C, int H, int W, const Dil& dil, int num_iter,
                  cudaStream_t st) {
   static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("ACR_PAMR_CFG"); cfg = e ? atoi(e) : 7; }   // 7 = measured best on B200 (scripts/pamr_sweep.sh)
+  if (cfg < 0) { const char* e = getenv("ACR_PAMR_CFG"); cfg = e ? atoi(e) : 100; }   // 100 = shared-memory tiles; 7 = best scalar config
+  int R = 0;
+  for (int i = 0; i < dil.n; ++i) R = dil.d[i] > R ? dil.d[i] : R;
+  constexpr int kCG = 7;
+  const bool smem_ok = cfg == 100 && dil.n <= 6 && R <= kPamrHalo && (long long)B * ((C + kCG - 1) / kCG) <= 65535;
   const float* cur = ping;
   for (int it = 0; it < num_iter; ++it) {
     float* dst = (it == num_iter - 1) ? out : ((cur == ping) ? pong : ping);
     int e = 0;
-    switch (cfg) {
+    if (smem_ok) {
+      switch (dil.n) {
+        case 1: e = launch_iter_smem<1, kCG>(wgt, cur, dst, B, C, H, W, dil, st); break;
+        case 2: e = launch_iter_smem<2, kCG>(wgt, cur, dst, B, C, H, W, dil, st); break;
+        case 3: e = launch_iter_smem<3, kCG>(wgt, cur, dst, B, C, H, W, dil, st); break;
+        case 4: e = launch_iter_smem<4, kCG>(wgt, cur, dst, B, C, H, W, dil, st); break;
+        case 5: e = launch_iter_smem<5, kCG>(wgt, cur, dst, B, C, H, W, dil, st); break;
+        default: e = launch_iter_smem<6, kCG>(wgt, cur, dst, B, C, H, W, dil, st); break;
+      }
+      if (e) return e;
+      cur = dst;
+      continue;
+    }
+    switch (cfg == 100 ? 7 : cfg) {
       case 1: e = launch_iter<4, 256>(wgt, cur, dst, B, C, H, W, dil, st); break;
       case 2: e = launch_iter<8, 64>(wgt, cur, dst, B, C, H, W, dil, st); break;
       case 3: e = launch_iter<4, 64>(wgt, cur, dst, B, C, H, W, dil, st); break;
