@@ -99,7 +99,7 @@ def run_reference(args):
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     v, sec, cores = cpu_reference_step_time(steps, warmup)
     sample = f"{steps} timed steps (+{warmup} warm-up) of batch 1 of the same workload; fp32; torch CPU threads={cores}"
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "note": "reference algorithm on host CPU cores (oracle port of train_acr.py:127-174)"},
@@ -274,7 +274,7 @@ def run_ours(args):
             v, sec, cores = cpu_reference_step_time(2, 1)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "2 timed steps (+1 warm-up) of batch 1 of the same workload, fp32 torch CPU (oracle port)"}
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -291,6 +291,15 @@ def main():
     ap.add_argument("--no-cam", action="store_true", help="skip the secondary CAM-inference measurement")
     ap.add_argument("--profile-range", action="store_true", help="wrap one extra step in cudaProfilerStart/Stop (for ncu)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything libraries print while the bench runs (e.g. NCCL's version banner goes
+    # to stdout) is sent to stderr instead, at file-descriptor level, and the line is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    def _emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (line + "\n").encode())
     if args.impl == "reference":
         run_reference(args)
     else:
