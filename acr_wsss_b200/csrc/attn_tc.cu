@@ -230,8 +230,16 @@ __device__ __forceinline__ float gcode_weight(const GCode& gc, int q, float invH
 // byte k (0..3) of a word moved to the top byte of an fp32: 0x3F -> +0.5f, 0xBF -> -0.5f, 0x00 -> 0
 #define ACR_CODE_F(word, k) __uint_as_float(__byte_perm((word), 0u, 0x0444u | ((k) << 12)))
 
+// Softmax side: MEAN_SW warps = 4 TMEM lane quadrants x (MEAN_SW / 4) column slices of MEAN_COLS columns; each thread owns
+// one query row and MEAN_COLS key columns of the tile.  16 warps (4 per scheduler) instead of 8: the per-head chain
+// wait -> tcgen05.ld -> wait -> 32 exponentials of a warp is latency bound (clock64 timeline: 1500 cycles per head against
+// ~600 cycles of SFU work with 2 warps per scheduler), more resident warps hide it.
+constexpr int MEAN_SW = 16;
+constexpr int MEAN_COLS = BN / (MEAN_SW / 4);      // 32
+constexpr int MEAN_THREADS = 128 + MEAN_SW * 32;   // 640
+
 template <int MODE>
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(MEAN_THREADS, 1)
 attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __restrict__ lse, float* __restrict__ mean,
                  long long mean_bs, long long mean_ld, GCode gc, float* __restrict__ p_row0, int N, int H, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
@@ -242,7 +250,7 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_qkv);
     for (int i = 0; i < MEAN_STAGES; ++i) { tc::mbar_init(&s.full[i], 1); tc::mbar_init(&s.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.t_full[i], 1); tc::mbar_init(&s.t_empty[i], 256); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.t_full[i], 1); tc::mbar_init(&s.t_empty[i], MEAN_SW * 32); }
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc<256>(&s.tmem_base);
@@ -278,27 +286,29 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
       }
     }
   } else if (warp >= 4) {
-    const int we = warp - 4;                       // 0..7
-    const int row = (warp & 3) * 32 + lane;
-    const int half = we >> 2;                      // which 64-column half of the tile
+    const int we = warp - 4;                       // 0..MEAN_SW-1
+    const int row = (warp & 3) * 32 + lane;        // TMEM lane quadrant = warp % 4
+    const int slice = we >> 2;                     // which MEAN_COLS-column slice of the tile
+    const int sidx = we * 32 + lane;               // 0..MEAN_SW*32-1
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const bool row_ok = (q0 + row) < N;
-    float acc[64];
+    const int col0 = kv0 + slice * MEAN_COLS;      // first key column of this thread
+    float acc[MEAN_COLS];
     const float invH = 1.f / (float)H;
     if (MODE == 0) {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+      for (int i = 0; i < MEAN_COLS; ++i) acc[i] = 0.f;
     } else if (gc.ptr == nullptr) {
       // G tile of this thread's row, pre-scaled by 1/H; zero outside the map
-      const float* grow = mean + (size_t)b * mean_bs + (size_t)(q0 + row) * mean_ld + kv0 + half * 64;
+      const float* grow = mean + (size_t)b * mean_bs + (size_t)(q0 + row) * mean_ld + col0;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) acc[i] = (row_ok && kv0 + half * 64 + i < N) ? __ldg(grow + i) * invH : 0.f;
+      for (int i = 0; i < MEAN_COLS; ++i) acc[i] = (row_ok && col0 + i < N) ? __ldg(grow + i) * invH : 0.f;
     } else {
-      // sign codes: 64 bytes of this row (rows are padded to a multiple of 128 bytes, so the loads stay in bounds)
+      // sign codes: MEAN_COLS bytes of this row (rows are padded to a multiple of 128 bytes, so the loads stay in bounds)
       const float w2 = gcode_weight(gc, q0 + row, invH);
-      const uint4* crow = reinterpret_cast<const uint4*>(gc.ptr + (size_t)b * gc.bs + (size_t)min(q0 + row, N - 1) * gc.ld + kv0 + half * 64);
+      const uint4* crow = reinterpret_cast<const uint4*>(gc.ptr + (size_t)b * gc.bs + (size_t)min(q0 + row, N - 1) * gc.ld + col0);
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
+      for (int v = 0; v < MEAN_COLS / 16; ++v) {
         const uint4 t = __ldg(crow + v);
         const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
@@ -306,31 +316,31 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int i = v * 16 + j * 4 + k;
-            acc[i] = (row_ok && kv0 + half * 64 + i < N) ? ACR_CODE_F(w[j], k) * w2 : 0.f;
+            acc[i] = (row_ok && col0 + i < N) ? ACR_CODE_F(w[j], k) * w2 : 0.f;
           }
       }
     }
     // log2-domain LSE of this tile's rows for every head, staged once: s.lse2[h][row] (+inf for rows past N -> P = 0).
-    // Thread t owns row t & 127 for heads (t >> 7), +2, ...; the loads of a batch of 8 heads are issued before the first
-    // store so that their latencies overlap (this sits on the CTA's critical path before the first head).
+    // The loads of a batch of heads are issued before the first store (this sits on the CTA's critical path).
     {
-      const int t = we * 32 + lane, rr = t & (BM - 1);
+      constexpr int HSTEP = MEAN_SW * 32 / BM;     // heads covered per pass of all softmax threads
+      const int rr = sidx & (BM - 1);
       const bool ok = (q0 + rr) < N;
       const float* lp = lse + (size_t)b * H * N + q0 + rr;
-      for (int h0 = t >> 7; h0 < H; h0 += 16) {
-        float v[8];
+      for (int h0 = sidx / BM; h0 < H; h0 += HSTEP * 4) {
+        float v[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (ok && h0 + 2 * k < H) ? __ldg(lp + (size_t)(h0 + 2 * k) * N) : INFINITY;
+        for (int k = 0; k < 4; ++k) v[k] = (ok && h0 + HSTEP * k < H) ? __ldg(lp + (size_t)(h0 + HSTEP * k) * N) : INFINITY;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (h0 + 2 * k < H) s.lse2[h0 + 2 * k][rr] = v[k] * kLog2e;
+        for (int k = 0; k < 4; ++k)
+          if (h0 + HSTEP * k < H) s.lse2[h0 + HSTEP * k][rr] = v[k] * kLog2e;
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(MEAN_SW * 32) : "memory");
     const bool tail = (kv0 + BN > N);
     const bool row0_warp = (MODE == 0) && (p_row0 != nullptr) && (q0 == 0) && ((warp & 3) == 0);
-    // thin last tiles (N = p*p+1): warps whose 32 rows or 64 columns all lie past N only keep the barrier protocol going
-    const bool live = (q0 + (warp & 3) * 32 < N) && (kv0 + half * 64 < N);
+    // thin last tiles (N = p*p+1): warps whose 32 rows or columns all lie past N only keep the barrier protocol going
+    const bool live = (q0 + (warp & 3) * 32 < N) && (col0 < N);
     uint32_t r[32];
     for (int h = 0; h < H; ++h) {
       const int ab = h & 1;
@@ -339,10 +349,10 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
       tc::tc_fence_after();
       float part = 0.f;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int colbase = kv0 + half * 64 + c * 32;
+      for (int c = 0; c < MEAN_COLS / 32; ++c) {
+        const int colbase = col0 + c * 32;
         if (!live || (tail && colbase >= N)) break;
-        tc::tmem_ld32(tmem + ab * 128 + lane_off + half * 64 + c * 32, r);
+        tc::tmem_ld32(tmem + ab * 128 + lane_off + slice * MEAN_COLS + c * 32, r);
         tc::tmem_ld_wait();
         if (!tail) {
 #pragma unroll
@@ -376,12 +386,13 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
     // buffers are free -> stage the tile so that global stores are row-contiguous.
     float* stage = reinterpret_cast<float*>(&s.qk[0][0][0]);
 #pragma unroll
-    for (int i = 0; i < 64; ++i) stage[row * STAGE_LD + half * 64 + i] = acc[i] * invH;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    // each warp writes 16 rows, 4 at a time: 16 shared loads in flight before the 16 (row-contiguous, 128-byte) stores
+    for (int i = 0; i < MEAN_COLS; ++i) stage[row * STAGE_LD + slice * MEAN_COLS + i] = acc[i] * invH;
+    asm volatile("bar.sync 1, %0;" ::"n"(MEAN_SW * 32) : "memory");
+    // each warp writes BM / MEAN_SW rows, 4 at a time: 16 shared loads in flight before the 16 (row-contiguous, 128-byte) stores
     float* dst = mean + (size_t)b * mean_bs;
+    constexpr int RPW = BM / MEAN_SW;
 #pragma unroll 1
-    for (int r4 = we * 16; r4 < we * 16 + 16; r4 += 4) {
+    for (int r4 = we * RPW; r4 < we * RPW + RPW; r4 += 4) {
       if (q0 + r4 >= N) break;
       float v[4][4];
 #pragma unroll
@@ -478,7 +489,7 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
     }
     dim3 grid(kt, qt, B);
     acr::KernelTimer kt_("attn_mean_kernel", st);
-    attn_mean_kernel<0><<<grid, 384, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, (long long)N, GCode{}, p_row0, N, H, scale_log2);
+    attn_mean_kernel<0><<<grid, MEAN_THREADS, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, (long long)N, GCode{}, p_row0, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel")) return e;
   }
   return 0;
@@ -922,7 +933,7 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
     }
     dim3 grid(kt, qt, B);
     acr::KernelTimer kt_("attn_delta_kernel", st);
-    attn_mean_kernel<1><<<grid, 384, smem, st>>>(tmap_qkv, lse, const_cast<float*>(g_mean), g_batch_stride, g_row_stride, gc, delta, N, H, scale_log2);
+    attn_mean_kernel<1><<<grid, MEAN_THREADS, smem, st>>>(tmap_qkv, lse, const_cast<float*>(g_mean), g_batch_stride, g_row_stride, gc, delta, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel<1>")) return e;
   }
   {
