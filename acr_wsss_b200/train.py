@@ -85,7 +85,8 @@ class _FlatPolySGD:
 
 class Trainer:
     """One object = one rank.  `step(img, label)` takes HOST (pinned) or device tensors and returns the loss tensor
-    (device, detached); gradients are averaged across ranks when torch.distributed is initialised."""
+    (device, detached); gradients are averaged across ranks when torch.distributed is initialised.  `prefetch(img, label)`
+    followed by `step()` overlaps the host->device copy of the next batch with the current step."""
 
     def __init__(self, model, lr=0.01, wt_dec=5e-4, max_step=100000, alpha=100.0, bucket_bytes=64 << 20, cuda_graph=None):
         self.model = model
@@ -110,6 +111,9 @@ class Trainer:
         self._loss = None
         self._eager_steps = 0
         self._side = None
+        self._copy_stream = None
+        self._pf_img = self._pf_label = None
+        self._pf_ready = self._pf_taken = None
 
     def _stage(self, img, label):
         if self._img is None or self._img.shape != img.shape:
@@ -121,6 +125,41 @@ class Trainer:
         self._label.copy_(label, non_blocking=True)
         return self._img, self._label
 
+    def prefetch(self, img, label):
+        """Start the host->device copy of the NEXT batch (pinned host tensors) on a copy stream; it overlaps whatever the
+        compute stream is doing (normally the current step).  Consume it with step() called without arguments.  The
+        reference loads and copies synchronously inside the step loop (train_acr.py:127-133)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._pf_img = torch.empty(img.shape, device=self.dev, dtype=img.dtype)
+            self._pf_label = torch.empty(label.shape, device=self.dev, dtype=label.dtype)
+        cs = self._copy_stream
+        if self._pf_taken is not None:
+            cs.wait_event(self._pf_taken)            # the previous prefetched batch has been moved into the step's input buffers
+        with torch.cuda.stream(cs):
+            self._pf_img.copy_(img, non_blocking=True)
+            self._pf_label.copy_(label, non_blocking=True)
+            self._pf_ready = torch.cuda.Event()
+            self._pf_ready.record(cs)
+
+    def _take_prefetched(self):
+        if self._pf_ready is None:
+            raise RuntimeError("Trainer.step() without arguments needs a preceding prefetch()")
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(self._pf_ready)
+        self._pf_ready = None
+        img, label = self._stage(self._pf_img, self._pf_label)      # device-to-device into the (graph-captured) input buffers
+        self._pf_taken = torch.cuda.Event()
+        self._pf_taken.record(cur)
+        return img, label
+
+    def step_prefetched(self, next_img, next_label):
+        """One step on the batch given to the previous prefetch() / step_prefetched() call, while the copy of
+        (next_img, next_label) -- pinned host tensors -- runs underneath it."""
+        img, label = self._take_prefetched()
+        self.prefetch(next_img, next_label)
+        return self.step(img, label)
+
     def _forward_backward(self, img, label):
         img2 = img.flip(-1)                                   # transforms.RandomHorizontalFlip(p=1), train_acr.py:135
         cls_list, (attn1, attn2) = self.model.forward_mirror(img, img2)
@@ -129,7 +168,9 @@ class Trainer:
         loss.backward()
         return loss.detach()
 
-    def step(self, img, label):
+    def step(self, img=None, label=None):
+        if img is None:
+            img, label = self._take_prefetched()
         if not self.graph:
             if not img.is_cuda:
                 img, label = self._stage(img, label)
@@ -137,7 +178,8 @@ class Trainer:
             self.buckets.finish()
             self.opt.step()
             return loss
-        img, label = self._stage(img, label)
+        if img is not self._img:
+            img, label = self._stage(img, label)
         if self._g_fb is None and self._eager_steps < 2:
             # warm-up eagerly (lazy initialisation inside the kernels' host code, cuBLAS workspaces, autotuning) on the
             # SAME side stream the capture will use, so autograd's gradient-accumulation nodes are bound to it

@@ -633,3 +633,33 @@ def test_sgd_momentum_step_vs_torch(dev):
     assert torch.equal(buf, br)
     assert rel_err(t2n(p), t2n(pr)) < 1e-6
     assert torch.equal(p16, p.to(torch.bfloat16))
+
+
+def test_trainer_prefetch_pipeline_matches_plain_steps(dev):
+    """step_prefetched() (copy of batch k+1 under step k) == the same batches through plain step()."""
+    from acr_wsss_b200 import ACR, Trainer, synth
+    orc = _orc()
+    S, B, C = 64, 2, 20
+    sd = orc.synth_state_dict(orc.vit_shapes(768, 12, C), qkv_gain=2.0)
+    batches = [(synth.images(B, S, seed=k).pin_memory(), synth.labels(B, C, seed=k).pin_memory()) for k in range(4)]
+    losses = []
+    for mode in ("plain", "prefetch"):
+        m = ACR(C, "vitb", precision="bf16").to(dev)
+        m.load_state_dict(sd)
+        for n, p in m.named_parameters():
+            if n.startswith(("pretrained.model.norm.", "pretrained.model.head.", "scratch.")) or n.endswith("bkg_token"):
+                p.requires_grad_(False)
+        tr = Trainer(m, lr=0.01, max_step=50, alpha=100.0)
+        ls = []
+        if mode == "plain":
+            for img, lab in batches:
+                ls.append(float(tr.step(img, lab)))
+        else:
+            tr.prefetch(*batches[0])
+            for k in range(4):
+                nxt = batches[(k + 1) % 4]
+                ls.append(float(tr.step_prefetched(*nxt)))
+        losses.append(ls)
+    for a, b in zip(*losses):
+        assert abs(a - b) <= 2e-2 * abs(b), losses
+    assert abs(losses[0][0] - losses[1][0]) <= 1e-6 * abs(losses[0][0]), losses     # first step: identical inputs and weights
