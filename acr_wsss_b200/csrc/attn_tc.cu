@@ -30,12 +30,21 @@ struct FwdSmem {
   uint8_t q[TILE_BYTES];
   uint8_t k[2][TILE_BYTES];
   uint8_t v[2][TILE_BYTES];
-  uint64_t q_full, kv_full[2], kv_empty[2], s_full, p_full, o_full;
+  uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, o_full;
   uint32_t tmem_base;
 };
 
 // 2 CTAs per SM: 256 threads x 128 registers at launch; the control warpgroup (TMA / MMA issue / TMEM alloc) hands
 // its registers to the softmax warpgroup (setmaxnreg), so one CTA's softmax overlaps the other's MMAs.
+//
+// Per key tile the softmax warps read S out of TMEM ONCE (128 columns into registers) and hand tS back at once (s_free),
+// so the MMA warp issues S(j+1) under the exponentials of tile j.  O never leaves TMEM during the loop: the P.V MMAs
+// accumulate in place, and a row is rescaled (tcgen05.ld / multiply / tcgen05.st, warp-uniform decision) only when its
+// running maximum grew by more than 2^8 since the last rescale -- P stays <= 2^8, far inside bf16 / fp32 range, and the
+// final O / l is exact whatever stabiliser was used.  (clock64 timeline of the previous version, which re-read S for a
+// separate max pass and pulled O into registers every tile: 4100 cycles per tile, of which 700 max pass, 1000 waiting
+// for the P.V round trip, 230 O update.)
+constexpr float kRescaleThreshold = 8.f;          // log2 units
 __global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                 int N, int H, float scale_log2) {
@@ -50,6 +59,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
     tc::mbar_init(&s.q_full, 1);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.kv_full[i], 1); tc::mbar_init(&s.kv_empty[i], 1); }
     tc::mbar_init(&s.s_full, 1);
+    tc::mbar_init(&s.s_free, 128);
     tc::mbar_init(&s.p_full, 128);
     tc::mbar_init(&s.o_full, 1);
     tc::fence_barrier_init();
@@ -79,20 +89,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
     if (lane == 0) {
       tc::mbar_wait(&s.q_full, 0);
       const uint32_t q_addr = tc::smem_u32(s.q);
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j & 1;
-        tc::mbar_wait(&s.kv_full[st], (j >> 1) & 1);
-        tc::tc_fence_after();
-        const uint32_t k_addr = tc::smem_u32(s.k[st]), v_addr = tc::smem_u32(s.v[st]);
+      auto issue_s = [&](int j) {
+        const uint32_t k_addr = tc::smem_u32(s.k[j & 1]);
 #pragma unroll
         for (int ks = 0; ks < HD / 16; ++ks)
           tc::mma_ss(tS, tc::smem_desc_sw128(q_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(k_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
         tc::tc_commit(&s.s_full);
+      };
+      tc::mbar_wait(&s.kv_full[0], 0);
+      tc::tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        if (j + 1 < ntiles) {                      // S(j+1) as soon as the softmax warps hold S(j) in registers
+          tc::mbar_wait(&s.kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          tc::mbar_wait(&s.s_free, j & 1);
+          tc::tc_fence_after();
+          issue_s(j + 1);
+        }
         tc::mbar_wait(&s.p_full, j & 1);
         tc::tc_fence_after();
+        const uint32_t v_addr = tc::smem_u32(s.v[st]);
 #pragma unroll
         for (int ks = 0; ks < BN / 16; ++ks)
-          tc::mma_ts(tO, tP + ks * 8, tc::smem_desc_sw128(v_addr + ks * 2048, 1024, 1024), IDESC_PV, ks > 0);
+          tc::mma_ts(tO, tP + ks * 8, tc::smem_desc_sw128(v_addr + ks * 2048, 1024, 1024), IDESC_PV, (j > 0) || (ks > 0));
         tc::tc_commit(&s.o_full);
         tc::tc_commit(&s.kv_empty[st]);
       }
@@ -103,95 +123,109 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
     tc::reg_alloc<216>();
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    float m = -INFINITY, l = 0.f;      // m: running row max of the RAW scores (scale > 0, so max commutes with scaling)
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    uint32_t r[32];
+    float m = -INFINITY, l = 0.f;      // m: the stabiliser in use = row max of the RAW scores at the last rescale
+    uint32_t r[BN];
     // N = p*p+1 leaves a thin last tile: warps whose 32 query rows all lie past N only keep the barrier protocol going
-    // (their TMEM lanes hold garbage that is never stored), and 32-column chunks past N are skipped in the key tail tile.
+    // (their TMEM lanes hold garbage that is never stored).
     const bool rows_live = q0 + (warp & 3) * 32 < N;
     for (int j = 0; j < ntiles; ++j) {
       tc::mbar_wait(&s.s_full, j & 1);
       tc::tc_fence_after();
       if (!rows_live) {
         tc::tc_fence_before();
+        tc::mbar_arrive(&s.s_free);
         tc::mbar_arrive(&s.p_full);
-        tc::mbar_wait(&s.o_full, j & 1);
         continue;
       }
       const int col0 = j * BN;
-      const bool tail = (col0 + BN > N);
-      float mx = m;
+      const int ncols = min(BN, N - col0);           // valid key columns of this tile
+      const int nch = (ncols + 31) >> 5;             // 32-column chunks that hold any (warp-uniform)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < nch) tc::tmem_ld32(tS + lane_off + c * 32, r + c * 32);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&s.s_free);                    // tS may be overwritten by S(j+1)
+      float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        if (tail && col0 + c * 32 >= N) break;
-        tc::tmem_ld32(tS + lane_off + c * 32, r);
-        tc::tmem_ld_wait();
-        if (!tail) {
+        if (c < nch) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + c * 32 + i < N) mx = fmaxf(mx, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) {
+            if (c * 32 + i >= ncols) r[c * 32 + i] = 0xff800000u;      // -inf: keys past N
+            mx = fmaxf(mx, __uint_as_float(r[c * 32 + i]));
+          }
         }
       }
-      const float ms = mx * scale_log2;
-      const float alpha = tc::fast_exp2((m - mx) * scale_log2);
+      // the previous P.V MMA must have retired before tP is rewritten (and before O may be rescaled)
+      if (j > 0) {
+        tc::mbar_wait(&s.o_full, (j - 1) & 1);
+        tc::tc_fence_after();
+      }
+      if (j == 0) {
+        m = mx;
+      } else {
+        const bool need = (mx - m) * scale_log2 > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {         // rare after the first tiles; warp-collective TMEM access
+          const float alpha = need ? tc::fast_exp2((m - mx) * scale_log2) : 1.f;
+          if (need) { m = mx; l *= alpha; }
+          uint32_t o[32];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tc::tmem_ld32(tO + lane_off + c * 32, o);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tc::tmem_st16(tO + lane_off + c * 32, o);
+            tc::tmem_st16(tO + lane_off + c * 32 + 16, o + 16);
+          }
+        }
+      }
+      const float ms = m * scale_log2;
       float rowsum = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
-        if (tail && col0 + c * 32 >= N) {          // keys past N: P = 0 (V rows there are zero-filled, 0 * garbage must stay finite)
+        if (c < nch) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = tc::fast_exp2(fmaf(__uint_as_float(r[c * 32 + 2 * i]), scale_log2, -ms));
+            const float p1 = tc::fast_exp2(fmaf(__uint_as_float(r[c * 32 + 2 * i + 1]), scale_log2, -ms));
+            rowsum += p0 + p1;
+            pk[i] = tc::pack_bf16(p0, p1);
+          }
+        } else {                                     // keys past N: P = 0 (V rows there are zero-filled, 0 * garbage must stay finite)
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = 0u;
-          tc::tmem_st16(tP + lane_off + c * 16, pk);
-          continue;
-        }
-        tc::tmem_ld32(tS + lane_off + c * 32, r);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = tc::fast_exp2(fmaf(__uint_as_float(r[2 * i]), scale_log2, -ms));
-          float p1 = tc::fast_exp2(fmaf(__uint_as_float(r[2 * i + 1]), scale_log2, -ms));
-          if (tail) {
-            if (col0 + c * 32 + 2 * i >= N) p0 = 0.f;
-            if (col0 + c * 32 + 2 * i + 1 >= N) p1 = 0.f;
-          }
-          rowsum += p0 + p1;
-          pk[i] = tc::pack_bf16(p0, p1);
         }
         tc::tmem_st16(tP + lane_off + c * 16, pk);
       }
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(&s.p_full);
-      l = l * alpha + rowsum;
-      m = mx;
-      tc::mbar_wait(&s.o_full, j & 1);
-      tc::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tc::tmem_ld32(tO + lane_off + c * 32, r);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
-      }
+      l += rowsum;
     }
-    if (q0 + row < N) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * ((size_t)H * HD) + (size_t)h * HD;
+    if (rows_live) {
+      tc::mbar_wait(&s.o_full, (ntiles - 1) & 1);
+      tc::tc_fence_after();
+      uint32_t o[HD];
+      tc::tmem_ld32(tO + lane_off, o);
+      tc::tmem_ld32(tO + lane_off + 32, o + 32);
+      tc::tmem_ld_wait();
+      if (q0 + row < N) {
+        const float inv = 1.f / l;
+        __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * ((size_t)H * HD) + (size_t)h * HD;
 #pragma unroll
-      for (int c = 0; c < HD / 8; ++c) {
-        uint4 v;
-        v.x = tc::pack_bf16(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
-        v.y = tc::pack_bf16(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
-        v.z = tc::pack_bf16(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
-        v.w = tc::pack_bf16(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
-        reinterpret_cast<uint4*>(dst)[c] = v;
+        for (int c = 0; c < HD / 8; ++c) {
+          uint4 v;
+          v.x = tc::pack_bf16(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
+          v.y = tc::pack_bf16(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
+          v.z = tc::pack_bf16(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
+          v.w = tc::pack_bf16(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
+          reinterpret_cast<uint4*>(dst)[c] = v;
+        }
+        lse[((size_t)b * H + h) * N + q0 + row] = (m * scale_log2 + log2f(l)) * kLn2;
       }
-      lse[((size_t)b * H + h) * N + q0 + row] = (m * scale_log2 + log2f(l)) * kLn2;
     }
   }
   tc::tc_fence_before();
