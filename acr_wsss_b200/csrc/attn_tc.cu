@@ -135,6 +135,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
         tc::tc_fence_before();
         tc::mbar_arrive(&s.s_free);
         tc::mbar_arrive(&s.p_full);
+        // S(j+1) can complete while the live warps are still on tile j: without this wait the next arrival of this
+        // warp would be counted in phase j of p_full and release the P.V MMA before P(j) is complete
+        tc::mbar_wait(&s.p_full, j & 1);
         continue;
       }
       const int col0 = j * BN;
