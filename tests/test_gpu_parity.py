@@ -514,11 +514,14 @@ def test_layernorm_kernel_vs_torch_reference(dev, M, E, bf16):
         assert rel_err(t2n(a), t2n(r)) < tol
 
 
-def test_trainer_cuda_graph_matches_eager(dev):
-    """Trainer's CUDA-graph step (flat SGD, device-side lr) == the eager step with the PolyOptimizer mirror."""
+@pytest.mark.parametrize("S,B", [(64, 2), (448, 1)])
+def test_trainer_cuda_graph_matches_eager(dev, S, B):
+    """Trainer's CUDA-graph step (flat SGD, device-side lr, cached bf16 weights, fused glue kernels, sign-code gradients)
+    == the eager step with the PolyOptimizer mirror (autocast Linear layers, autograd accumulation).  S = 448 puts the
+    thin last tile of N = 785 through every fused kernel."""
     from acr_wsss_b200 import ACR, Trainer, synth
     orc = _orc()
-    S, B, C = 64, 2, 20
+    C = 20
     sd = orc.synth_state_dict(orc.vit_shapes(768, 12, C), qkv_gain=2.0)
     img, label = synth.images(B, S), synth.labels(B, C)
     losses, finals = [], []
