@@ -122,19 +122,26 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 
 __global__ void __launch_bounds__(256)
 gelu_colsum_finish_kernel(const float* __restrict__ partial, int nparts, int F, float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= F) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int p = 0;
-  for (; p + 3 < nparts; p += 4) {
-    s0 += __ldg(partial + (size_t)p * F + c);
-    s1 += __ldg(partial + (size_t)(p + 1) * F + c);
-    s2 += __ldg(partial + (size_t)(p + 2) * F + c);
-    s3 += __ldg(partial + (size_t)(p + 3) * F + c);
+  // 64 columns x 4 part groups per CTA: four times shorter load chains than one thread per column (the kernel is pure
+  // latency: 64 partial rows of F floats), folded in a fixed order -> deterministic
+  __shared__ float red[4][64];
+  const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < F) {
+    int p = grp;
+    for (; p + 4 < nparts; p += 8) {
+      s0 += __ldg(partial + (size_t)p * F + c);
+      s1 += __ldg(partial + (size_t)(p + 4) * F + c);
+    }
+    for (; p < nparts; p += 4) s0 += __ldg(partial + (size_t)p * F + c);
   }
-  for (; p < nparts; ++p) s0 += __ldg(partial + (size_t)p * F + c);
-  const float s = (s0 + s1) + (s2 + s3);
-  out[c] = accumulate ? out[c] + s : s;
+  red[grp][cl] = s0 + s1;
+  __syncthreads();
+  if (grp == 0 && c < F) {
+    const float s = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
+    out[c] = accumulate ? out[c] + s : s;
+  }
 }
 
 }  // namespace
@@ -166,7 +173,7 @@ extern "C" int acr_gelu_bwd_bf16(const void* x, const void* dy, void* dx, int M,
                                         colsum ? (float*)workspace : nullptr);
   if (int e = acr::check_launch("gelu_bwd_kernel")) return e;
   if (colsum) {
-    gelu_colsum_finish_kernel<<<(F + 255) / 256, 256, 0, st>>>((const float*)workspace, chunks, F, colsum, accumulate);
+    gelu_colsum_finish_kernel<<<(F + 63) / 64, 256, 0, st>>>((const float*)workspace, chunks, F, colsum, accumulate);
     return acr::check_launch("gelu_colsum_finish_kernel");
   }
   return 0;

@@ -234,11 +234,26 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, int M, int F, int rows_p
 
 __global__ void __launch_bounds__(256)
 colsum_finish_kernel(const float* __restrict__ partial, int nparts, int F, float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= F) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partial[(size_t)p * F + c];
-  out[c] = accumulate ? out[c] + s : s;
+  // 64 columns x 4 part groups per CTA: four times shorter load chains than one thread per column (the kernel is pure
+  // latency: 64 partial rows of F floats), folded in a fixed order -> deterministic
+  __shared__ float red[4][64];
+  const int cl = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < F) {
+    int p = grp;
+    for (; p + 4 < nparts; p += 8) {
+      s0 += __ldg(partial + (size_t)p * F + c);
+      s1 += __ldg(partial + (size_t)(p + 4) * F + c);
+    }
+    for (; p < nparts; p += 4) s0 += __ldg(partial + (size_t)p * F + c);
+  }
+  red[grp][cl] = s0 + s1;
+  __syncthreads();
+  if (grp == 0 && c < F) {
+    const float s = (red[0][cl] + red[1][cl]) + (red[2][cl] + red[3][cl]);
+    out[c] = accumulate ? out[c] + s : s;
+  }
 }
 
 constexpr int kBwdCtas = 296;     // 2 per SM (register limit: ~105 per thread at E = 768)
@@ -358,6 +373,6 @@ extern "C" int acr_colsum_bf16(const void* x, int M, int F, float* out, int accu
   dim3 grid((F + 63) / 64, chunks);
   colsum_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, M, F, rows_per_chunk, (float*)workspace);
   if (int e = acr::check_launch("colsum_bf16_kernel")) return e;
-  colsum_finish_kernel<<<(F + 255) / 256, 256, 0, st>>>((const float*)workspace, chunks, F, out, accumulate);
+  colsum_finish_kernel<<<(F + 63) / 64, 256, 0, st>>>((const float*)workspace, chunks, F, out, accumulate);
   return acr::check_launch("colsum_finish_kernel");
 }
