@@ -55,6 +55,27 @@ def test_invalid_arguments_are_rejected_before_any_launch():
     assert L.acr_consistency_workspace(8, 12, 785) >= 8 * 12 * 785 * 4
     assert L.acr_bilateral_workspace(1, 21, 224, 224) > 0
     assert L.acr_pamr_workspace(1, 3, 21, 448, 448, 6) > 0
+    # the trunk-glue / optimiser / data-path entry points validate before touching the device too
+    import ctypes
+    buf = ctypes.create_string_buffer(4096)
+    al = ctypes.c_void_p((ctypes.addressof(buf) + 255) & ~255)          # a 256-byte aligned host address: never dereferenced
+    mis = ctypes.c_void_p(al.value + 2)
+    assert L.acr_gelu_fwd_bf16(None, None, 8, None) == -1
+    assert L.acr_gelu_fwd_bf16(mis, al, 8, None) == -2
+    assert L.acr_gelu_bwd_bf16(al, al, al, 4, 12, None, 0, None, 0, None) == -1            # F not a multiple of 8
+    assert L.acr_gelu_bwd_bf16(al, al, al, 4, 16, al, 1, al, 8, None) == -4                # workspace too small
+    assert L.acr_gelu_bwd_workspace(3072) == 64 * 3072 * 4
+    assert L.acr_layernorm_fwd(al, 1, al, None, al, al, 4, 768, 1e-6, al, 1, al, al, None) == -1   # residual without sum_out
+    assert L.acr_layernorm_fwd(al, 1, None, None, al, al, 4, 100, 1e-6, al, 1, al, al, None) == -1  # E not a multiple of 128
+    assert L.acr_layernorm_bwd(al, 1, None, al, 1, al, al, al, 4, 768, al, al, al, None, 0, al, 16, None) == -4
+    assert L.acr_layernorm_bwd_workspace(768) == 3 * 296 * 768 * 4
+    assert L.acr_sgd_momentum_step(al, al, al, None, 6, 0.5, al, None) == -1               # n not a multiple of 4
+    assert L.acr_sgd_momentum_step(mis, al, al, None, 8, 0.5, al, None) == -2
+    assert L.acr_augment_batch(None, None, None, 1, 64, None, None, None) == -1
+    assert L.acr_augment_batch(al, al, al, 0, 64, al, None, None) == -1
+    assert L.acr_colsum_bf16(al, 4, 7, al, 0, al, 1 << 20, None) == -1                    # F odd
+    tot, cnt = ctypes.c_double(), ctypes.c_longlong()
+    assert L.acr_profile_read(None, ctypes.byref(tot), ctypes.byref(cnt)) == -1
 
 
 def test_pseudo_label_writer_roundtrip(tmp_path):
