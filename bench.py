@@ -92,6 +92,23 @@ def cpu_reference_step_time(steps, warmup, batch=1):
     return batch / sec, sec, cores
 
 
+def cpu_reference_cam_time():
+    """The reference's CAM-inference loop body (infer_cam.py:145-215: 2 flips, one full backward per present class, GETAM +
+    affinity refinement) on host cores through the oracle port: ONE image of the same cfg1 workload (bounded sample)."""
+    import torch
+    from oracle import acr_oracle as orc
+    from acr_wsss_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = orc.synth_state_dict(orc.vit_shapes(768, LAYERS, C))
+    img = synth.images(1, S, seed=100)
+    lab = synth.labels(1, C, present=(3, 7, 14))
+    t0 = time.perf_counter()
+    orc.infer_cam_image(sd, img, lab, (S, S), scales=(1,), start_layer=10, getam_func="grad")
+    sec = time.perf_counter() - t0
+    return 1.0 / sec, sec, cores
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -278,6 +295,10 @@ def run_ours(args):
             v, sec, cores = cpu_reference_step_time(2, 1)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "2 timed steps (+1 warm-up) of batch 1 of the same workload, fp32 torch CPU (oracle port)"}
+            if cam is not None:
+                v, sec, cores = cpu_reference_cam_time()
+                cam["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": cores, "kind": "port",
+                                       "sample": "1 image of the same cfg1 workload (2 flips, 3 classes, full backward per class), fp32 torch CPU (oracle port)"}
         _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
