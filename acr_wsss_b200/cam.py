@@ -86,7 +86,8 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
     C = label.shape[1]
     b, c, h, w = img.shape
     rows, cols = out_size
-    present = [ci for ci in range(C) if float(label[0, ci]) > 1e-5]
+    lab_host = label[0].tolist()                       # one device->host read (the reference tests the labels one by one)
+    present = [ci for ci in range(C) if lab_host[ci] > 1e-5]
     cam_list, patch_cam_list = [], []
     nblocks = len(model.pretrained.model.blocks)
     batched = truncate_backward and batch_classes and len(present) > 0 and 0 < start_layer < nblocks
