@@ -70,8 +70,63 @@ def label_iou(pred_labels, gt_labels, num_cls=21):
     return iou, float(np.mean(iou))
 
 
+def _lowres_pass(model, both, present_idx, n_present, start_layer, getam_func, aff, t, normalize, max_replicas):
+    """Device-only part of one scale of the batched path: trunk forward on both flips, blocks >= start_layer on one copy
+    per present class, ONE backward, GETAM rows, affinity refinement.  Everything that depends on WHICH classes are present
+    goes through the device tensor `present_idx`, so the pass is CUDA-graph capturable per (shape, n_present).
+    Returns (patch_cam [2,Np,C], cams [2,Np,n_present])."""
+    rows_v = [[], []]
+    attn = patch_cam = None
+    for c0 in range(0, n_present, max_replicas):
+        n = min(max_replicas, n_present - c0)
+        cls_rep, _, attn, patch_cam = model.forward_cam_batched(both, n, start_layer)
+        model.backward_for_getam_batched(cls_rep, present_idx[c0:c0 + n].repeat(2))
+        for v in range(2):
+            for k in range(n):
+                cam, _, _ = model.getam(v * n + k, start_layer=start_layer, func=getam_func)
+                rows_v[v].append(cam[0])
+    cams = torch.stack([torch.stack(rows_v[v], dim=1) for v in range(2)])            # [2,Np,C']
+    if aff:
+        cams = torch.cat([affinity_refine(attn[v:v + 1].detach(), cams[v:v + 1], t=t, normalize=normalize) for v in range(2)])
+    return patch_cam.detach(), cams
+
+
+class _LowresGraph:
+    """CUDA graph of _lowres_pass for one (model, input shape, number of present classes, options) key: the pass is ~270
+    launches of small kernels at batch 2 and is CPU-launch bound when run eagerly (8.4 ms per image, 2.8 ms of GPU time)."""
+
+    def __init__(self, model, shape, n_present, args):
+        dev = next(model.parameters()).device
+        self.both = torch.empty(shape, device=dev)
+        self.idx = torch.zeros(n_present, device=dev, dtype=torch.long)
+        self.model, self.n, self.args = model, n_present, args
+        self.graph = None
+        self.calls = 0
+        self.stream = torch.cuda.Stream(device=dev)
+
+    def run(self, both, present_idx):
+        self.both.copy_(both)
+        self.idx.copy_(present_idx)
+        self.calls += 1
+        cur = torch.cuda.current_stream()
+        if self.graph is None and self.calls <= 2:          # warm up eagerly on the capture stream (lazy inits, cuBLAS workspaces)
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                out = _lowres_pass(self.model, self.both, self.idx, self.n, *self.args)
+            cur.wait_stream(self.stream)
+            return out
+        if self.graph is None:
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self.out = _lowres_pass(self.model, self.both, self.idx, self.n, *self.args)
+        self.graph.replay()
+        return self.out
+
+
 def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, getam_func="cam_grad_s",
-                    aff=True, t=1, normalize=False, truncate_backward=True, batch_classes=True, max_replicas=8):
+                    aff=True, t=1, normalize=False, truncate_backward=True, batch_classes=True, max_replicas=8,
+                    cuda_graph=False):
     """One image of the infer_cam.py loop body (:145-215).
 
     img [1,3,h,w] (normalised), label [1,C] multi-hot, out_size = (rows, cols) of the original image (the
@@ -81,6 +136,8 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
     batch_classes (needs truncate_backward): both flips go through the trunk as one batch of 2, the blocks >= start_layer
     run on one copy of the token stream per present class (at most max_replicas per pass) and ONE backward delivers every
     class's attention gradients for both flips.
+    cuda_graph (batched path on a GPU): replay the device-only part as a CUDA graph, cached on the model per (input shape,
+    number of present classes, options); the first two calls of a key run eagerly.  Do not change the weights in between.
     """
     assert img.shape[0] == 1, "the reference infers one image at a time (infer_cam.py:122)"
     C = label.shape[1]
@@ -91,9 +148,11 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
     cam_list, patch_cam_list = [], []
     nblocks = len(model.pretrained.model.blocks)
     batched = truncate_backward and batch_classes and len(present) > 0 and 0 < start_layer < nblocks
+    present_idx = torch.tensor(present, device=img.device, dtype=torch.long) if present else None
 
-    def finish_view(attn, patch_cam, rows0, flipped, ph, pw):
-        """infer_cam.py:153-199 for one flip: patch CAM and (affinity-refined) GETAM maps at the original image size."""
+    def finish_view(attn, patch_cam, cams, flipped, ph, pw):
+        """infer_cam.py:153-199 for one flip: patch CAM and (affinity-refined) GETAM maps at the original image size.
+        cams [1,Np,C'] (already refined when attn is None)."""
         patch_cam = patch_cam.permute(0, 2, 1).reshape(1, C, ph, pw)
         patch_cam = F.interpolate(patch_cam, [rows, cols], mode="bilinear", align_corners=False)[0]
         patch_cam = patch_cam.detach() * label[0, :].view(C, 1, 1)
@@ -102,12 +161,11 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
         patch_cam_list.append(patch_cam)
         cam_matrix = torch.zeros(C, rows, cols, device=img.device)
         if present:
-            cams = torch.stack(rows0, dim=1).unsqueeze(0)        # [1,Np,C']
-            if aff:
+            if aff and attn is not None:
                 cams = affinity_refine(attn.detach(), cams, t=t, normalize=normalize)
             cams = cams[0].t().reshape(len(present), 1, ph, pw)
             cams = F.interpolate(cams, (rows, cols), mode="bilinear", align_corners=True)[:, 0]
-            cam_matrix[present] = cams
+            cam_matrix.index_copy_(0, present_idx, cams)
         if flipped:
             cam_matrix = cam_matrix.flip(-1)
         cam_list.append(cam_matrix)
@@ -120,17 +178,19 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
             # both flips as one batch of 2, every present class as a copy of the token stream from block start_layer on:
             # one forward and ONE backward per scale (the reference: 2 forwards and 2*C' full backwards)
             both = torch.cat([inp.flip(-1), inp], dim=0)          # hflip = 1 (flipped) first, then 2, as infer_cam.py:148-151
-            rows_v = [[], []]
-            for c0 in range(0, len(present), max_replicas):
-                chunk = present[c0:c0 + max_replicas]
-                cls_rep, _, attn, patch_cam = model.forward_cam_batched(both, len(chunk), start_layer)
-                model.backward_for_getam_batched(cls_rep, chunk * 2)
-                for v in range(2):
-                    for k in range(len(chunk)):
-                        cam, _, _ = model.getam(v * len(chunk) + k, start_layer=start_layer, func=getam_func)
-                        rows_v[v].append(cam[0])
+            args = (start_layer, getam_func, aff, t, normalize, max_replicas)
+            if cuda_graph and img.is_cuda:
+                cache = model.__dict__.setdefault("_cam_graphs", {})
+                key = (tuple(both.shape), len(present)) + args
+                if key not in cache:
+                    if len(cache) >= 8:
+                        cache.clear()
+                    cache[key] = _LowresGraph(model, tuple(both.shape), len(present), args)
+                patch_cam, cams = cache[key].run(both, present_idx)
+            else:
+                patch_cam, cams = _lowres_pass(model, both, present_idx, len(present), *args)
             for v in range(2):
-                finish_view(attn[v:v + 1], patch_cam[v:v + 1], rows_v[v], v == 0, ph, pw)
+                finish_view(None, patch_cam[v:v + 1], cams[v:v + 1], v == 0, ph, pw)
             continue
         for hflip in (1, 2):
             model.zero_grad()
@@ -146,14 +206,15 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
                     output[ci].backward(retain_graph=True)      # one_hot * output, infer_cam.py:173-179
                 cam, _, _ = model.getam(0, start_layer=start_layer, func=getam_func)
                 rows0.append(cam[0])
-            finish_view(attn, patch_cam, rows0, hflip % 2 == 1, ph, pw)
+            cams = torch.stack(rows0, dim=1).unsqueeze(0) if present else None        # [1,Np,C']
+            finish_view(attn, patch_cam, cams, hflip % 2 == 1, ph, pw)
     patch_sum = torch.stack(patch_cam_list).sum(0)
     patch_norm = normalize_cam(patch_sum, 1e-5)
     sum_cam = torch.stack(cam_list).sum(0)
     norm_cam = normalize_cam(sum_cam, 1e-6)
     # only the present classes go to the host (what the reference keeps, infer_cam.py:217-228), through one pinned buffer
     if present:
-        both = torch.stack([norm_cam[present], patch_norm[present]])           # [2,C',rows,cols]
+        both = torch.stack([norm_cam.index_select(0, present_idx), patch_norm.index_select(0, present_idx)])     # [2,C',rows,cols]
         host = _pinned(both.shape) if both.is_cuda else torch.empty(both.shape)
         host.copy_(both, non_blocking=True)
         if both.is_cuda:

@@ -410,8 +410,8 @@ class ACR(nn.Module):
     def backward_for_getam_batched(self, x_cls, classes):
         """One backward for all copies: batch index i receives the one-hot cotangent of classes[i] (infer_cam.py:173-179
         runs one full backward per class).  Afterwards getam(i, start_layer, ...) is the GETAM of classes[i] for that copy."""
-        idx = torch.as_tensor(list(classes), device=x_cls.device)
-        sel = x_cls[torch.arange(len(classes), device=x_cls.device), idx].sum()
+        idx = classes if torch.is_tensor(classes) else torch.as_tensor(list(classes), device=x_cls.device)
+        sel = x_cls.gather(1, idx.view(-1, 1)).sum()
         torch.autograd.grad(sel, self.pretrained.model._rep_in)
 
     def forward_mirror(self, x1, x2):

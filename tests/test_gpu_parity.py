@@ -304,6 +304,24 @@ def test_infer_cam_bf16_448(dev):
 
 
 # ------------------------------------------------------------------ (a10) PAMR
+def test_infer_cam_cuda_graph_matches_eager(dev):
+    """cuda_graph=True: two eager warm-ups, capture, replays -- same CAMs as the eager path, also for a different image and
+    a different set of present classes of the same size (the class indices are graph INPUTS)."""
+    from acr_wsss_b200 import infer_cam_image, synth
+    m, _ = _build(dev, 20, "vitb", "bf16", 2.0)
+    m.eval()
+    cases = [(3, (3, 7, 14)), (3, (3, 7, 14)), (4, (1, 7, 19)), (5, (0, 2, 5)), (6, (3, 7, 14))]
+    for seed, present in cases:
+        img = synth.images(1, 128, seed=seed).to(dev)
+        label = synth.labels(1, 20, present=present).to(dev)
+        a, pa, _ = infer_cam_image(m, img, label, (60, 80), start_layer=10, getam_func="grad", cuda_graph=True)
+        b, pb, _ = infer_cam_image(m, img, label, (60, 80), start_layer=10, getam_func="grad", cuda_graph=False)
+        assert sorted(a) == sorted(present)
+        for c in present:
+            assert rel_err(a[c], b[c]) < 1e-5 and rel_err(pa[c], pb[c]) < 1e-5, (seed, c)
+    assert len(m._cam_graphs) == 1 and next(iter(m._cam_graphs.values())).graph is not None
+
+
 def test_pamr_matches_reference(dev):
     from acr_wsss_b200 import PAMR, synth
     g = load_golden("pamr.npz")
