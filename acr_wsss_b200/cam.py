@@ -137,7 +137,9 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
     run on one copy of the token stream per present class (at most max_replicas per pass) and ONE backward delivers every
     class's attention gradients for both flips.
     cuda_graph (batched path on a GPU): replay the device-only part as a CUDA graph, cached on the model per (input shape,
-    number of present classes, options); the first two calls of a key run eagerly.  Do not change the weights in between.
+    number of present classes, options); the first two calls of a key run eagerly.  In-place weight updates are picked
+    up by the replays (the graph reads the parameter storage); re-allocating parameters (e.g. model.to(...)) needs
+    `model._cam_graphs.clear()`.
     """
     assert img.shape[0] == 1, "the reference infers one image at a time (infer_cam.py:122)"
     C = label.shape[1]
