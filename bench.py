@@ -302,7 +302,9 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "tokens": N_TOK, "parallelism": f"dp{world}",
                        "precision": precision, "cuda_graph": bool(trainer.graph), "l2": "inputs larger than L2: each step streams 2 x 237 MB attention stacks + gradients"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(img_h.numel() * 4 + lab_h.numel() * 4) * world,
-                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps,
+                    "api": "Trainer.step_prefetched(next_img, next_label): every timed step copies one pinned-host batch to the device "
+                           "(the one the next step consumes, on a copy stream under this step's kernels) and reads float(loss) back"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cam_infer": cam,
         }
         if world == 1 and not args.no_cpu_baseline:
