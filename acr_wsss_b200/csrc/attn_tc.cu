@@ -394,9 +394,7 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
         if (!tail) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            // every 4th exponential on the FMA pipe instead of the SFU (see tc::exp2_fma)
-            const float x = fmaf(__uint_as_float(r[i]), scale_log2, -lse2);
-            const float p = ((i & 3) == 3) ? tc::exp2_fma(x) : tc::fast_exp2(x);
+            const float p = tc::fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -lse2));
             if (MODE == 0) { acc[c * 32 + i] += p; r[i] = __float_as_uint(p); } else part = fmaf(p, acc[c * 32 + i], part);
           }
         } else {

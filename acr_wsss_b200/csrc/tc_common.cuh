@@ -150,24 +150,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// 2^x for x <= 0 WITHOUT the SFU (FMA / integer pipes only): round-to-nearest split x = n + f via the 1.5*2^23 trick,
-// 2^f on [-0.5, 0.5] by a degree-5 polynomial (relative error 2.4e-6), exponent added as an integer.  The softmax kernels
-// are bound by the 16 ex2/clk/SM of the SFU while their FMA pipe idles; sending a quarter of the elements through this
-// path balances the two.  x is clamped at -126 (result ~1e-38 instead of 0: below every tolerance here; -inf is safe).
-__device__ __forceinline__ float exp2_fma(float x) {
-  x = fmaxf(x, -126.f);
-  const float magic = 12582912.f;
-  const float xr = x + magic;                 // n in the low mantissa bits
-  const float f = x - (xr - magic);
-  float p = 1.3333558e-3f;
-  p = fmaf(p, f, 9.6181291e-3f);
-  p = fmaf(p, f, 5.5504109e-2f);
-  p = fmaf(p, f, 2.4022651e-1f);
-  p = fmaf(p, f, 6.9314718e-1f);
-  p = fmaf(p, f, 1.f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
-}
-
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
