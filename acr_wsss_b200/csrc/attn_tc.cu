@@ -10,20 +10,12 @@
 //                    fp32 tile of A-bar straight into slot l of the [B,L,N,N] stack (coalesced, via smem staging).
 //                    Also emits the cls-token row of every head's P (GETAM input).
 // N = p*p+1 is never a multiple of 128: TMA zero-fills out-of-range rows, key columns >= N are masked to -inf / 0.
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "attn_tc.cuh"
+#include <cstdlib>
+
+using namespace acr_attn;
 
 namespace {
-
-constexpr int BM = 128;               // query rows per CTA
-constexpr int BN = 128;               // key rows per tile
-constexpr int HD = 64;                // head dim (128-byte bf16 rows = one SWIZZLE_128B atom row)
-constexpr uint32_t TILE_BYTES = BM * HD * 2;
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-
-constexpr uint32_t IDESC_S = tc::idesc_bf16_f32(128, 128, 0, 0);   // S = Q K^T : A, B K-major
-constexpr uint32_t IDESC_PV = tc::idesc_bf16_f32(128, 64, 0, 1);   // O = P V   : A (TMEM) K-major, B = V MN-major
 
 // ---------------------------------------------------------------------------------------------
 struct FwdSmem {
@@ -73,49 +65,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
 
   if (warp == 0) {
     tc::reg_dealloc<40>();
-    if (lane == 0) {
+    // all lanes wait, one elected lane issues (tc::elect_one: no ELECT/branch loop around every TMA / MMA instruction)
+    if (tc::elect_one()) {
       tc::mbar_arrive_expect_tx(&s.q_full, TILE_BYTES);
       tc::tma_load_4d(s.q, &tmap_qkv, &s.q_full, 0, h, q0, b);
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j & 1;
-        tc::mbar_wait(&s.kv_empty[st], ((j >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j & 1;
+      tc::mbar_wait(&s.kv_empty[st], ((j >> 1) & 1) ^ 1);
+      if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(&s.kv_full[st], 2 * TILE_BYTES);
         tc::tma_load_4d(s.k[st], &tmap_qkv, &s.kv_full[st], 0, H + h, j * BN, b);
         tc::tma_load_4d(s.v[st], &tmap_qkv, &s.kv_full[st], 0, 2 * H + h, j * BN, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     tc::reg_dealloc<40>();
-    if (lane == 0) {
-      tc::mbar_wait(&s.q_full, 0);
-      const uint32_t q_addr = tc::smem_u32(s.q);
-      auto issue_s = [&](int j) {
-        const uint32_t k_addr = tc::smem_u32(s.k[j & 1]);
+    tc::mbar_wait(&s.q_full, 0);
+    const uint64_t qd = tc::smem_desc_sw128(tc::smem_u32(s.q), 16, 1024);
+    auto issue_s = [&](int j) {
+      const uint64_t kd = tc::smem_desc_sw128(tc::smem_u32(s.k[j & 1]), 16, 1024);
+      if (tc::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-          tc::mma_ss(tS, tc::smem_desc_sw128(q_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(k_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
+        for (int ks = 0; ks < HD / 16; ++ks) tc::mma_ss_off(tS, qd, ks * 2, kd, ks * 2, IDESC_S, ks > 0);
         tc::tc_commit(&s.s_full);
-      };
-      tc::mbar_wait(&s.kv_full[0], 0);
-      tc::tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j & 1;
-        if (j + 1 < ntiles) {                      // S(j+1) as soon as the softmax warps hold S(j) in registers
-          tc::mbar_wait(&s.kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-          tc::mbar_wait(&s.s_free, j & 1);
-          tc::tc_fence_after();
-          issue_s(j + 1);
-        }
-        tc::mbar_wait(&s.p_full, j & 1);
+      }
+      __syncwarp();
+    };
+    tc::mbar_wait(&s.kv_full[0], 0);
+    tc::tc_fence_after();
+    issue_s(0);
+    for (int j = 0; j < ntiles; ++j) {
+      const int st = j & 1;
+      if (j + 1 < ntiles) {                      // S(j+1) as soon as the softmax warps hold S(j) in registers
+        tc::mbar_wait(&s.kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        tc::mbar_wait(&s.s_free, j & 1);
         tc::tc_fence_after();
-        const uint32_t v_addr = tc::smem_u32(s.v[st]);
+        issue_s(j + 1);
+      }
+      tc::mbar_wait(&s.p_full, j & 1);
+      tc::tc_fence_after();
+      const uint64_t vd = tc::smem_desc_sw128(tc::smem_u32(s.v[st]), 1024, 1024);
+      if (tc::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks)
-          tc::mma_ts(tO, tP + ks * 8, tc::smem_desc_sw128(v_addr + ks * 2048, 1024, 1024), IDESC_PV, (j > 0) || (ks > 0));
+        for (int ks = 0; ks < BN / 16; ++ks) tc::mma_ts_off(tO, tP + ks * 8, vd, ks * 128, IDESC_PV, (j > 0) || (ks > 0));
         tc::tc_commit(&s.o_full);
         tc::tc_commit(&s.kv_empty[st]);
       }
+      __syncwarp();
     }
   } else if (warp < 4) {
     tc::reg_dealloc<40>();
@@ -241,7 +240,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
 
 // ---------------------------------------------------------------------------------------------
 constexpr int MEAN_STAGES = 3;
-constexpr int MEAN_MAX_H = 32;
 struct MeanSmem {
   uint8_t qk[MEAN_STAGES][2][TILE_BYTES];      // [stage][0=Q,1=K]; reused as the fp32 staging tile at the end
   float lse2[MEAN_MAX_H][BM];
@@ -253,20 +251,6 @@ static_assert(sizeof(float) * BM * STAGE_LD <= sizeof(uint8_t) * MEAN_STAGES * 2
 
 // MODE 0: mean[b,q,kv] = (1/H) sum_h P_h ; MODE 1 (backward pre-pass): delta[b,h,q] += (1/H) sum_kv P_h[q,kv] * G[b,q,kv]
 // (`mean` is then the read-only G, `p_row0` the delta accumulator).
-// Sign-code form of G (acr_consistency_fwd_bwd): one byte per element = top byte of +-0.5f; strides in bytes.
-struct GCode {
-  const unsigned char* ptr;
-  long long bs, ld;
-  float w_cls, w_aff;
-  const float* scale;     // optional device scalar
-};
-__device__ __forceinline__ float gcode_weight(const GCode& gc, int q, float invH) {   // 2*w*scale/H of query row q
-  const float sc = gc.scale ? __ldg(gc.scale) : 1.f;
-  return 2.f * invH * sc * (q == 0 ? gc.w_cls : gc.w_aff);
-}
-// byte k (0..3) of a word moved to the top byte of an fp32: 0x3F -> +0.5f, 0xBF -> -0.5f, 0x00 -> 0
-#define ACR_CODE_F(word, k) __uint_as_float(__byte_perm((word), 0u, 0x0444u | ((k) << 12)))
-
 // Softmax side: MEAN_SW warps = 4 TMEM lane quadrants x (MEAN_SW / 4) column slices of MEAN_COLS columns; each thread owns
 // one query row and MEAN_COLS key columns of the tile.  16 warps (4 per scheduler) instead of 8: the per-head chain
 // wait -> tcgen05.ld -> wait -> 32 exponentials of a warp is latency bound (clock64 timeline: 1500 cycles per head against
@@ -297,30 +281,30 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
   const uint32_t tmem = s.tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int h = 0; h < H; ++h) {
-        const int st = h % MEAN_STAGES;
-        tc::mbar_wait(&s.empty[st], ((h / MEAN_STAGES) & 1) ^ 1);
+    for (int h = 0; h < H; ++h) {
+      const int st = h % MEAN_STAGES;
+      tc::mbar_wait(&s.empty[st], ((h / MEAN_STAGES) & 1) ^ 1);
+      if (tc::elect_one()) {
         tc::mbar_arrive_expect_tx(&s.full[st], 2 * TILE_BYTES);
         tc::tma_load_4d(s.qk[st][0], &tmap_qkv, &s.full[st], 0, h, q0, b);
         tc::tma_load_4d(s.qk[st][1], &tmap_qkv, &s.full[st], 0, H + h, kv0, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      for (int h = 0; h < H; ++h) {
-        const int st = h % MEAN_STAGES, ab = h & 1;
-        tc::mbar_wait(&s.full[st], (h / MEAN_STAGES) & 1);
-        tc::mbar_wait(&s.t_empty[ab], ((h >> 1) & 1) ^ 1);
-        tc::tc_fence_after();
-        const uint32_t q_addr = tc::smem_u32(s.qk[st][0]), k_addr = tc::smem_u32(s.qk[st][1]);
+    for (int h = 0; h < H; ++h) {
+      const int st = h % MEAN_STAGES, ab = h & 1;
+      tc::mbar_wait(&s.full[st], (h / MEAN_STAGES) & 1);
+      tc::mbar_wait(&s.t_empty[ab], ((h >> 1) & 1) ^ 1);
+      tc::tc_fence_after();
+      const uint64_t qd = tc::smem_desc_sw128(tc::smem_u32(s.qk[st][0]), 16, 1024), kd = tc::smem_desc_sw128(tc::smem_u32(s.qk[st][1]), 16, 1024);
+      if (tc::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-          tc::mma_ss(tmem + ab * 128, tc::smem_desc_sw128(q_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(k_addr + ks * 32, 16, 1024),
-                     IDESC_S, ks > 0);
+        for (int ks = 0; ks < HD / 16; ++ks) tc::mma_ss_off(tmem + ab * 128, qd, ks * 2, kd, ks * 2, IDESC_S, ks > 0);
         tc::tc_commit(&s.empty[st]);
         tc::tc_commit(&s.t_full[ab]);
       }
+      __syncwarp();
     }
   } else if (warp >= 4) {
     const int we = warp - 4;                       // 0..MEAN_SW-1
@@ -456,10 +440,9 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
 }
 
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+}  // namespace
 
+namespace acr_attn {
 EncodeTiledFn get_encode_fn() {
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
@@ -472,7 +455,6 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor [B, N, S*H, D] (S = 3 for qkv, 1 for out / d_out) viewed as 4-D (d, sh, n, b); box = 128 rows x 64 d.
 int make_tmap(CUtensorMap* m, const void* base, int B, int N, int SH, int D) {
   EncodeTiledFn fn = get_encode_fn();
   ACR_REQUIRE(fn != nullptr, ACR_E_NOSM100, "cuTensorMapEncodeTiled unavailable");
@@ -486,7 +468,7 @@ int make_tmap(CUtensorMap* m, const void* base, int B, int N, int SH, int D) {
   return 0;
 }
 
-}  // namespace
+}  // namespace acr_attn
 
 extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, float scale,
                                  void* out, float* lse, float* attn_mean, long long mean_batch_stride,
@@ -505,11 +487,8 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
   const int qt = (N + BM - 1) / BM, kt = (N + BN - 1) / BN;
   {
     const size_t smem = sizeof(FwdSmem) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-      ACR_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    static bool attr_set[64] = {false};
+    if (int e = set_max_smem(attn_fwd_kernel, smem, attr_set)) return e;
     dim3 grid(qt, H, B);
     acr::KernelTimer kt_("attn_fwd_kernel", st);
     attn_fwd_kernel<<<grid, 256, smem, st>>>(tmap, (__nv_bfloat16*)out, lse, N, H, scale_log2);
@@ -517,11 +496,8 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
   }
   if (attn_mean) {
     const size_t smem = sizeof(MeanSmem) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-      ACR_CUDA(cudaFuncSetAttribute(attn_mean_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    static bool attr_set[64] = {false};
+    if (int e = set_max_smem(attn_mean_kernel<0>, smem, attr_set)) return e;
     dim3 grid(kt, qt, B);
     acr::KernelTimer kt_("attn_mean_kernel", st);
     attn_mean_kernel<0><<<grid, MEAN_THREADS, smem, st>>>(tmap, lse, attn_mean, mean_batch_stride, (long long)N, GCode{}, p_row0, N, H, scale_log2);
@@ -540,7 +516,6 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
 // =============================================================================================
 namespace {
 
-constexpr uint32_t IDESC_DQ = tc::idesc_bf16_f32(128, 64, 1, 1);   // dQ = dS K : A = dS^T tile in smem (MN-major), B = K MN-major
 
 __global__ void __launch_bounds__(256)
 bwd_delta_kernel(const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ d_out, float* __restrict__ delta,
@@ -690,7 +665,7 @@ __device__ __forceinline__ void bwd_tile_body(BwdSmem& s, int buf, uint32_t tS, 
 // MMA issue order: the scores of tile i+1 are issued BEFORE the gradient MMAs of tile i, so the softmax warps of tile
 // i+1 only wait for 2 of the 5 MMAs; dQ tiles are reduced over key tiles with vectorised fp32 reductions.
 __global__ void __launch_bounds__(384, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+attn_bwd_kernel_r1(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_dq, const float* __restrict__ lse, const float* __restrict__ delta, const float* __restrict__ g_mean, long long g_bs,
                 long long g_ld, GCode gc, __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ dq_acc, float* __restrict__ g_row0,
                 int N, int H, float scale, float scale_log2) {
@@ -961,28 +936,26 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
   if (int e = acr::check_launch("bwd_delta_kernel")) return e;
   if (g_mean || g_code) {
     const size_t smem = sizeof(MeanSmem) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-      ACR_CUDA(cudaFuncSetAttribute(attn_mean_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    static bool attr_set[64] = {false};
+    if (int e = set_max_smem(attn_mean_kernel<1>, smem, attr_set)) return e;
     dim3 grid(kt, qt, B);
     acr::KernelTimer kt_("attn_delta_kernel", st);
     attn_mean_kernel<1><<<grid, MEAN_THREADS, smem, st>>>(tmap_qkv, lse, const_cast<float*>(g_mean), g_batch_stride, g_row_stride, gc, delta, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel<1>")) return e;
   }
-  {
+  static const bool use_r1 = getenv("ACR_BWD_R1") != nullptr;      // round-1 kernel, kept for A/B measurements only
+  if (use_r1) {
     const size_t smem = sizeof(BwdSmem) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-      ACR_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    static bool attr_set[64] = {false};
+    if (int e = set_max_smem(attn_bwd_kernel_r1, smem, attr_set)) return e;
     dim3 grid(kt, H, B);
     acr::KernelTimer kt_("attn_bwd_kernel", st);
-    attn_bwd_kernel<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, tmap_dq, lse, delta, g_mean, g_batch_stride, g_row_stride, gc, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
+    attn_bwd_kernel_r1<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, tmap_dq, lse, delta, g_mean, g_batch_stride, g_row_stride, gc, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
                                              N, H, scale, scale_log2);
-    if (int e = acr::check_launch("attn_bwd_kernel")) return e;
+    if (int e = acr::check_launch("attn_bwd_kernel_r1")) return e;
+  } else {
+    if (int e = launch_attn_bwd(tmap_qkv, tmap_do, tmap_dq, lse, delta, g_mean, g_batch_stride, g_row_stride, gc, (__nv_bfloat16*)d_qkv, g_row0, B, N, H, scale, st))
+      return e;
   }
   const long long nconv = (long long)rows * (HD / 8);
   bwd_dq_convert_kernel<<<(unsigned)((nconv + 255) / 256), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)d_qkv, B, N, H, scale);

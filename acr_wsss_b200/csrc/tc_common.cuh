@@ -43,6 +43,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp (elect.sync).  Single-thread instructions (tcgen05.mma / commit, TMA) issued under
+// `if (elect_one())` compile to straight-line code; under `if (lane == 0)` ptxas wraps every one of them in an
+// ELECT / BRA.U.ANY loop (~70 cycles per tcgen05.mma instead of ~20).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -96,6 +105,30 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// The same MMAs with a K-step offset added to the descriptors' start-address fields (16-byte units) INSIDE the asm statement.
+// Built in C++ (desc + ks * step), the descriptor variants of a tile are loop-invariant: ptxas hoists all of them out of the
+// tile loop and spills them in the 40..48-register MMA warp.  No carry leaves the 14-bit field: every tile lies below 256 KB.
+__device__ __forceinline__ void mma_ss_off(uint32_t d_tmem, uint64_t a_desc, uint32_t a_off, uint64_t b_desc, uint32_t b_off, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db, t;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "cvt.u64.u32 t, %2;\n\tadd.u64 da, %1, t;\n\t"
+      "cvt.u64.u32 t, %4;\n\tadd.u64 db, %3, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "r"(a_off), "l"(b_desc), "r"(b_off), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_off(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t b_off, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db, t;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "cvt.u64.u32 t, %3;\n\tadd.u64 db, %2, t;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(b_off), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
