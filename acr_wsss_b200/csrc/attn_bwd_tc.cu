@@ -4,7 +4,7 @@
 // (delta comes from bwd_delta_kernel + attn_mean_kernel<1>, attn_tc.cu).
 //
 // One CTA per (key tile j, head, image): K_j, V_j stationary, loop over query tiles i.  512 threads, five roles:
-//   warp 0      TMA producer: K, V once; per query tile Q_i, dO_i and the 128x128-byte tile of sign codes of G
+//   warp 0      TMA producer: K, V once; per query tile Q_i, dO_i (three-stage ring)
 //   warp 1      MMA issuer (one thread): S = Q_i K_j^T, dP = dO_i V_j^T (SS, 128x128x64), then dV += P^T dO_i,
 //               dK += dS^T Q_i, dQ_i = dS K_j from the bf16 P / dS tiles the softmax warps publish in shared memory
 //   warps 2-3   row statistics (log2-domain LSE, delta) of the next query tile into shared memory
@@ -12,29 +12,28 @@
 //               registers in one go and hands tS/tDP back at once (sdp_free), so the scores of tile i+1 run on the tensor
 //               pipe UNDER the exponentials of tile i; P and dS stay in registers until the gradient MMAs of tile i-1 have
 //               released the single-buffered smem tiles (pds_free)
-//   warps 12-15 dQ drain: TMEM -> fp32 staging tile -> two cp.reduce.async.bulk.tensor (fp32 add) per tile; tDQ is double
-//               buffered so the dQ MMA of tile i+1 never waits for the drain of tile i
+//   warps 12-15 dQ drain: TMEM -> fp32 staging tile -> two cp.reduce.async.bulk.tensor (fp32 add) per tile
 // The softmax warps therefore execute nothing but the element-wise chain (round 1's kernel spent ~75 % of their time in
 // barrier waits, the dQ hand-over and the exposed S/dP MMA latency: profiles/r01g_ncu_attn_bwd_full.txt).
 // Element-wise math uses the packed fp32x2 instructions (FFMA2 / FMUL2 / FADD2): 5 issue slots per element instead of 8.
 #include "attn_tc.cuh"
-#include <cstring>
 
 using namespace acr_attn;
 
 namespace {
 
+constexpr int NST = 3;
+
 struct BwdSmem {
   uint8_t k[TILE_BYTES];
   uint8_t v[TILE_BYTES];
-  uint8_t q[2][TILE_BYTES];
-  uint8_t d_o[2][TILE_BYTES];
+  uint8_t q[NST][TILE_BYTES];      // Q_i / dO_i ring: three stages, because a slot is only released by the gradient MMAs of its
+  uint8_t d_o[NST][TILE_BYTES];    // tile and the TMA refill takes ~1500 cycles (two stages left that latency exposed every tile)
   uint8_t p[2][TILE_BYTES];        // [kv block of 64][q row][64 kv] bf16, SWIZZLE_128B rows (one row per thread)
   uint8_t ds[2][TILE_BYTES];       // same layout: read MN-major (A = dS^T / P^T) and K-major (A = dS)
   uint8_t dq[2][TILE_BYTES];       // fp32 staging of one dQ tile: [32-column half][q row][32 floats], SWIZZLE_128B
-  uint8_t code[2][TILE_BYTES];     // [stage][q row][128 kv] sign codes of G, SWIZZLE_128B
-  float stat[2][2][BM];            // [stage][0: lse * log2(e), 1: delta][q row]
-  uint64_t kv_full, qdo_full[2], qdo_empty[2], stat_full[2], sdp_full, sdp_free, pds_full, pds_free, dq_full[2], dq_free[2], all_done;
+  float stat[2][2][BM];            // [tile parity][0: lse * log2(e), 1: delta][q row]
+  uint64_t kv_full, qdo_full[NST], qdo_empty[NST], stat_full[2], sdp_full, sdp_free, pds_full, pds_free, dq_full, dq_free, all_done;
   uint32_t tmem_base;
 };
 static_assert(sizeof(BwdSmem) <= 232448, "BwdSmem exceeds the 227 KB dynamic shared memory limit");
@@ -78,24 +77,19 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-
 // Softmax backward of one thread's share of a tile: query row `row`, key columns colbase .. colbase+63 (`half` of the tile).
 // Pulls S / dP out of TMEM 32 columns at a time, releases them (sdp_free) after the second pull and writes P and dS as bf16
 // into this thread's rows of the swizzled shared-memory tiles (p_row / ds_row: shared addresses of the row start).  The tiles are
 // single-buffered: the first store waits for the gradient MMAs of the previous tile (pds_free, parity pds_par; < 0: no wait).
 // GMODE: 0 no affinity gradient, 1 fp32 rows (scalar loads, bounds checked), 2 fp32 rows (128-bit loads), 3 sign codes
-// (shared-memory tile filled by TMA; `gw` then carries 2*w*scale/H of this row, otherwise 1/H).
+// (64 bytes of this row in cwt, loaded one tile ahead; `gw` then carries 2*w*scale/H of this row, otherwise 1/H).
 template <int GMODE, bool TAIL>
-__device__ __forceinline__ void bwd_softmax_tile(BwdSmem& s, uint32_t tS, uint32_t tDP, uint32_t lane_off, int half, int row, int colbase, int N,
-                                                 const float* __restrict__ grow, uint32_t crow, float gw, float scale_log2, float lse2,
+__device__ __forceinline__ void bwd_softmax_tile(BwdSmem& s, uint32_t tS, uint32_t tDP, uint32_t tDS, uint32_t lane_off, int half, int row, int colbase, int N,
+                                                 const float* __restrict__ grow, const uint32_t (&cwt)[16], float gw, float scale_log2, float lse2,
                                                  float dlt, float* __restrict__ rd_row0, uint32_t p_row, uint32_t ds_row, int pds_par) {
   const int nlive = TAIL ? (N - colbase) : 64;         // live key columns of this thread (warp-uniform; may be <= 0)
   const uint64_t sc2 = f2_pack(scale_log2, scale_log2), nl2 = f2_pack(-lse2, -lse2), nd2 = f2_pack(-dlt, -dlt), gw2 = f2_pack(gw, gw);
+  uint32_t pk[32], dk[32];        // P and dS of the whole tile as packed bf16 pairs: held until the previous tile's gradient MMAs retire
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     // 32 columns at a time (a tcgen05.ld.x32 needs 32 consecutive registers; four such blocks live at once made ptxas spill)
@@ -113,20 +107,13 @@ __device__ __forceinline__ void bwd_softmax_tile(BwdSmem& s, uint32_t tS, uint32
       tc::mbar_arrive(&s.sdp_free);
       if (half == 0 && row < 32) BWD_TRACE(1, (pds_par < 0 ? 0 : 15), 2);      // only tile 0 and "some later tile" (slot 15)
     }
-    uint32_t pk[16], dk[16];
     if (!live) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) pk[e] = dk[e] = 0u;
+      for (int e = 0; e < 16; ++e) pk[c * 16 + e] = dk[c * 16 + e] = 0u;
     } else {
-    uint32_t cw[8];
+    const uint32_t* cw = cwt + c * 8;        // sign codes of these 32 columns (GMODE 3), prefetched by the caller
     float g[GMODE == 1 || GMODE == 2 ? 32 : 1];
-    if (GMODE == 3) {
-#pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const uint4 t = lds128(crow ^ (uint32_t)((half * 4 + c * 2 + v) << 4));
-        cw[v * 4 + 0] = t.x; cw[v * 4 + 1] = t.y; cw[v * 4 + 2] = t.z; cw[v * 4 + 3] = t.w;
-      }
-    } else if (GMODE == 2) {
+    if (GMODE == 2) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(grow + c * 32) + e);
@@ -158,7 +145,11 @@ __device__ __forceinline__ void bwd_softmax_tile(BwdSmem& s, uint32_t tS, uint32
       }
       uint64_t dp = f2_pack(__uint_as_float(rd[2 * e]), __uint_as_float(rd[2 * e + 1]));
       if (GMODE == 3) {
-        const float g0 = ACR_CODE_F(cw[e >> 1], (2 * e) & 3), g1 = ACR_CODE_F(cw[e >> 1], (2 * e + 1) & 3);
+        float g0 = ACR_CODE_F(cw[e >> 1], (2 * e) & 3), g1 = ACR_CODE_F(cw[e >> 1], (2 * e + 1) & 3);
+        if (TAIL) {        // bytes past N are row padding (never written by the loss kernel)
+          if (i0 >= nlive) g0 = 0.f;
+          if (i0 + 1 >= nlive) g1 = 0.f;
+        }
         dp = f2_fma(f2_pack(g0, g1), gw2, dp);
       } else if (GMODE != 0) {
         dp = f2_fma(f2_pack(g[2 * e], g[2 * e + 1]), gw2, dp);
@@ -166,31 +157,41 @@ __device__ __forceinline__ void bwd_softmax_tile(BwdSmem& s, uint32_t tS, uint32
       const uint64_t dsv = f2_mul(f2_pack(p0, p1), f2_add(dp, nd2));
       float d0, d1;
       f2_unpack(dsv, d0, d1);
-      pk[e] = tc::pack_bf16(p0, p1);
-      dk[e] = tc::pack_bf16(d0, d1);
+      pk[c * 16 + e] = tc::pack_bf16(p0, p1);
+      dk[c * 16 + e] = tc::pack_bf16(d0, d1);
     }
     }   // live
-    // the gradient MMAs of the previous tile read the (single-buffered) P / dS tiles: wait for them to retire
-    if (c == 0 && pds_par >= 0) {
-      if (half == 0 && row < 32) BWD_TRACE(1, 15, 3);
-      tc::mbar_wait(&s.pds_free, (uint32_t)pds_par);
-      if (half == 0 && row < 32) BWD_TRACE(1, 15, 5);
-    }
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {               // 16-byte chunk (c*4 + cc) of this row at position chunk ^ (row & 7)
-      // p_row / ds_row = (row start) ^ ((row & 7) << 4): rows are 128-byte aligned, so one XOR with an immediate addresses the chunk
-      sts128(p_row ^ (uint32_t)((c * 4 + cc) << 4), pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-      sts128(ds_row ^ (uint32_t)((c * 4 + cc) << 4), dk[cc * 4 + 0], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]);
-    }
   }
+  // The P / dS tiles are single-buffered: the dV / dK MMAs of the previous tile (pds_free) and its dQ MMA (dq_full, reads tDS)
+  // must have retired.  Waiting here, after the whole tile has been computed, keeps that off the critical path.
+  if (pds_par >= 0) {
+    if (half == 0 && row < 32) BWD_TRACE(1, 15, 3);
+    tc::mbar_wait(&s.pds_free, (uint32_t)pds_par);
+    tc::mbar_wait(&s.dq_full, (uint32_t)pds_par);
+    tc::tc_fence_after();
+    if (half == 0 && row < 32) BWD_TRACE(1, 15, 5);
+  }
+#pragma unroll
+  for (int cc = 0; cc < 8; ++cc) {               // 16-byte chunk cc of this row at position cc ^ (row & 7)
+    // p_row / ds_row = (row start) ^ ((row & 7) << 4): rows are 128-byte aligned, so one XOR with an immediate addresses the chunk
+    sts128(p_row ^ (uint32_t)(cc << 4), pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
+    sts128(ds_row ^ (uint32_t)(cc << 4), dk[cc * 4 + 0], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]);
+  }
+  // dS a second time, as the TMEM-resident A operand of dQ = dS K (64 keys = 32 packed columns): the dQ MMA then reads only K
+  // from shared memory, whose bandwidth (128 B/clk) is what bounds this kernel
+  tc::tmem_st16(tDS + lane_off + half * 32, dk);
+  tc::tmem_st16(tDS + lane_off + half * 32 + 16, dk + 16);
+  tc::tmem_st_wait();
 }
 
 struct SoftmaxArgs {
-  uint32_t tS, tDP, lane_off;
+  uint32_t tS, tDP, tDS, lane_off;
   int half, row, colbase, N, H, ntiles, b, h;
   const float* g_mean;
   long long g_bs, g_ld;
   float* g_row0;
+  const unsigned char* code;
+  long long code_bs, code_ld;
   float w_cls2, w_aff2, invH, scale_log2;
   uint32_t p_row, ds_row, swz;
 };
@@ -200,18 +201,36 @@ template <int GMODE, bool TAIL>
 __device__ __forceinline__ void bwd_softmax_loop(BwdSmem& s, const SoftmaxArgs& a) {
   const int row = a.row, N = a.N;
   const int wq = row & ~31;                            // first row of this warp's TMEM lane quadrant
+  // Sign codes: 64 bytes of this thread's row per tile, straight from global memory (each byte is used by one thread of one
+  // CTA per head, so staging through shared memory would only add traffic to the resource that bounds the kernel); the loads
+  // of tile i+1 are issued at the top of tile i.  Rows past N read the (valid) last row: their P is 0.
+  uint32_t cwn[16];
+  auto load_codes = [&](int i) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.code + (size_t)a.b * a.code_bs + (size_t)min(i * BM + row, N - 1) * a.code_ld + a.colbase);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      uint4 t = make_uint4(0u, 0u, 0u, 0u);
+      if (!TAIL || a.colbase + v * 16 < N) t = __ldg(src + v);
+      cwn[v * 4 + 0] = t.x; cwn[v * 4 + 1] = t.y; cwn[v * 4 + 2] = t.z; cwn[v * 4 + 3] = t.w;
+    }
+  };
+  if (GMODE == 3) load_codes(0);
   for (int i = 0; i < a.ntiles; ++i) {
-    const int st = i & 1;
+    uint32_t cw[16];
+    if (GMODE == 3) {
+#pragma unroll
+      for (int v = 0; v < 16; ++v) cw[v] = cwn[v];
+      if (i + 1 < a.ntiles) load_codes(i + 1);
+    }
     const int q0 = i * BM;
     const int pds_par = (i > 0) ? ((i - 1) & 1) : -1;
     const int qi = q0 + row;
     const bool rows_live = q0 + wq < N;                // warp-uniform
     float lse2 = INFINITY, dlt = 0.f;
     if (rows_live) {
-      tc::mbar_wait(&s.stat_full[st], (i >> 1) & 1);
-      lse2 = s.stat[st][0][row];
-      dlt = s.stat[st][1][row];
-      if (GMODE == 3) tc::mbar_wait(&s.qdo_full[st], (i >> 1) & 1);     // the code tile arrives with Q / dO
+      tc::mbar_wait(&s.stat_full[i & 1], (i >> 1) & 1);
+      lse2 = s.stat[i & 1][0][row];
+      dlt = s.stat[i & 1][1][row];
     }
     if (a.half == 0 && row < 32) BWD_TRACE(1, i, 0);
     tc::mbar_wait(&s.sdp_full, i & 1);
@@ -222,20 +241,31 @@ __device__ __forceinline__ void bwd_softmax_loop(BwdSmem& s, const SoftmaxArgs& 
       // zero-filled dO / Q rows in the gradient MMAs)
       tc::tc_fence_before();
       tc::mbar_arrive(&s.sdp_free);
-      if (pds_par >= 0) tc::mbar_wait(&s.pds_free, (uint32_t)pds_par);
+      if (pds_par >= 0) {
+        tc::mbar_wait(&s.pds_free, (uint32_t)pds_par);
+        tc::mbar_wait(&s.dq_full, (uint32_t)pds_par);
+        tc::tc_fence_after();
+      }
 #pragma unroll
       for (int cc = 0; cc < 8; ++cc) {
         sts128(a.p_row ^ (uint32_t)(cc << 4), 0u, 0u, 0u, 0u);
         sts128(a.ds_row ^ (uint32_t)(cc << 4), 0u, 0u, 0u, 0u);
+      }
+      {
+        uint32_t z[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) z[e] = 0u;
+        tc::tmem_st16(a.tDS + a.lane_off + a.half * 32, z);
+        tc::tmem_st16(a.tDS + a.lane_off + a.half * 32 + 16, z);
+        tc::tmem_st_wait();
       }
     } else {
       // rows past N inside a live warp read a clamped (valid) row of G: their P is 0, so the value is irrelevant (the tile body
       // contains warp-collective tcgen05.ld, so all lanes run it)
       const float* grow = (GMODE == 1 || GMODE == 2) ? a.g_mean + (size_t)a.b * a.g_bs + (size_t)min(qi, N - 1) * a.g_ld + a.colbase : nullptr;
       float* rd_row0 = (a.g_row0 != nullptr && qi == 0) ? a.g_row0 + ((size_t)a.b * a.H + a.h) * N + a.colbase : nullptr;
-      const uint32_t crow = (tc::smem_u32(s.code[st]) + row * 128) ^ a.swz;
       const float gw = (GMODE == 3) ? ((qi == 0) ? a.w_cls2 : a.w_aff2) : a.invH;
-      bwd_softmax_tile<GMODE, TAIL>(s, a.tS, a.tDP, a.lane_off, a.half, row, a.colbase, N, grow, crow, gw, a.scale_log2, lse2, dlt, rd_row0,
+      bwd_softmax_tile<GMODE, TAIL>(s, a.tS, a.tDP, a.tDS, a.lane_off, a.half, row, a.colbase, N, grow, cw, gw, a.scale_log2, lse2, dlt, rd_row0,
                                     a.p_row, a.ds_row, pds_par);
     }
     tc::fence_proxy_async_smem();
@@ -246,7 +276,7 @@ __device__ __forceinline__ void bwd_softmax_loop(BwdSmem& s, const SoftmaxArgs& 
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                const __grid_constant__ CUtensorMap tmap_dq, const __grid_constant__ CUtensorMap tmap_code,
+                const __grid_constant__ CUtensorMap tmap_dq,
                 const float* __restrict__ lse, const float* __restrict__ delta, const float* __restrict__ g_mean, long long g_bs,
                 long long g_ld, GCode gc, __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ g_row0, int N, int H, float scale,
                 float scale_log2) {
@@ -262,19 +292,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     tc::prefetch_tmap(&tmap_qkv);
     tc::prefetch_tmap(&tmap_do);
     tc::prefetch_tmap(&tmap_dq);
-    if (has_code) tc::prefetch_tmap(&tmap_code);
     tc::mbar_init(&s.kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NST; ++i) {
       tc::mbar_init(&s.qdo_full[i], 1);
       tc::mbar_init(&s.qdo_empty[i], 1);
-      tc::mbar_init(&s.stat_full[i], 64);
-      tc::mbar_init(&s.dq_full[i], 1);
-      tc::mbar_init(&s.dq_free[i], 128);
     }
+    for (int i = 0; i < 2; ++i) tc::mbar_init(&s.stat_full[i], 64);
     tc::mbar_init(&s.sdp_full, 1);
     tc::mbar_init(&s.sdp_free, 256);
     tc::mbar_init(&s.pds_full, 256);
     tc::mbar_init(&s.pds_free, 1);
+    tc::mbar_init(&s.dq_full, 1);
+    tc::mbar_init(&s.dq_free, 128);
     tc::mbar_init(&s.all_done, 1);
     tc::fence_barrier_init();
   }
@@ -284,7 +313,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   tc::tc_fence_after();
   if (warp == 0) BWD_TRACE(3, 0, 0);
   const uint32_t tmem = s.tmem_base;
-  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;   // tDQ: 2 x 64 columns
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384, tDS = tmem + 448;   // tDS: dS as bf16 (A operand of the dQ MMA)
 
   if (warp < 4) {
     tc::reg_dealloc<REG_CTRL>();
@@ -296,17 +325,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       }
       __syncwarp();
       for (int i = 0; i < ntiles; ++i) {
-        const int st = i & 1;
-        tc::mbar_wait(&s.qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        const int st = i % NST;
+        tc::mbar_wait(&s.qdo_empty[st], ((i / NST) & 1) ^ 1);
         if (tc::elect_one()) {
-          tc::mbar_arrive_expect_tx(&s.qdo_full[st], (has_code ? 3 : 2) * TILE_BYTES);
+          tc::mbar_arrive_expect_tx(&s.qdo_full[st], 2 * TILE_BYTES);
           tc::tma_load_4d(s.q[st], &tmap_qkv, &s.qdo_full[st], 0, h, i * BM, b);
           tc::tma_load_4d(s.d_o[st], &tmap_do, &s.qdo_full[st], 0, h, i * BM, b);
-          if (has_code)
-            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                             tc::smem_u32(s.code[st])),
-                         "l"(reinterpret_cast<uint64_t>(&tmap_code)), "r"(tc::smem_u32(&s.qdo_full[st])), "r"(kv0), "r"(i * BM), "r"(b)
-                         : "memory");
         }
         __syncwarp();
       }
@@ -320,10 +344,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       const uint64_t kd_mn = tc::smem_desc_sw128(tc::smem_u32(s.k), 1024, 1024);     // K, MN-major  (B of dQ)
       const uint64_t pd_mn = tc::smem_desc_sw128(tc::smem_u32(s.p[0]), TILE_BYTES, 1024);    // P^T  (A of dV): two 64-wide M blocks 16 KB apart
       const uint64_t dsd_mn = tc::smem_desc_sw128(tc::smem_u32(s.ds[0]), TILE_BYTES, 1024);  // dS^T (A of dK)
-      const uint64_t dsd_k = tc::smem_desc_sw128(tc::smem_u32(s.ds[0]), 16, 1024);           // dS   (A of dQ), K-major
       auto issue_scores = [&](int i) {      // S = Q K^T, dP = dO V^T
-        const int st = i & 1;
-        tc::mbar_wait(&s.qdo_full[st], (i >> 1) & 1);
+        const int st = i % NST;
+        tc::mbar_wait(&s.qdo_full[st], (i / NST) & 1);
         tc::tc_fence_after();
         BWD_TRACE(0, i, 0);
         const uint64_t qd = tc::smem_desc_sw128(tc::smem_u32(s.q[st]), 16, 1024), dod = tc::smem_desc_sw128(tc::smem_u32(s.d_o[st]), 16, 1024);
@@ -338,7 +361,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       };
       issue_scores(0);
       for (int i = 0; i < ntiles; ++i) {
-        const int st = i & 1;
+        const int st = i % NST;
         if (i + 1 < ntiles) {                // scores of the next tile as soon as the softmax warps hold S/dP(i) in registers
           tc::mbar_wait(&s.sdp_free, i & 1);
           issue_scores(i + 1);
@@ -347,23 +370,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         BWD_TRACE(0, i, 1);
         tc::mbar_wait(&s.pds_full, i & 1);                          // P / dS(i) published
         BWD_TRACE(0, i, 2);
-        if (i >= 2) tc::mbar_wait(&s.dq_free[st], ((i >> 1) - 1) & 1);   // dQ(i-2) has left tDQ[st]
+        if (i >= 1) tc::mbar_wait(&s.dq_free, (i - 1) & 1);         // dQ(i-1) has left tDQ
         tc::tc_fence_after();
-        const uint32_t tdq = tDQ + st * 64;
         const uint32_t acc = (i > 0) ? 1u : 0u;
         if (tc::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < BM / 16; ++ks)      // dV += P^T dO   (M = kv, K = q: 16 q rows = 2048 bytes per step)
-            tc::mma_ss_off(tDV, pd_mn, ks * 128, dod_mn, ks * 128, IDESC_DQ, acc | (ks > 0));
-#pragma unroll
-          for (int ks = 0; ks < BM / 16; ++ks)      // dK += dS^T Q
+          for (int ks = 0; ks < BM / 16; ++ks)      // dK += dS^T Q   (M = kv, K = q: 16 q rows = 2048 bytes per step)
             tc::mma_ss_off(tDK, dsd_mn, ks * 128, qd_mn, ks * 128, IDESC_DQ, acc | (ks > 0));
 #pragma unroll
-          for (int ks = 0; ks < BN / 16; ++ks)      // dQ_i = dS K   (A = dS tile K-major: 64-wide block ks/4, 32-byte k step; B = K MN-major)
-            tc::mma_ss_off(tdq, dsd_k, (ks >> 2) * (TILE_BYTES >> 4) + (ks & 3) * 2, kd_mn, ks * 128, IDESC_PV, ks > 0);
-          tc::tc_commit(&s.dq_full[st]);
+          for (int ks = 0; ks < BM / 16; ++ks)      // dV += P^T dO
+            tc::mma_ss_off(tDV, pd_mn, ks * 128, dod_mn, ks * 128, IDESC_DQ, acc | (ks > 0));
+          tc::tc_commit(&s.pds_free);               // the shared-memory P / dS tiles and Q / dO are free again ...
           tc::tc_commit(&s.qdo_empty[st]);
-          tc::tc_commit(&s.pds_free);
+#pragma unroll
+          for (int ks = 0; ks < BN / 16; ++ks)      // dQ_i = dS K   (A = dS out of TMEM: 16 keys = 8 columns per step; B = K MN-major)
+            tc::mma_ts_off(tDQ, tDS + ks * 8, kd_mn, ks * 128, IDESC_PV, ks > 0);
+          tc::tc_commit(&s.dq_full);                // ... and with dq_full so is tDS
           if (i + 1 == ntiles) tc::tc_commit(&s.all_done);
         }
         __syncwarp();
@@ -375,7 +397,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       const float* src = (which == 0 ? lse : delta) + ((size_t)b * H + h) * N;
       for (int i = 0; i < ntiles; ++i) {
         const int st = i & 1;
-        tc::mbar_wait(&s.qdo_empty[st], ((i >> 1) & 1) ^ 1);      // the softmax of tile i-2 read its statistics long before
+        // slot reuse: the gradient MMAs of tile i-2 have retired, so its softmax read the statistics long ago
+        if (i >= 2) tc::mbar_wait(&s.qdo_empty[(i - 2) % NST], ((i - 2) / NST) & 1);
         float v[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -408,7 +431,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const uint32_t p_row = (tc::smem_u32(s.p[half]) + row * 128) ^ swz, ds_row = (tc::smem_u32(s.ds[half]) + row * 128) ^ swz;
     // one instantiation of the tile loop per (form of G, key-tail) pair, chosen once: with the choice inside the loop ptxas hoists
     // the invariants of all six bodies and spills
-    const SoftmaxArgs sa{tS, tDP, lane_off, half, row, colbase, N, H, ntiles, b, h, g_mean, g_bs, g_ld, g_row0, w_cls2, w_aff2, invH, scale_log2,
+    const SoftmaxArgs sa{tS, tDP, tDS, lane_off, half, row, colbase, N, H, ntiles, b, h, g_mean, g_bs, g_ld, g_row0, gc.ptr, gc.bs, gc.ld, w_cls2, w_aff2, invH, scale_log2,
                          p_row, ds_row, swz};
     if (has_code) {
       if (!tail) bwd_softmax_loop<3, false>(s, sa); else bwd_softmax_loop<3, true>(s, sa);
@@ -456,9 +479,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const uint32_t dq_row = (tc::smem_u32(s.dq[0]) + row * 128) ^ ((uint32_t)(row & 7) << 4);      // row start ^ swizzle term
     uint32_t r[32];
     for (int i = 0; i < ntiles; ++i) {
-      const int st = i & 1;
       if (warp == 12) BWD_TRACE(2, i, 0);
-      tc::mbar_wait(&s.dq_full[st], (i >> 1) & 1);
+      tc::mbar_wait(&s.dq_full, i & 1);
       tc::tc_fence_after();
       if (warp == 12) BWD_TRACE(2, i, 1);
       if (i > 0) {          // the reduce-add of the previous tile must have read the staging tile
@@ -468,14 +490,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       if (warp == 12) BWD_TRACE(2, i, 2);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        tc::tmem_ld32(tDQ + st * 64 + lane_off + c * 32, r);
+        tc::tmem_ld32(tDQ + lane_off + c * 32, r);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 8; ++e)
           sts128((dq_row + c * TILE_BYTES) ^ (uint32_t)(e << 4), r[4 * e], r[4 * e + 1], r[4 * e + 2], r[4 * e + 3]);
       }
       tc::tc_fence_before();
-      tc::mbar_arrive(&s.dq_free[st]);
+      tc::mbar_arrive(&s.dq_free);
       tc::fence_proxy_async_smem();
       asm volatile("bar.sync 3, 128;" ::: "memory");
       if (leader) {
@@ -508,28 +530,13 @@ namespace acr_attn {
 int launch_attn_bwd(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_do, const CUtensorMap& tmap_dq, const float* lse, const float* delta,
                     const float* g_mean, long long g_bs, long long g_ld, const GCode& gc, __nv_bfloat16* d_qkv, float* g_row0,
                     int B, int N, int H, float scale, cudaStream_t st) {
-  CUtensorMap tmap_code;
-  memset(&tmap_code, 0, sizeof(tmap_code));
-  if (gc.ptr != nullptr) {
-    // sign codes of block l: uint8 [B, N, ld] (rows padded to 128 bytes) viewed as (col, row, b) with the TRUE extent N in both
-    // map dimensions: bytes past N (row padding, rows of the thin last tile) are zero-filled by TMA = "no gradient"
-    EncodeTiledFn fn = get_encode_fn();
-    ACR_REQUIRE(fn != nullptr, ACR_E_NOSM100, "cuTensorMapEncodeTiled unavailable");
-    cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)N, (cuuint64_t)B};
-    cuuint64_t strides[2] = {(cuuint64_t)gc.ld, (cuuint64_t)gc.bs};
-    cuuint32_t box[3] = {128, (cuuint32_t)BM, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(&tmap_code, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<unsigned char*>(gc.ptr), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    ACR_REQUIRE(r == CUDA_SUCCESS, ACR_E_INVAL, "cuTensorMapEncodeTiled(codes) failed (%d)", (int)r);
-  }
   const size_t smem = sizeof(BwdSmem);
   static bool attr_set[64] = {false};
   if (int e = set_max_smem(attn_bwd_kernel, smem, attr_set)) return e;
   const int kt = (N + BN - 1) / BN;
   dim3 grid(kt, H, B);
   acr::KernelTimer kt_("attn_bwd_kernel", st);
-  attn_bwd_kernel<<<grid, BWD_THREADS, smem, st>>>(tmap_qkv, tmap_do, tmap_dq, tmap_code, lse, delta, g_mean, g_bs, g_ld, gc, d_qkv, g_row0, N, H,
+  attn_bwd_kernel<<<grid, BWD_THREADS, smem, st>>>(tmap_qkv, tmap_do, tmap_dq, lse, delta, g_mean, g_bs, g_ld, gc, d_qkv, g_row0, N, H,
                                                     scale, scale * kLog2e);
   return acr::check_launch("attn_bwd_kernel");
 }
