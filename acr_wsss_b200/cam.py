@@ -175,7 +175,6 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
     for scale in scales:
         inp = F.interpolate(img, size=(int(h * scale), int(w * scale)), mode="bilinear", align_corners=False)
         ph, pw = int((h * scale) // 16), int((w * scale) // 16)
-        model.zero_grad()
         if batched:
             # both flips as one batch of 2, every present class as a copy of the token stream from block start_layer on:
             # one forward and ONE backward per scale (the reference: 2 forwards and 2*C' full backwards)
@@ -195,7 +194,6 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
                 finish_view(None, patch_cam[v:v + 1], cams[v:v + 1], v == 0, ph, pw)
             continue
         for hflip in (1, 2):
-            model.zero_grad()
             view = inp.flip(-1) if hflip % 2 == 1 else inp
             cls_pred, _, attn, patch_cam = model.forward_cam(view)
             output = cls_pred[0, :]
@@ -204,7 +202,8 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
                 if truncate_backward:
                     model.backward_for_getam(output[ci], start_layer)
                 else:
-                    model.zero_grad()
+                    # (set_to_none=False: a Trainer-attached model keeps its .grad views of the flat gradient buffer)
+                    model.zero_grad(set_to_none=False)
                     output[ci].backward(retain_graph=True)      # one_hot * output, infer_cam.py:173-179
                 cam, _, _ = model.getam(0, start_layer=start_layer, func=getam_func)
                 rows0.append(cam[0])

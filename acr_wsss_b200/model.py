@@ -41,7 +41,7 @@ def _lin(mod, x, skip_bias_grad=False):
 def _fold_bias(mod, x):
     """The bias Parameter whose gradient add_layer_norm's backward can take over (cached bf16 path with fp32 .grad), or None."""
     b = mod.bias
-    if b is not None and _cached(mod, x) and b.requires_grad and b.grad is not None and b.grad.dtype == torch.float32:
+    if ops.DIRECT_GRADS and b is not None and _cached(mod, x) and b.requires_grad and b.grad is not None and b.grad.dtype == torch.float32:
         return b
     return None
 
@@ -189,6 +189,7 @@ class VisionTransformer(nn.Module):
                  precision="fp32"):
         super().__init__()
         self.patch_size = [patch_size, patch_size]
+        self.residual = "auto"         # bf16 path: "auto" (bf16 stream in train mode, fp32 in eval mode), "bf16" or "fp32"
         self.start_index = 1
         self.embed_dim = embed_dim
         self.patch_embed = PatchEmbed(img_size, patch_size, 3, embed_dim)
@@ -250,6 +251,12 @@ class VisionTransformer(nn.Module):
             self._rep_in = t
             return t
 
+        # Residual stream of the bf16 path.  Training keeps it in bf16 (the add is folded into the LayerNorm kernels and the
+        # stream is read / written once per LayerNorm in 2-byte elements); inference (eval mode) keeps it in fp32 like stock
+        # bf16 autocast does: 24 roundings of the stream to bf16 are what separates the CAMs from the fp32 reference
+        # (patch CAM 1.6e-2 -> 0.85e-2 of the reference at 448x448, scripts/diag_bf16_448.py), and speed is not at stake there.
+        if self.residual == "fp32" or (self.residual == "auto" and not self.training):
+            x = x.float()
         if len(self.blocks) and self.blocks[0].fused_ok(x):
             pending = pbias = None
             for i, blk in enumerate(self.blocks):        # the last block's branch meets a plain add: it keeps its own bias gradient

@@ -35,6 +35,24 @@ class _Profile:
 
 PROFILE = _Profile()
 
+# Direct accumulation into preallocated fp32 .grad buffers (weight gradients by the GEMM itself, bias / LayerNorm gradients by
+# this repo's kernels) is an optimisation of the TRAINING step only: Trainer switches it on around its forward+backward.
+# Everything else (CAM inference on a Trainer-attached model, autograd.grad for activations, user code) gets ordinary
+# autograd-returned gradients, whatever the parameters' .grad happen to hold.
+DIRECT_GRADS = False
+
+
+class direct_grads:
+    """Context manager: with ops.direct_grads(): loss = ...; loss.backward()"""
+
+    def __enter__(self):
+        global DIRECT_GRADS
+        self.prev, DIRECT_GRADS = DIRECT_GRADS, True
+
+    def __exit__(self, *exc):
+        global DIRECT_GRADS
+        DIRECT_GRADS = self.prev
+
 
 def _call(name, nlaunch, *args):
     """Invoke C-ABI entry `name`; raises on failure.  `nlaunch` = kernels this call launches (for gpu_launches)."""
@@ -168,13 +186,20 @@ class _AttnCoreBF16(torch.autograd.Function):
                  else d_out.contiguous().to(torch.bfloat16))
         gs, gl = 0, 0
         code, cbs, cld, w_cls, w_aff, g_scale = None, 0, 0, 0.0, 0.0, None
-        if g_mean is not None:
-            g_mean, gs, gl = _strided_map(g_mean.float())
-        elif ctx.state is not None and ctx.state.get("g_code") is not None:
+        if ctx.state is not None and ctx.state.get("g_code") is not None:
+            # always consumed (popped), whatever else arrives: a stale slice must never leak into a later backward
             code = ctx.state.pop("g_code")                      # [B,N,ld] uint8 view of the [B,L,N,ld] code tensor
-            cbs, cld = code.stride(0), code.stride(1)
             w_cls, w_aff = ctx.state.pop("g_w")
             g_scale = ctx.state.pop("g_scale")
+            if g_mean is not None:
+                # a dense gradient reached the same stack through autograd (an extra loss on attn1 / attn2): the kernel takes
+                # ONE form of G, so the codes are decoded into the dense map (rare path, one elementwise pass)
+                g_mean = g_mean.float() + decode_sign_codes(code, N, w_cls, w_aff, g_scale)
+                code, w_cls, w_aff, g_scale = None, 0.0, 0.0, None
+            else:
+                cbs, cld = code.stride(0), code.stride(1)
+        if g_mean is not None:
+            g_mean, gs, gl = _strided_map(g_mean.float())
         d_qkv = torch.empty_like(qkv)
         want_row0 = ctx.state is not None and ctx.state.get("capture_grad", True)
         g_row0 = torch.empty(B, H, N, device=qkv.device, dtype=torch.float32) if want_row0 else None
@@ -186,6 +211,17 @@ class _AttnCoreBF16(torch.autograd.Function):
         if want_row0:
             ctx.state["grad_row0"] = g_row0
         return d_qkv, None, None, None, None
+
+
+def decode_sign_codes(code, N, w_cls, w_aff, g_scale=None):
+    """Sign codes [B,N,ld] (0x00 / 0x3F / 0xBF) -> the dense gradient they stand for, [B,N,N] fp32: +-w (w_cls on the cls row,
+    w_aff elsewhere), times the upstream scalar."""
+    c = code[..., :N]
+    g = (c == 0x3F).float() - (c == 0xBF).float()
+    w = torch.full((N, 1), float(w_aff), device=code.device)
+    w[0, 0] = float(w_cls)
+    g = g * w
+    return g * g_scale.reshape(()) if g_scale is not None else g
 
 
 def attention_core(qkv, num_heads, scale, mean_slot=None, state=None, precision="fp32"):
@@ -280,22 +316,16 @@ class _LinearCachedBF16(torch.autograd.Function):
         gw = gb = None
         if not ctx.needs_input_grad[1]:
             pass                                    # e.g. the truncated GETAM backward: only the activations' gradient is wanted
-        elif weight.grad is not None and weight.grad.dtype == torch.float32 and dy2.is_cuda and dy2.dtype == torch.bfloat16:
+        elif DIRECT_GRADS and weight.grad is not None and weight.grad.dtype == torch.float32 and dy2.is_cuda and dy2.dtype == torch.bfloat16:
             # dW accumulated by the GEMM itself: bf16 operands, fp32 accumulator written in place (no bf16 dW, no add kernel)
             torch.addmm(weight.grad, dy2.t(), x2, out_dtype=torch.float32, out=weight.grad)
-        elif weight.grad is not None:
-            weight.grad.add_(dy2.t() @ x2)
         else:
             gw = (dy2.t() @ x2).float()
         if bias is not None and ctx.needs_input_grad[2]:
-            if bias.grad is not None and dy2.is_cuda and dy2.dtype == torch.bfloat16 and dy2.is_contiguous() and dy2.shape[1] % 2 == 0:
+            if DIRECT_GRADS and bias.grad is not None and dy2.is_cuda and dy2.dtype == torch.bfloat16 and dy2.is_contiguous() and dy2.shape[1] % 2 == 0:
                 colsum_bf16(dy2, bias.grad, accumulate=True)       # db accumulated straight into the fp32 .grad
             else:
-                db = dy2.sum(0, dtype=torch.float32)
-                if bias.grad is not None:
-                    bias.grad.add_(db)
-                else:
-                    gb = db
+                gb = dy2.sum(0, dtype=torch.float32)
         return dx, gw, gb, None, None, None
 
 
@@ -352,7 +382,7 @@ class _LinearGeluCachedBF16(torch.autograd.Function):
         dy2 = dy.reshape(M, F).contiguous()
         df = torch.empty_like(f)
         want_w, want_b = ctx.needs_input_grad[1], bias is not None and ctx.needs_input_grad[2]
-        fused_bias = want_b and bias.grad is not None and bias.grad.dtype == torch.float32
+        fused_bias = DIRECT_GRADS and want_b and bias.grad is not None and bias.grad.dtype == torch.float32
         gb = None
         if fused_bias:
             wsb = _lib.lib().acr_gelu_bwd_workspace(F)
@@ -366,7 +396,7 @@ class _LinearGeluCachedBF16(torch.autograd.Function):
         gw = None
         if not want_w:
             pass
-        elif weight.grad is not None and weight.grad.dtype == torch.float32:
+        elif DIRECT_GRADS and weight.grad is not None and weight.grad.dtype == torch.float32:
             torch.addmm(weight.grad, df.t(), x2, out_dtype=torch.float32, out=weight.grad)
         else:
             gw = (df.t() @ x2).float()
@@ -467,7 +497,7 @@ class _AddLayerNorm(torch.autograd.Function):
         # bias gradient of the Linear that produced `branch` = column sums of dx, taken in the same pass
         col = bb.grad if bb is not None else None
         nw, nb = ctx.norm_params
-        direct = all(p_.grad is not None and p_.grad.dtype == torch.float32 and p_.grad.is_contiguous() for p_ in (nw, nb))
+        direct = DIRECT_GRADS and all(p_.grad is not None and p_.grad.dtype == torch.float32 and p_.grad.is_contiguous() for p_ in (nw, nb))
         if direct:          # d-gamma / d-beta added straight into the fp32 .grad buffers by the finish kernel
             dg, db = nw.grad, nb.grad
         else:
@@ -489,9 +519,9 @@ def add_layer_norm(x, branch, weight, bias, eps=1e-6, out_bf16=False, branch_bia
     """(x + branch, LayerNorm(x + branch)) with the add fused into the LayerNorm kernels (forward and backward).
     branch_bias: the bias Parameter of the Linear that produced `branch` (via linear_cached_bf16(..., skip_bias_grad=True));
     its fp32 .grad is incremented by the column sums of the branch gradient inside the backward kernel."""
-    if branch_bias is not None and not (branch_bias.grad is not None and branch_bias.grad.dtype == torch.float32
+    if branch_bias is not None and not (DIRECT_GRADS and branch_bias.grad is not None and branch_bias.grad.dtype == torch.float32
                                         and x.dtype == torch.bfloat16 and out_bf16):
-        raise RuntimeError("add_layer_norm: branch_bias needs a preallocated fp32 .grad and the bf16 stream")
+        raise RuntimeError("add_layer_norm: branch_bias needs ops.direct_grads(), a preallocated fp32 .grad and the bf16 stream")
     return _AddLayerNorm.apply(x, branch, weight, bias, eps, out_bf16, branch_bias)
 
 
@@ -503,9 +533,10 @@ def layer_norm(x, weight, bias, eps=1e-6, out_bf16=False):
 # ----------------------------------------------------------------------------------------------
 # (a7) consistency loss
 # ----------------------------------------------------------------------------------------------
-def consistency_codes(attn1, attn2, p, one_buffer=False):
+def consistency_codes(attn1, attn2, p, one_buffer=False, swapped=False):
     """loss2 plus the gradient as SIGN CODES: uint8 [B,L,N,ld] (ld = N padded to 128), 0x00 / 0x3F (+) / 0xBF (-).
-    one_buffer: c1/c2 are the two halves of a single [2B,L,N,ld] tensor (views batched through the trunk together)."""
+    one_buffer: c1/c2 are the two halves of a single [2B,L,N,ld] tensor (views batched through the trunk together);
+    swapped: attn1 is the SECOND half of that batch (consistency_loss(attn2, attn1)), so c1 must land in rows [B:]."""
     _need_cuda(attn1, attn2)
     B, L, N, _ = attn1.shape
     a1 = attn1.contiguous().float()
@@ -514,7 +545,7 @@ def consistency_codes(attn1, attn2, p, one_buffer=False):
     loss2 = torch.empty(2, device=a1.device, dtype=torch.float32)
     if one_buffer:
         c = torch.empty(2 * B, L, N, ld, device=a1.device, dtype=torch.uint8)
-        c1, c2 = c[:B], c[B:]
+        c1, c2 = (c[B:], c[:B]) if swapped else (c[:B], c[B:])
     else:
         c1 = torch.empty(B, L, N, ld, device=a1.device, dtype=torch.uint8)
         c2 = torch.empty(B, L, N, ld, device=a1.device, dtype=torch.uint8)
@@ -575,10 +606,10 @@ class _ConsistencyLossCodes(torch.autograd.Function):
     after this node because the stack it produced feeds this loss)."""
 
     @staticmethod
-    def forward(ctx, attn1, attn2, p, alpha, states1, states2):
+    def forward(ctx, attn1, attn2, p, alpha, states1, states2, swapped):
         B, L, N, _ = attn1.shape
         merged = states1 is states2 or (len(states1) == len(states2) and all(a is b for a, b in zip(states1, states2)))
-        loss2, c1, c2 = consistency_codes(attn1.detach(), attn2.detach(), p, merged)
+        loss2, c1, c2 = consistency_codes(attn1.detach(), attn2.detach(), p, merged, swapped and merged)
         if merged:      # both views went through the trunk as one batch of 2B: c1/c2 are the halves of one buffer
             ctx.codes = (c1._base if c1._base is not None else c1,)
             ctx.states = (states1,)
@@ -595,10 +626,15 @@ class _ConsistencyLossCodes(torch.autograd.Function):
         scale = g_total.detach().reshape(1).float().contiguous()
         for codes, states in zip(ctx.codes, ctx.states):
             for l, st in enumerate(states):
+                if st.get("g_code") is not None:
+                    # a second loss on the same stacks: codes cannot be summed byte-wise
+                    raise RuntimeError("consistency_loss was applied twice to the same attention stacks; its sign-code gradient "
+                                       "cannot be accumulated -- combine the terms into one call, or detach the stacks' "
+                                       "_acr_states attribute to use the dense-gradient path")
                 st["g_code"] = codes[:, l]
                 st["g_w"] = ctx.w
                 st["g_scale"] = scale
-        return None, None, None, None, None, None
+        return None, None, None, None, None, None, None
 
 
 def consistency_loss(attn1, attn2, p, alpha):
@@ -610,7 +646,10 @@ def consistency_loss(attn1, attn2, p, alpha):
     st1, st2 = getattr(attn1, "_acr_states", None), getattr(attn2, "_acr_states", None)
     if (st1 is not None and st2 is not None and attn1.requires_grad and attn2.requires_grad
             and all(s is not None and s.get("fused") for s in st1 + st2)):
-        return _ConsistencyLossCodes.apply(attn1, attn2, int(p), float(alpha), st1, st2)
+        h1, h2 = getattr(attn1, "_acr_half", None), getattr(attn2, "_acr_half", None)
+        merged = len(st1) == len(st2) and all(a is b for a, b in zip(st1, st2))
+        if not merged or (h1, h2) in ((0, 1), (1, 0)):         # (the same half twice would need two code slices per block)
+            return _ConsistencyLossCodes.apply(attn1, attn2, int(p), float(alpha), st1, st2, (h1, h2) == (1, 0))
     return _ConsistencyLoss.apply(attn1, attn2, int(p), float(alpha))
 
 

@@ -88,13 +88,26 @@ class Trainer:
     (device, detached); gradients are averaged across ranks when torch.distributed is initialised.  `prefetch(img, label)`
     followed by `step()` overlaps the host->device copy of the next batch with the current step."""
 
-    def __init__(self, model, lr=0.01, wt_dec=5e-4, max_step=100000, alpha=100.0, bucket_bytes=64 << 20, cuda_graph=None):
+    def __init__(self, model, lr=0.01, wt_dec=5e-4, max_step=100000, alpha=100.0, bucket_bytes=64 << 20, cuda_graph=None,
+                 dense_crf=None):
+        """dense_crf: None, or the options of the dense-CRF regulariser of BASELINE.json configs[3] (flags of infer_cam.py:58-65):
+        dict(weight=1e-7, sigma_rgb=15.0, sigma_xy=100.0, scale=0.5, mean=120.0, std=58.0).  The term is applied to the softmax over
+        [background, classes] of view 1's patch-token logits up-sampled to the image size (K = C + 1 planes), on the image
+        de-normalised to 0..255 with (mean, std)."""
         self.model = model
         self.alpha = alpha
+        self.dense_crf = None if dense_crf is None else dict({"weight": 1e-7, "sigma_rgb": 15.0, "sigma_xy": 100.0, "scale": 0.5,
+                                                              "mean": 120.0, "std": 58.0}, **dense_crf)
         model.train()
         model.set_capture_grad(False)
         self.dev = next(model.parameters()).device
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if self.world > 1:
+            # every replica starts from rank 0's weights (what DistributedDataParallel's constructor does for the reference,
+            # train_acr.py:99); buffers included.  Done BEFORE the flat fp32 / bf16 / momentum buffers are built from them.
+            with torch.no_grad():
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t.data, 0)
         self.graph = (self.dev.type == "cuda") if cuda_graph is None else bool(cuda_graph)
         # parameters the ACR path never reaches get no gradient in the reference either (SURVEY Q4)
         self.buckets = GradBuckets(list(model.parameters()), bucket_bytes, hooks=not self.graph)
@@ -104,6 +117,9 @@ class Trainer:
                 self.opt.attach_bf16_views(model.pretrained.model.blocks)
         else:
             self.opt = PolyOptimizer(model.parameters(), lr=lr, weight_decay=wt_dec, max_step=max_step)
+        # weights loaded AFTER construction (model.load / load_state_dict copy into the flat master buffer in place) must
+        # reach the persistent bf16 copy the trunk's Linear layers read
+        self._load_hook = model.register_load_state_dict_post_hook(lambda module, incompatible: self.refresh_bf16())
         self._img = None
         self._label = None
         self._g_fb = None
@@ -114,6 +130,24 @@ class Trainer:
         self._copy_stream = None
         self._pf_img = self._pf_label = None
         self._pf_ready = self._pf_taken = None
+
+    def refresh_bf16(self):
+        """Re-cast the fp32 master weights into the persistent bf16 copy (normally refreshed inside the optimiser step only).
+        Call after writing to the parameters by hand; load_state_dict() does it through a post-hook."""
+        if self.graph and hasattr(self.opt, "flat_param16"):
+            self.opt.flat_param16.copy_(self.opt.flat_param)
+
+    def check_replicas_in_sync(self):
+        """Max |parameter checksum difference| across ranks (0.0 on one rank): every rank must hold bit-identical weights after
+        an all-reduced step.  One small all-gather; meant for tests and bench.py, not for the hot loop."""
+        flat = self.opt.flat_param if self.graph else torch.cat([p.detach().reshape(-1).float() for p in self.buckets.params])
+        cs = torch.stack([flat.double().sum(), flat.double().abs().sum(), (flat.double() * flat.double()).sum()])
+        if self.world == 1:
+            return 0.0
+        allcs = [torch.empty_like(cs) for _ in range(self.world)]
+        dist.all_gather(allcs, cs)
+        ref = allcs[0]
+        return float(max(((c - ref).abs() / (ref.abs() + 1e-300)).max() for c in allcs))
 
     def _stage(self, img, label):
         if self._img is None or self._img.shape != img.shape:
@@ -160,12 +194,31 @@ class Trainer:
         self.prefetch(next_img, next_label)
         return self.step(img, label)
 
+    def _dense_crf_term(self, img, cls_list):
+        """DenseCRF regulariser (losses.dense_crf_loss over this repo's permutohedral filter) for the step's first view."""
+        import torch.nn.functional as F
+        from .losses import dense_crf_loss
+        o = self.dense_crf
+        B, _, S, _ = img.shape
+        p = S // 16
+        layer_4 = self.model.pretrained.activations["4"][:B]                  # view 1 (both views ran as one batch of 2B)
+        logits = self.model.cls_head(layer_4[:, 1:, :])                         # [B, p*p, C] patch-token logits (DPT/ACR.py:133-134)
+        logits = logits.permute(0, 2, 1).reshape(B, -1, p, p)
+        logits = F.interpolate(logits, (S, S), mode="bilinear", align_corners=False)
+        seg = torch.softmax(torch.cat([torch.zeros_like(logits[:, :1]), logits], dim=1), dim=1)      # K = C + 1, background first
+        ori = (img * o["std"] + o["mean"]).clamp(0.0, 255.0)
+        roi = torch.ones(B, S, S, device=img.device)
+        return dense_crf_loss(ori, seg, roi, o["weight"], o["sigma_rgb"], o["sigma_xy"], o["scale"])
+
     def _forward_backward(self, img, label):
         img2 = img.flip(-1)                                   # transforms.RandomHorizontalFlip(p=1), train_acr.py:135
-        cls_list, (attn1, attn2) = self.model.forward_mirror(img, img2)
-        loss, parts = acr_total_loss(cls_list[0], cls_list[1], label, attn1, attn2, img.shape[2] // 16, self.alpha)
-        self.buckets.zero()
-        loss.backward()
+        with ops.direct_grads():          # gradients land straight in the flat fp32 buffer (see ops.DIRECT_GRADS)
+            cls_list, (attn1, attn2) = self.model.forward_mirror(img, img2)
+            loss, parts = acr_total_loss(cls_list[0], cls_list[1], label, attn1, attn2, img.shape[2] // 16, self.alpha)
+            if self.dense_crf is not None:
+                loss = loss + self._dense_crf_term(img, cls_list)
+            self.buckets.zero()
+            loss.backward()
         return loss.detach()
 
     def step(self, img=None, label=None):

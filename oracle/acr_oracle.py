@@ -262,7 +262,8 @@ def affinity_refine(attn, cam, t=1, normalize=False):
 
 def infer_cam_image(sd, img, label, out_size, scales=(1,), start_layer=9, getam_func="cam_grad_s", aff=True,
                     num_heads=12, t=1, normalize=False):
-    """infer_cam.py:145-215 for one image (numpy at the end like the reference)."""
+    """infer_cam.py:145-215 for one image (numpy at the end like the reference).  Device-agnostic: the GPU tests also run it
+    under bf16 autocast on the GPU as the "stock PyTorch bf16" comparator."""
     C = label.shape[1]
     b, c, h, w = img.shape
     rows, cols = out_size
@@ -270,7 +271,7 @@ def infer_cam_image(sd, img, label, out_size, scales=(1,), start_layer=9, getam_
     cam_list, patch_cam_list = [], []
     for scale in scales:
         for hflip in (1, 2):
-            cam_matrix = torch.zeros((b, C, rows, cols))
+            cam_matrix = torch.zeros((b, C, rows, cols), device=img.device)
             inp = F.interpolate(img, size=(int(h * scale), int(w * scale)), mode="bilinear", align_corners=False)
             if hflip % 2 == 1:
                 inp = inp.flip(-1)
@@ -278,7 +279,7 @@ def infer_cam_image(sd, img, label, out_size, scales=(1,), start_layer=9, getam_
             cls_pred, _, attn, patch_cam, maps = forward_cam(sd, inp, num_heads)
             patch_cam = patch_cam.permute(0, 2, 1).reshape(1, C, ph, pw)
             patch_cam = F.interpolate(patch_cam, [rows, cols], mode="bilinear", align_corners=False)[0]
-            patch_cam = patch_cam.detach().numpy() * label[0, :].clone().view(C, 1, 1).numpy()
+            patch_cam = patch_cam.detach().float().cpu().numpy() * label[0, :].clone().view(C, 1, 1).cpu().numpy()
             if hflip % 2 == 1:
                 patch_cam = np.flip(patch_cam, axis=-1)
             patch_cam_list.append(patch_cam)
@@ -290,7 +291,7 @@ def infer_cam_image(sd, img, label, out_size, scales=(1,), start_layer=9, getam_
                 if label[0, ci] > 1e-5:
                     for m in maps:
                         m.grad = None
-                    one_hot = torch.zeros(C)
+                    one_hot = torch.zeros(C, device=img.device)
                     one_hot[ci] = 1
                     torch.sum(one_hot * output).backward(retain_graph=True)
                     cam, _, _ = getam(maps, [m.grad for m in maps], 0, start_layer, getam_func)
@@ -300,8 +301,8 @@ def infer_cam_image(sd, img, label, out_size, scales=(1,), start_layer=9, getam_
                             cam = torch.matmul(patch_aff, cam)
                     cam = cam.reshape(ph, pw)
                     cam = F.interpolate(cam.unsqueeze(0).unsqueeze(0), (rows, cols), mode="bilinear", align_corners=True)
-                    cam_matrix[0, ci, :, :] = cam.detach()
-            cam_up = cam_matrix[0].numpy()
+                    cam_matrix[0, ci, :, :] = cam.detach().float()
+            cam_up = cam_matrix[0].cpu().numpy()
             if hflip % 2 == 1:
                 cam_up = np.flip(cam_up, axis=2)
             cam_list.append(cam_up)

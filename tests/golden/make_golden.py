@@ -89,11 +89,11 @@ def train_golden(name, backbone, S, B, C, alpha, depth_key=11, qkv_gain=4.0):
     save(name, **out)
 
 
-def infer_golden(name, S, C, present, out_size, start_layer, func, scales=(1,)):
+def infer_golden(name, S, C, present, out_size, start_layer, func, scales=(1,), qkv_gain=4.0):
     """infer_cam.py:145-215 around the reference model (lines restated; model/getam are the reference's)."""
     model = loader.build_acr(C, "vitb")
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
-    model.load_state_dict(orc.synth_state_dict(shapes))
+    model.load_state_dict(orc.synth_state_dict(shapes, qkv_gain=qkv_gain))
     model.eval()
     img = synth.images(1, S, seed=3)
     label = synth.labels(1, C, present=present)
@@ -150,7 +150,7 @@ def infer_golden(name, S, C, present, out_size, start_layer, func, scales=(1,)):
     cam_dict = {ci: norm_cam[ci] for ci in present}
     labels = {f"label_t{int(t * 100)}": orc.pseudo_label(cam_dict, C, t) for t in (0.25, 0.4)}
     save(name, norm_cam=norm_cam[list(present)], patch_norm_cam=patch_norm_cam[list(present)], present=list(present),
-         S=S, C=C, out_size=list(out_size), start_layer=start_layer, func=func, scales=list(scales), **labels, **raw)
+         S=S, C=C, out_size=list(out_size), start_layer=start_layer, func=func, scales=list(scales), qkv_gain=qkv_gain, **labels, **raw)
 
 
 def attention_golden():
@@ -183,6 +183,37 @@ def pamr_golden():
     save("pamr.npz", out_a=out_a, out_b=out_b, out_c=out_c)
 
 
+def pamr_448_golden():
+    """configs[2]'s PAMR call at full size: 448x448, 21 classes, 10 iterations, 6 dilations -- the reference module itself
+    (pamr.py:125-144); output sub-sampled ::7 in both image axes."""
+    _, ref_pamr, _ = loader.import_reference()
+    x = (synth.smooth_rgb(1, 448, 448, seed=4) - 120.0) / 58.0
+    mask = synth.probabilities(1, 21, 28, 28, seed=4)
+    out = ref_pamr.PAMR(10, [1, 2, 4, 8, 12, 24])(x, mask)
+    save("pamr_448.npz", out_sub=out[:, :, ::7, ::7], out_sum=out.sum(dim=(2, 3)))
+
+
+def densecrf_golden():
+    """configs[3]: the dense-CRF term at COCO shape, K = 81 planes, 448x448 inputs down-scaled by rloss-scale 0.5 to 224x224
+    (flags of infer_cam.py:58-65: sigma-rgb 15, sigma-xy 100, densecrfloss 1e-7).  The FILTER is the reference C++ compiled in
+    place (oracle/_ref); the loss on top of it follows the upstream rloss convention -- the only part the
+    reference repository does not contain."""
+    assert bo.have_ref(), "run `make -C oracle` first"
+    N, K, S, scale, srgb, sxy, weight = 2, 81, 448, 0.5, 15.0, 100.0, 1e-7
+    img = synth.smooth_rgb(N, S, S, seed=11)
+    seg = synth.probabilities(N, K, S, S, seed=11)
+    roi = (synth.smooth_rgb(N, S, S, seed=12)[:, 0] > 100.0).float()
+    img_s = F.interpolate(img, scale_factor=scale, recompute_scale_factor=True)
+    seg_s = F.interpolate(seg, scale_factor=scale, mode="bilinear", align_corners=False, recompute_scale_factor=True)
+    roi_s = F.interpolate(roi.unsqueeze(1), scale_factor=scale, recompute_scale_factor=True)
+    sp = (seg_s * roi_s).contiguous()
+    AS = torch.from_numpy(bo.ref_bilateral(img_s.numpy(), sp.numpy(), srgb, sxy * scale))
+    loss = -weight * (sp * AS).sum() / N
+    grad_sp = -2.0 * weight * AS * roi_s / N            # d loss / d seg_s
+    save("densecrf_81.npz", cfg=np.array([N, K, S, scale, srgb, sxy, weight], dtype=np.float64), loss=loss,
+         AS_sub=AS[:, ::4, ::5, ::5], AS_sum=AS.sum(dim=(2, 3)), grad_sub=grad_sp[:, ::4, ::5, ::5])
+
+
 def bilateral_golden():
     assert bo.have_ref(), "run `make -C oracle` first"
     cases = {"a": (2, 4, 24, 28, 15.0, 10.0, 4), "b": (1, 3, 33, 31, 8.0, 4.0, 5), "c": (1, 21, 112, 112, 15.0, 50.0, 6)}
@@ -198,13 +229,18 @@ def bilateral_golden():
 
 if __name__ == "__main__":
     assert loader.available(), "reference tree not found"
-    which = sys.argv[1:] or ["attention", "pamr", "bilateral", "train64", "train64g2", "train448", "vitl64", "infer448", "infer_ms"]
+    which = sys.argv[1:] or ["attention", "pamr", "pamr448", "bilateral", "densecrf", "train64", "train64g2", "train448", "train448g2", "vitl64",
+                             "infer448", "infer448g2", "infer_ms"]
     if "attention" in which: attention_golden()
     if "pamr" in which: pamr_golden()
+    if "pamr448" in which: pamr_448_golden()
     if "bilateral" in which: bilateral_golden()
+    if "densecrf" in which: densecrf_golden()
     if "train64" in which: train_golden("train_vitb_64.npz", "vitb", 64, 2, 20, 100.0)
     if "train64g2" in which: train_golden("train_vitb_64_g2.npz", "vitb", 64, 2, 20, 100.0, qkv_gain=2.0)
     if "train448" in which: train_golden("train_vitb_448.npz", "vitb", 448, 1, 20, 100.0)
+    if "train448g2" in which: train_golden("train_vitb_448_g2.npz", "vitb", 448, 2, 20, 100.0, qkv_gain=2.0)
     if "vitl64" in which: train_golden("train_vitl_96.npz", "vitl", 96, 1, 20, 100.0, depth_key=23, qkv_gain=2.5)
     if "infer448" in which: infer_golden("infer_vitb_448.npz", 448, 20, (3, 7, 14), (60, 80), 10, "grad")
+    if "infer448g2" in which: infer_golden("infer_vitb_448_g2.npz", 448, 20, (3, 7, 14), (60, 80), 10, "grad", qkv_gain=2.0)
     if "infer_ms" in which: infer_golden("infer_vitb_128_ms.npz", 128, 20, (2, 9), (40, 36), 9, "cam_grad_s", scales=(0.5, 1, 1.5))

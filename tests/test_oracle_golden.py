@@ -125,3 +125,33 @@ def test_bilateral_c_oracle_vs_compiled_reference_when_present():
     lhs = bo.oracle_bilateral(img, 2 * x + y, 15.0, 10.0)
     rhs = 2 * bo.oracle_bilateral(img, x, 15.0, 10.0) + bo.oracle_bilateral(img, y, 15.0, 10.0)
     assert rel_err(lhs, rhs) < 1e-5
+
+
+def test_densecrf_k81_oracle_matches_reference_filter_and_closed_form():
+    """configs[3] shape (K = 81 planes, 224x224 after rloss-scale 0.5): the C oracle is bit-exact with the compiled reference filter
+    on the golden's sub-sample, and the loss / gradient restatement reproduces the golden's numbers."""
+    import torch.nn.functional as F
+    g = load_golden("densecrf_81.npz")
+    N, K, S, scale, srgb, sxy, weight = g["cfg"]
+    N, K, S = int(N), int(K), int(S)
+    img = synth.smooth_rgb(N, S, S, seed=11)
+    seg = synth.probabilities(N, K, S, S, seed=11)
+    roi = (synth.smooth_rgb(N, S, S, seed=12)[:, 0] > 100.0).float()
+    img_s = F.interpolate(img, scale_factor=float(scale), recompute_scale_factor=True)
+    seg_s = F.interpolate(seg, scale_factor=float(scale), mode="bilinear", align_corners=False, recompute_scale_factor=True)
+    roi_s = F.interpolate(roi.unsqueeze(1), scale_factor=float(scale), recompute_scale_factor=True)
+    sp = (seg_s * roi_s).contiguous()
+    # 21 of the 81 planes (every 4th, the golden's sub-sample): the planes are filtered independently
+    AS = bo.oracle_bilateral(img_s.numpy(), sp[:, ::4].contiguous().numpy(), float(srgb), float(sxy) * float(scale))
+    assert np.array_equal(AS[:, :, ::5, ::5], g["AS_sub"])
+    loss, grad = orc.dense_crf_loss_from_filter(seg_s[:, ::4], roi_s, torch.from_numpy(AS), float(weight))
+    assert rel_err(t2n(grad[:, :, ::5, ::5]), g["grad_sub"]) < 1e-6
+
+
+def test_pamr_448_oracle_matches_reference():
+    g = load_golden("pamr_448.npz")
+    x = (synth.smooth_rgb(1, 448, 448, seed=4) - 120.0) / 58.0
+    mask = synth.probabilities(1, 21, 28, 28, seed=4)
+    out = orc.pamr(x, mask, 10, [1, 2, 4, 8, 12, 24])
+    assert rel_err(t2n(out[:, :, ::7, ::7]), g["out_sub"]) < TOL
+    assert rel_err(t2n(out.sum(dim=(2, 3))), g["out_sum"]) < 1e-4
