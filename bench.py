@@ -24,6 +24,16 @@ S, C, B_PER_GPU, ALPHA, LR = 448, 20, 8, 100.0, 0.01
 N_TOK, HEADS, HD, LAYERS = (S // 16) ** 2 + 1, 12, 64, 12
 METRIC, UNIT = "train_imgs_per_sec", "img/s"
 WORKLOAD = "train_acr.py VOC-shaped: ViT-B/16 448x448, two-view all-pairs consistency loss, B=8/GPU, bf16 operands"
+# BASELINE.json configs: [1] = voc448 (the headline), [3] = coco448crf, [4] = vitl512
+CONFIGS = {
+    "voc448": dict(backbone="vitb", S=448, C=20, B=8, heads=12, layers=12, dense_crf=None, workload=WORKLOAD),
+    "coco448crf": dict(backbone="vitb", S=448, C=80, B=8, heads=12, layers=12,
+                       dense_crf={"weight": 1e-7, "sigma_rgb": 15.0, "sigma_xy": 100.0, "scale": 0.5},
+                       workload="train_acr_coco.py COCO-shaped: ViT-B/16 448x448, 80 classes, two-view consistency loss + bilateral dense-CRF term "
+                                "(K=81 planes at 224x224, sigma_rgb 15, sigma_xy 100, rloss-scale 0.5, weight 1e-7), B=8/GPU, bf16 operands"),
+    "vitl512": dict(backbone="vitl", S=512, C=20, B=4, heads=16, layers=24, dense_crf=None,
+                    workload="stress: ViT-L/16 512x512 (1025 tokens), all-pairs consistency over all 24 blocks, B=4/GPU, bf16 operands"),
+}
 
 
 def peaks():
@@ -127,6 +137,80 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------
+def build_trainer(cfg, dev, precision, world):
+    import torch
+    from acr_wsss_b200 import ACR, Trainer
+    torch.manual_seed(0)
+    model = ACR(cfg["C"], cfg["backbone"], precision=precision).to(dev)
+    for n, p in model.named_parameters():   # parameters without gradient on the ACR path (SURVEY Q4)
+        if n.startswith(("pretrained.model.norm.", "pretrained.model.head.", "scratch.")) or n.endswith("bkg_token"):
+            p.requires_grad_(False)
+    # (Trainer broadcasts rank 0's weights to every rank before it builds its flat buffers)
+    return model, Trainer(model, lr=LR, max_step=10 ** 6, alpha=ALPHA, dense_crf=cfg["dense_crf"])
+
+
+def measure_other_config(name, dev, precision, world, rank, timed, steps=5):
+    """Device-resident step time of another BASELINE config with the same Trainer (inputs in HBM, N ranks, all-reduce included)."""
+    import gc
+    import torch
+    from acr_wsss_b200 import synth
+    cfg = CONFIGS[name]
+    model, trainer = build_trainer(cfg, dev, precision, world)
+    img = synth.images(cfg["B"], cfg["S"], seed=rank).to(dev)
+    lab = synth.labels(cfg["B"], cfg["C"], seed=rank).to(dev)
+    losses = [float(trainer.step(img, lab)) for _ in range(4)]
+    ms = timed(lambda: trainer.step(img, lab), steps)
+    out = {"workload": cfg["workload"], "value": cfg["B"] * world * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "per_gpu_batch": cfg["B"], "tokens": (cfg["S"] // 16) ** 2 + 1, "first_losses": [round(l, 4) for l in losses],
+           "replicas_in_sync_max_rel_diff": trainer.check_replicas_in_sync(), "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    del trainer, model
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def measure_refine(dev, pk):
+    """BASELINE north star (4): PAMR and the bilateral filter, each timed alone with CUDA events (L2 flushed between iterations)
+    against the measured HBM peak on ALGORITHMIC bytes."""
+    import torch
+    from acr_wsss_b200 import ops, synth, PAMR
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timeit(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / iters      # ms
+
+    res = {}
+    it, dil = 10, [1, 2, 4, 8, 12, 24]
+    for key, (B, Cm, Sz) in {"pamr_cfg3": (1, 21, 448), "pamr_batch8": (8, 21, 448)}.items():
+        x = ((synth.smooth_rgb(B, Sz, Sz, seed=4) - 120.0) / 58.0).to(dev)
+        mask = synth.probabilities(B, Cm, Sz // 16, Sz // 16, seed=4).to(dev)
+        pamr = PAMR(it, dil)
+        ms = timeit(lambda: pamr(x, mask))
+        D, HW = len(dil), Sz * Sz
+        alg = B * (HW * (3 * 4 + 8 * D * 4) + it * HW * (8 * D * 4 + 2 * Cm * 4))       # image + weight planes written once; per iteration: weights + mask in/out
+        res[key] = {"workload": f"PAMR B={B} C={Cm} {Sz}x{Sz}, {it} iterations, dilations {dil}", "ms": ms, "algorithmic_bytes": alg,
+                    "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg / ms / 1e6 / pk["hbm_gbs"]}}
+    for key, (N, K, Sz) in {"bilateral_cfg_k21": (8, 21, 224), "bilateral_cfg4_k81": (8, 81, 224)}.items():
+        img = synth.smooth_rgb(N, Sz, Sz, seed=0).to(dev)
+        ins = synth.probabilities(N, K, Sz, Sz, seed=0).to(dev)
+        ms = timeit(lambda: ops.bilateral_filter(img, ins, 15.0, 50.0))
+        alg = 2 * N * K * Sz * Sz * 4 + N * 3 * Sz * Sz * 4                                  # planes in + out, image in
+        res[key] = {"workload": f"bilateral filter N={N} K={K} {Sz}x{Sz}, sigma_rgb 15, sigma_xy 50", "ms": ms, "algorithmic_bytes": alg,
+                    "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg / ms / 1e6 / pk["hbm_gbs"]}}
+    del flush
+    return res
+
+
+# ---------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -147,16 +231,13 @@ def run_ours(args):
     if precision == "bf16" and not _lib.lib().acr_device_is_sm100():
         raise SystemExit("bench.py: bf16 fused path needs sm_100a")
 
-    torch.manual_seed(0)
-    model = ACR(C, "vitb", precision=precision).to(dev)
-    if world > 1:
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
-    for n, p in model.named_parameters():   # parameters without gradient on the ACR path (SURVEY Q4)
-        if n.startswith(("pretrained.model.norm.", "pretrained.model.head.", "scratch.")) or n.endswith("bkg_token"):
-            p.requires_grad_(False)
-    trainer = Trainer(model, lr=LR, max_step=10 ** 6, alpha=ALPHA)
-    B = args.batch
+    cfg = dict(CONFIGS[args.config])
+    if args.batch:
+        cfg["B"] = args.batch
+    S, C = cfg["S"], cfg["C"]
+    N_TOK, HEADS, LAYERS = (S // 16) ** 2 + 1, cfg["heads"], cfg["layers"]
+    model, trainer = build_trainer(cfg, dev, precision, world)
+    B = cfg["B"]
     img_h = synth.images(B, S, seed=rank).pin_memory()
     lab_h = synth.labels(B, C, seed=rank).pin_memory()
     img_d, lab_d = img_h.to(dev), lab_h.to(dev)
@@ -226,11 +307,14 @@ def run_ours(args):
             kern[kname] = {"ms": tot.value, "launches": cnt.value}
     L.acr_profile_enable(0)
     launches = prof["launches"] // args.steps * args.steps
+    in_sync = trainer.check_replicas_in_sync()        # every rank holds bit-identical weights after the all-reduced steps
+    if world > 1 and in_sync > 0.0:
+        raise SystemExit(f"bench.py: replicas diverged after the timed steps (max relative checksum difference {in_sync:.3e})")
 
     # secondary metric: CAM inference (BASELINE.json configs[0]): forward_cam + GETAM over 3 present classes + affinity
     # refinement, 2 flips, one 448x448 image at a time, images sharded per rank, no collective
     cam = None
-    if not args.no_cam:
+    if not args.no_cam and args.config == "voc448":
         from acr_wsss_b200 import infer_cam_image
         model.eval()
         model.set_capture_grad(True)
@@ -242,7 +326,15 @@ def run_ours(args):
         for _ in range(3):        # warm-up: cuBLAS heuristics for the batch-2 / batch-6 shapes, allocator, pinned staging buffer
             infer_cam_image(model, img1, lab1, (S, S), start_layer=10, getam_func="grad", cuda_graph=True)
         ms_cam = timed(lambda: infer_cam_image(model, img1, lab1, (S, S), start_layer=10, getam_func="grad", cuda_graph=True), n_img)
+        # algorithmic FLOPs per image: trunk forward on 2 flips (blocks < start_layer) + blocks >= start_layer forward and backward on
+        # 2 x 3 class copies; per block and image 2*N*(12 E^2) (Linear layers) + 4*N^2*E (attention), backward = 2x forward
+        E_, st_l, n_cls = 768, 10, 3
+        blk = 2.0 * N_TOK * 12 * E_ * E_ + 4.0 * N_TOK * N_TOK * E_
+        cam_flops = 2 * st_l * blk + 2 * n_cls * (LAYERS - st_l) * blk * 3.0
         cam = {"metric": "cam_infer_imgs_per_sec", "value": n_img * world / (ms_cam / 1e3), "unit": "img/s", "ms_per_image": ms_cam / n_img,
+               "roofline": {"bound": "tensor", "achieved": cam_flops / (ms_cam / n_img * 1e-3) / 1e12, "peak": peaks()["tflops_sustained"], "unit": "TFLOP/s",
+                            "frac": cam_flops / (ms_cam / n_img * 1e-3) / 1e12 / peaks()["tflops_sustained"], "algorithmic_flop_per_image": cam_flops,
+                            "note": "batch-2 / batch-6 GEMMs and ~270 launches per image: latency bound, replayed as a CUDA graph"},
                "workload": "infer_cam.py: ViT-B/16 448x448, 2 flips, 3 present classes, GETAM start_layer=10 + affinity refine, results copied to host"}
         # BASELINE.json configs[2]: multi-scale (0.5/1.0/1.5/2.0 + flip), affinity power t=2 (row-normalised), then PAMR on the CAMs
         from acr_wsss_b200 import PAMR
@@ -259,6 +351,18 @@ def run_ours(args):
         cam["multiscale"] = {"value": 4 * world / (ms_multi / 1e3), "unit": "img/s", "ms_per_image": ms_multi / 4,
                              "workload": "scales 0.5/1.0/1.5/2.0 x 2 flips, t=2 row-normalised affinity power, PAMR(10 it., 6 dilations) on the 20-class CAM"}
 
+    # the other BASELINE configs with the same Trainer, and the refinement kernels of north star (4): short secondary measurements
+    others, refine = None, None
+    if not args.no_extra and args.config == "voc448":
+        import gc
+        del trainer, model
+        gc.collect()
+        torch.cuda.empty_cache()
+        others = {name: measure_other_config(name, dev, precision, world, rank, timed) for name in ("coco448crf", "vitl512")}
+        if rank == 0:
+            refine = measure_refine(dev, peaks())
+        sync()
+        trainer = None
     if rank == 0:
         pk = peaks()
         imgs = B * world * args.steps
@@ -299,15 +403,16 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "tokens": N_TOK, "parallelism": f"dp{world}",
-                       "precision": precision, "cuda_graph": bool(trainer.graph), "l2": "inputs larger than L2: each step streams 2 x 237 MB attention stacks + gradients"},
+            "config": {"workload": cfg["workload"], "name": args.config, "global_batch": B * world, "per_gpu_batch": B, "tokens": N_TOK, "parallelism": f"dp{world}",
+                       "precision": precision, "cuda_graph": True, "l2": "inputs larger than L2: each step streams 2 x 237 MB attention stacks + gradients"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(img_h.numel() * 4 + lab_h.numel() * 4) * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps,
                     "api": "Trainer.step_prefetched(next_img, next_label): every timed step copies one pinned-host batch to the device "
                            "(the one the next step consumes, on a copy stream under this step's kernels) and reads float(loss) back"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cam_infer": cam,
+            "replicas_in_sync_max_rel_diff": in_sync, "other_configs": others, "refine": refine,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.config == "voc448":
             v, sec, cores = cpu_reference_step_time(2, 1)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": "2 timed steps (+1 warm-up) of batch 1 of the same workload, fp32 torch CPU (oracle port)"}
@@ -327,7 +432,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--config", default="voc448", choices=sorted(CONFIGS), help="BASELINE.json configs[1] (default) / [3] / [4]")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (other configs, PAMR / bilateral)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cam", action="store_true", help="skip the secondary CAM-inference measurement")
     ap.add_argument("--profile-range", action="store_true", help="wrap one extra step in cudaProfilerStart/Stop (for ncu)")
