@@ -23,24 +23,32 @@ __device__ __forceinline__ int flip_token(int t, int p) {
 
 // kGrad: 0 = loss only, 1 = dense fp32 gradients, 2 = sign codes (one byte per element: 0x00 zero, 0x3F plus, 0xBF minus,
 // i.e. the top byte of +-0.5f, so that a consumer decodes with one byte-permute: float(code << 24) * 2w).
-// One WARP per (b,l,i) row, kRowsPerCta rows per CTA, no block-level synchronisation; each lane keeps kUnroll
-// independent load pairs in flight.
-constexpr int kRowsPerCta = 8;
+// One WARP per (b,l,i) row at a time, kWarps warps per CTA walking kRowsPerWarp rows each; each lane keeps kUnroll
+// independent load pairs in flight.  The column permutation pi is the same for every row: it is tabulated once per CTA in
+// shared memory (the two integer divisions of flip_token per element made the kernel issue bound: 76 % of the issue slots
+// at 54 % of HBM peak, profiles/r01g_ncu_refine_kernels.txt).
+constexpr int kWarps = 8;
+constexpr int kRowsPerWarp = 4;
+constexpr int kRowsPerCta = kWarps * kRowsPerWarp;
 constexpr int kUnroll = 8;
 
 template <int kGrad>
-__global__ void __launch_bounds__(kRowsPerCta * 32)
+__global__ void __launch_bounds__(kWarps * 32)
 consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ a2, long long rows,
                         int N, int p, float w_cls, float w_aff,
                         float* __restrict__ g1, float* __restrict__ g2, long long g_ld,
                         unsigned char* __restrict__ c1, unsigned char* __restrict__ c2, long long c_ld,
                         float* __restrict__ partials) {
+  extern __shared__ unsigned short pi_tab[];      // pi(j), j < N
+  for (int j = threadIdx.x; j < N; j += blockDim.x) pi_tab[j] = (unsigned short)flip_token(j, p);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * kRowsPerCta + (threadIdx.x >> 5);      // (b*L + l)*N + i
+  for (int rw = 0; rw < kRowsPerWarp; ++rw) {
+  const long long row = (long long)blockIdx.x * kRowsPerCta + (long long)rw * kWarps + (threadIdx.x >> 5);      // (b*L + l)*N + i
   if (row >= rows) return;
   const int i = (int)(row % N);
   const long long img = row / N;               // b*L + l
-  const int pi_i = flip_token(i, p);
+  const int pi_i = pi_tab[i];
   const float* r1 = a1 + (img * N + i) * (long long)N;
   const float* r2 = a2 + (img * N + pi_i) * (long long)N;
   const float w = (i == 0) ? w_cls : w_aff;
@@ -57,7 +65,7 @@ consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ 
     for (int k = 0; k < kUnroll; ++k) {
       const int j = j0 + k * 32 + lane;
       if (j < N) {
-        pj[k] = flip_token(j, p);
+        pj[k] = pi_tab[j];
         v1[k] = __ldg(r1 + j);
         v2[k] = __ldg(r2 + pj[k]);
       }
@@ -86,8 +94,15 @@ consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ 
       }
     }
   }
+  if (kGrad == 2) {      // row padding [N, c_ld): consumers read whole 16-byte chunks of a row; keep them defined (= no gradient)
+    for (long long j = N + lane; j < c_ld; j += 32) {
+      b1[j] = 0;
+      b2[j] = 0;
+    }
+  }
   acc = acr::warp_sum(acc);
   if (lane == 0) partials[row] = acc;
+  }
 }
 
 // Folds the per-row partials: rows with i==0 feed cls_align, the rest aff_align.
@@ -148,6 +163,8 @@ extern "C" int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, i
   cudaStream_t st = (cudaStream_t)stream;
   const long long rows = (long long)B * L * N;
   ACR_REQUIRE(rows < (1ll << 31), ACR_E_INVAL, "acr_consistency_fwd_bwd: too many rows");
+  ACR_REQUIRE(N <= 16384, ACR_E_INVAL, "acr_consistency_fwd_bwd: N=%d too large (<= 16384)", N);
+  const size_t smem = (size_t)N * sizeof(unsigned short);
   const double cnt_cls = (double)B * L * (N - 1);
   const double cnt_aff = (double)B * L * (double)(N - 1) * (double)(N - 1);
   const float w_cls = (float)((double)alpha_cls / cnt_cls);
@@ -155,11 +172,11 @@ extern "C" int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, i
   float* partials = (float*)workspace;
   const unsigned grid = (unsigned)((rows + kRowsPerCta - 1) / kRowsPerCta);
   if (g1) {
-    consistency_rows_kernel<1><<<grid, kRowsPerCta * 32, 0, st>>>(attn1, attn2, rows, N, p, w_cls, w_aff, g1, g2, g_row_stride, nullptr, nullptr, 0, partials);
+    consistency_rows_kernel<1><<<grid, kWarps * 32, smem, st>>>(attn1, attn2, rows, N, p, w_cls, w_aff, g1, g2, g_row_stride, nullptr, nullptr, 0, partials);
   } else if (code1) {
-    consistency_rows_kernel<2><<<grid, kRowsPerCta * 32, 0, st>>>(attn1, attn2, rows, N, p, w_cls, w_aff, nullptr, nullptr, 0, code1, code2, code_row_stride, partials);
+    consistency_rows_kernel<2><<<grid, kWarps * 32, smem, st>>>(attn1, attn2, rows, N, p, w_cls, w_aff, nullptr, nullptr, 0, code1, code2, code_row_stride, partials);
   } else {
-    consistency_rows_kernel<0><<<grid, kRowsPerCta * 32, 0, st>>>(attn1, attn2, rows, N, p, w_cls, w_aff, nullptr, nullptr, 0, nullptr, nullptr, 0, partials);
+    consistency_rows_kernel<0><<<grid, kWarps * 32, smem, st>>>(attn1, attn2, rows, N, p, w_cls, w_aff, nullptr, nullptr, 0, nullptr, nullptr, 0, partials);
   }
   if (int e = acr::check_launch("consistency_rows_kernel")) return e;
   consistency_finish_kernel<<<1, 1024, 0, st>>>(partials, rows, N, 1.0 / cnt_cls, 1.0 / cnt_aff, loss2);

@@ -9,7 +9,7 @@
 // Neighbour order per dilation is row-major over the 3x3 window without its centre (pamr.py:24-33);
 // dilations are concatenated in list order (pamr.py:55); borders replicate (pamr.py:51).
 // Bandwidth-bound: algorithmic bytes = HW(4K + 32D) for step 2 and HW(32D + 8C) per iteration.
-#include "common.cuh"
+#include "attn_tc.cuh"      // tc:: mbarrier / TMA helpers, acr_attn::get_encode_fn
 #include <cstdlib>
 
 namespace {
@@ -20,13 +20,15 @@ struct Dil { int d[kMaxDil]; int n; };
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 __global__ void __launch_bounds__(256)
-pamr_upsample_kernel(const float* __restrict__ src, int planes, int h, int w, int H, int W, float* __restrict__ dst) {
+pamr_upsample_kernel(const float* __restrict__ src, int planes, int h, int w, int H, int W, int pad, float* __restrict__ dst) {
+  // dst: [planes, H + 2 pad, W + 2 pad]; the pad ring repeats the edge pixels (replicate padding for the TMA-fed iteration)
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)planes * H * W;
+  const long long total = (long long)planes * Hp * Wp;
   if (idx >= total) return;
-  const int x = (int)(idx % W);
-  const int y = (int)((idx / W) % H);
-  const long long pl = idx / ((long long)W * H);
+  const int x = clampi((int)(idx % Wp) - pad, 0, W - 1);
+  const int y = clampi((int)((idx / Wp) % Hp) - pad, 0, H - 1);
+  const long long pl = idx / ((long long)Wp * Hp);
   const float sy = (H > 1) ? (float)(h - 1) / (float)(H - 1) : 0.f;
   const float sx = (W > 1) ? (float)(w - 1) / (float)(W - 1) : 0.f;
   const float fy = sy * (float)y, fx = sx * (float)x;
@@ -300,6 +302,172 @@ pamr_iter_smem_kernel(const float* __restrict__ wgt, const float* __restrict__ m
   }
 }
 
+
+// TMA-fed variant of the shared-memory iteration (the shipped one when W % 4 == 0).
+// What bounded pamr_iter_smem_kernel (ncu: profiles/r01g_ncu_refine_kernels.txt) was not the tap loop but the FILL of its
+// 179 KB tile: LDG -> register -> STS of a 6.25x halo-amplified region, un-overlapped with one CTA per SM.  Here the mask tile
+// arrives by cp.async.bulk.tensor (3-D box: 80 x 80 pixels x kPamrCh channels, out-of-image cells zero-filled) into a
+// two-stage ring, so the fill of channel chunk k+1 runs under the taps of chunk k and no thread touches the halo; only the
+// CTAs on the image border patch the zero-filled cells with the replicated edge values (pamr.py:51 pads with 'replicate').
+// Same tap order as the scalar kernel (bit-identical sums).  Bound: one warp-wide LDS per clock per SM.
+constexpr int kPamrCh = 3;                                         // channels per stage: 3 x 80 x 80 x 4 B = 76.8 KB
+constexpr int kPamrStage = kPamrCh * kPamrTS * kPamrTS;            // floats per stage
+// The dilation list every caller of the reference uses (pamr.py default of the upstream PAMR, BASELINE configs[2]) as
+// compile-time constants: every tap address becomes an immediate offset from ONE register.  With run-time dilations the tap
+// loop carried ~8 integer instructions per tap next to its 6 LDS + 6 FFMA and the kernel was issue bound (ncu r02a: 61 % of
+// the issue slots, ALU pipe 39 %, shared-memory pipe 45 %).
+__host__ __device__ constexpr int std_dil(int i) { return i == 0 ? 1 : i == 1 ? 2 : i == 2 ? 4 : i == 3 ? 8 : i == 4 ? 12 : 24; }
+
+// taps of NCH channels of one stage for this thread's two pixels
+template <int ND, int NCH, bool STD>
+__device__ __forceinline__ void pamr_taps(const float* __restrict__ t, int base, const Dil& dil, const float (&w0)[8 * ND], const float (&w1)[8 * ND],
+                                          float (&a0)[kPamrCh], float (&a1)[kPamrCh]) {
+  constexpr int TS = kPamrTS, per = TS * TS;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
+#pragma unroll
+  for (int di = 0; di < ND; ++di) {
+    const int d = STD ? std_dil(di) : dil.d[di];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      if (tp == 4) continue;
+      const int n = di * 8 + (tp < 4 ? tp : tp - 1);
+      const int off = base + (tp / 3 - 1) * d * TS + (tp % 3 - 1) * d;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        a0[c] = fmaf(w0[n], t[c * per + off], a0[c]);
+        a1[c] = fmaf(w1[n], t[c * per + off + 16 * TS], a1[c]);
+      }
+    }
+  }
+}
+
+// One CTA per (tile, channel group).  The SOURCE mask lives in a buffer padded by kPamrHalo pixels on every side whose ring
+// repeats the edge pixels (written by the up-sampling kernel / by pamr_pad_kernel after every iteration), so no TMA box ever
+// leaves the tensor and no thread patches halos in shared memory (patching the zero-filled cells of border tiles in shared
+// memory cost 23 us of an 69 us iteration at cfg3: it doubles the time of the CTAs every wave waits for).
+// dst_pad = 0: the last iteration writes the caller's unpadded output.
+// (A persistent variant -- one CTA per SM walking over the work items with the TMA ring running across items -- was 40 %
+// SLOWER: the per-item state pushed the 96 weight registers into local memory, profiles/r02_ncu_pamr_persistent.txt.)
+template <int ND, int CG, bool STD>
+__global__ void __launch_bounds__(512, 1)
+pamr_iter_tma_kernel(const __grid_constant__ CUtensorMap tmap_mask, const float* __restrict__ wgt, float* __restrict__ mout,
+                     int C, int H, int W, Dil dil, int groups, int dst_pad) {
+  extern __shared__ __align__(128) float tile[];                  // [2 stages][kPamrCh][TS][TS], then the two mbarriers
+  constexpr int TS = kPamrTS, R = kPamrHalo;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tile + 2 * kPamrStage);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 16 threads, two rows per thread (ty, ty + 16)
+  const int x0 = blockIdx.x * kPamrTile, y0 = blockIdx.y * kPamrTile;
+  const int b = blockIdx.z / groups, g = blockIdx.z % groups;
+  const int c0 = g * CG, cend = min(C, c0 + CG);
+  const int nchunks = (cend - c0 + kPamrCh - 1) / kPamrCh;
+  const long long HW = (long long)H * W;
+  auto issue = [&](int k) {                                        // one thread: chunk k -> stage k & 1
+    const int st = k & 1;
+    tc::mbar_arrive_expect_tx(&full[st], kPamrStage * sizeof(float));
+    // padded coordinates: image pixel (x, y) sits at (x + R, y + R), so the box of tile (x0, y0) starts at (x0, y0)
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     tc::smem_u32(tile + st * kPamrStage)),
+                 "l"(reinterpret_cast<uint64_t>(&tmap_mask)), "r"(tc::smem_u32(&full[st])), "r"(x0), "r"(y0), "r"(b * C + c0 + k * kPamrCh)
+                 : "memory");
+  };
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmap_mask);
+    tc::mbar_init(&full[0], 1);
+    tc::mbar_init(&full[1], 1);
+    tc::fence_barrier_init();
+    issue(0);
+    if (nchunks > 1) issue(1);
+  }
+  const int px = x0 + tx, py0 = y0 + ty, py1 = y0 + ty + 16;
+  const bool ok0 = px < W && py0 < H, ok1 = px < W && py1 < H;
+  float w0[8 * ND], w1[8 * ND];                                    // the 8*ND weights of this thread's two pixels, for all channels
+  {
+    // one running pointer per pixel (a 64-bit address rebuilt per plane cost ~10 integer instructions per weight)
+    const float* p0 = wgt + (long long)b * (8 * ND) * HW + (long long)min(py0, H - 1) * W + min(px, W - 1);
+    const float* p1 = wgt + (long long)b * (8 * ND) * HW + (long long)min(py1, H - 1) * W + min(px, W - 1);
+#pragma unroll
+    for (int n = 0; n < 8 * ND; ++n) {
+      w0[n] = __ldg(p0);
+      w1[n] = __ldg(p1);
+      p0 += HW;
+      p1 += HW;
+    }
+  }
+  __syncthreads();                                                 // barrier initialisation visible to every waiter
+  const int base = (ty + R) * TS + tx + R;
+  const int Wd = W + 2 * dst_pad;
+  const long long HWd = (long long)(H + 2 * dst_pad) * Wd;
+  for (int k = 0; k < nchunks; ++k) {
+    const int st = k & 1;
+    const float* t = tile + st * kPamrStage;
+    tc::mbar_wait(&full[st], (k >> 1) & 1);
+    float a0[kPamrCh], a1[kPamrCh];
+    const int nch = min(kPamrCh, cend - (c0 + k * kPamrCh));       // the last chunk of a group may hold fewer channels
+    if (nch == kPamrCh) pamr_taps<ND, kPamrCh, STD>(t, base, dil, w0, w1, a0, a1);
+    else if (nch == 2) pamr_taps<ND, 2, STD>(t, base, dil, w0, w1, a0, a1);
+    else pamr_taps<ND, 1, STD>(t, base, dil, w0, w1, a0, a1);
+    __syncthreads();                                               // every thread is done with stage st
+    if (threadIdx.x == 0 && k + 2 < nchunks) {
+      tc::fence_proxy_async_smem();                                // generic-proxy reads of the stage before the async-proxy refill
+      issue(k + 2);
+    }
+    float* op = mout + ((long long)b * C + c0 + k * kPamrCh) * HWd;
+    op += (long long)dst_pad * Wd + dst_pad + px;                  // interior of a padded destination; pamr_pad_kernel fills its ring
+#pragma unroll
+    for (int c = 0; c < kPamrCh; ++c) {
+      if (c < nch) {
+        if (ok0) op[c * HWd + (long long)py0 * Wd] = a0[c];
+        if (ok1) op[c * HWd + (long long)py1 * Wd] = a1[c];
+      }
+    }
+  }
+}
+
+// Ring of a padded mask buffer [planes, H + 2R, W + 2R]: every cell outside the image repeats the nearest image pixel
+// (pamr.py:51 pads with 'replicate').  One thread per ring cell: 4 (H + W + 2R) R cells per plane.
+__global__ void __launch_bounds__(256)
+pamr_pad_kernel(float* __restrict__ buf, int planes, int H, int W) {
+  constexpr int R = kPamrHalo;
+  const int Wp = W + 2 * R, Hp = H + 2 * R;
+  const int top = R * Wp;                                          // cells of the R rows above (and below) the image
+  const int ring = 2 * top + 2 * R * H;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)planes * ring) return;
+  const int e = (int)(idx % ring);
+  float* plane = buf + (idx / ring) * (long long)Hp * Wp;
+  int yp, xp;
+  if (e < top) { yp = e / Wp; xp = e - yp * Wp; }
+  else if (e < 2 * top) { const int q = e - top; yp = R + H + q / Wp; xp = q % Wp; }
+  else { const int q = e - 2 * top; yp = R + q / (2 * R); const int c = q % (2 * R); xp = c < R ? c : W + c; }
+  const int ys = clampi(yp, R, R + H - 1), xs = clampi(xp, R, R + W - 1);
+  plane[(long long)yp * Wp + xp] = plane[(long long)ys * Wp + xs];
+}
+
+int make_mask_tmap(CUtensorMap* m, const float* base, int planes, int H, int W) {      // H, W: PADDED extents
+  acr_attn::EncodeTiledFn fn = acr_attn::get_encode_fn();
+  ACR_REQUIRE(fn != nullptr, ACR_E_NOSM100, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kPamrTS, (cuuint32_t)kPamrTS, (cuuint32_t)kPamrCh};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ACR_REQUIRE(r == CUDA_SUCCESS, ACR_E_INVAL, "cuTensorMapEncodeTiled(mask) failed (%d)", (int)r);
+  return 0;
+}
+
+template <int ND, int CG, bool STD>
+int launch_iter_tma(const CUtensorMap& tmap, const float* wgt, float* dst, int dst_pad, int B, int C, int H, int W, const Dil& dil, cudaStream_t st) {
+  const int groups = (C + CG - 1) / CG;
+  const size_t smem = (size_t)2 * kPamrStage * sizeof(float) + 64;
+  static bool attr_set[64] = {false};
+  if (int e = acr_attn::set_max_smem(pamr_iter_tma_kernel<ND, CG, STD>, smem, attr_set)) return e;
+  dim3 grid((W + kPamrTile - 1) / kPamrTile, (H + kPamrTile - 1) / kPamrTile, B * groups);
+  pamr_iter_tma_kernel<ND, CG, STD><<<grid, 512, smem, st>>>(tmap, wgt, dst, C, H, W, dil, groups, dst_pad);
+  return acr::check_launch("pamr_iter_tma_kernel");
+}
+
 template <int ND, int CG>
 int launch_iter_smem(const float* wgt, const float* cur, float* dst, int B, int C, int H, int W, const Dil& dil, cudaStream_t st) {
   const int groups = (C + CG - 1) / CG;
@@ -330,18 +498,61 @@ int launch_iter(const float* wgt, const float* cur, float* dst, int B, int C, in
   return acr::check_launch("pamr_iter_kernel");
 }
 
-int pamr_iterate(const float* wgt, float* ping, float* pong, float* out, int B, int C, int H, int W, const Dil& dil, int num_iter,
-                 cudaStream_t st) {
+bool pamr_tma_path(const Dil& dil, int W) {
   static int cfg = -1;
-  if (cfg < 0) { const char* e = getenv("ACR_PAMR_CFG"); cfg = e ? atoi(e) : 100; }   // 100 = shared-memory tiles; 7 = best scalar config
+  if (cfg < 0) { const char* e = getenv("ACR_PAMR_CFG"); cfg = e ? atoi(e) : 100; }
+  int R = 0;
+  for (int i = 0; i < dil.n; ++i) R = dil.d[i] > R ? dil.d[i] : R;
+  // TMA-fed tiles need 16-byte aligned rows (W % 4 == 0), dilations within the compile-time halo and an sm_100 device
+  return cfg == 100 && dil.n <= 6 && R <= kPamrHalo && (W % 4 == 0) && acr_device_is_sm100();
+}
+
+// ping / pong: padded by kPamrHalo on every side when `padded` (the TMA path), plain [B*C, H, W] otherwise
+int pamr_iterate(const float* wgt, float* ping, float* pong, float* out, int B, int C, int H, int W, const Dil& dil, int num_iter,
+                 bool padded, cudaStream_t st) {
+  static int cfg = -1;
+  if (cfg < 0) { const char* e = getenv("ACR_PAMR_CFG"); cfg = e ? atoi(e) : 100; }   // 100 = TMA-fed tiles; 101 = register-staged tiles; 7 = best scalar config
   int R = 0;
   for (int i = 0; i < dil.n; ++i) R = dil.d[i] > R ? dil.d[i] : R;
   constexpr int kCG = 7;
-  const bool smem_ok = cfg == 100 && dil.n <= 6 && R <= kPamrHalo && (long long)B * ((C + kCG - 1) / kCG) <= 65535;
+  const bool smem_ok = (cfg == 100 || cfg == 101) && dil.n <= 6 && R <= kPamrHalo && (long long)B * ((C + kCG - 1) / kCG) <= 65535;
+  const bool tma_ok = padded;
+  CUtensorMap tm_ping, tm_pong;
+  if (tma_ok) {
+    if (int e = make_mask_tmap(&tm_ping, ping, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo)) return e;
+    if (int e = make_mask_tmap(&tm_pong, pong, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo)) return e;
+  }
   const float* cur = ping;
   for (int it = 0; it < num_iter; ++it) {
-    float* dst = (it == num_iter - 1) ? out : ((cur == ping) ? pong : ping);
+    const bool last = it == num_iter - 1;
+    float* dst = last ? out : ((cur == ping) ? pong : ping);
     int e = 0;
+    if (tma_ok) {
+      const CUtensorMap& tm = (cur == ping) ? tm_ping : tm_pong;
+      const int dp = last ? 0 : kPamrHalo;
+      bool std6 = dil.n == 6;
+      for (int i = 0; i < 6 && std6; ++i) std6 = dil.d[i] == std_dil(i);
+      if (std6) {
+        e = launch_iter_tma<6, kCG, true>(tm, wgt, dst, dp, B, C, H, W, dil, st);
+      } else {
+        switch (dil.n) {
+          case 1: e = launch_iter_tma<1, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 2: e = launch_iter_tma<2, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 3: e = launch_iter_tma<3, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 4: e = launch_iter_tma<4, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 5: e = launch_iter_tma<5, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          default: e = launch_iter_tma<6, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+        }
+      }
+      if (e) return e;
+      if (!last) {
+        const long long cells = (long long)B * C * (2 * kPamrHalo * (W + 2 * kPamrHalo) + 2 * kPamrHalo * H);
+        pamr_pad_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(dst, B * C, H, W);
+        if (int e2 = acr::check_launch("pamr_pad_kernel")) return e2;
+      }
+      cur = dst;
+      continue;
+    }
     if (smem_ok) {
       switch (dil.n) {
         case 1: e = launch_iter_smem<1, kCG>(wgt, cur, dst, B, C, H, W, dil, st); break;
@@ -377,7 +588,8 @@ extern "C" size_t acr_pamr_workspace(int B, int K, int C, int H, int W, int nd) 
   if (B <= 0 || K <= 0 || C <= 0 || H <= 0 || W <= 0 || nd <= 0) return 0;
   const size_t hw = (size_t)H * W;
   // +256: the quad loads of the fast path may touch up to 12 bytes past the last mask row
-  return acr::align_up((size_t)B * 8 * nd * hw * sizeof(float), 256) + 2 * acr::align_up((size_t)B * C * hw * sizeof(float), 256) + 256;
+  const size_t hwp = (size_t)(H + 2 * kPamrHalo) * (W + 2 * kPamrHalo);        // ping / pong carry a replicate-padded ring on the TMA path
+  return acr::align_up((size_t)B * 8 * nd * hw * sizeof(float), 256) + 2 * acr::align_up((size_t)B * C * hwp * sizeof(float), 256) + 256;
 }
 
 extern "C" int acr_pamr_fwd(const float* x, const float* mask, int B, int K, int C, int H, int W, int mh, int mw,
@@ -401,14 +613,17 @@ extern "C" int acr_pamr_fwd(const float* x, const float* mask, int B, int K, int
   char* ws = (char*)workspace;
   float* wgt = (float*)ws;
   ws += acr::align_up((size_t)B * 8 * nd * hw * sizeof(float), 256);
+  const size_t hwp = (size_t)(H + 2 * kPamrHalo) * (W + 2 * kPamrHalo);
   float* ping = (float*)ws;
-  ws += acr::align_up((size_t)B * C * hw * sizeof(float), 256);
+  ws += acr::align_up((size_t)B * C * hwp * sizeof(float), 256);
   float* pong = (float*)ws;
 
+  const bool padded = num_iter > 0 && pamr_tma_path(dil, W);
   float* first = (num_iter == 0) ? out : ping;
   {
-    const long long total = (long long)B * C * hw;
-    pamr_upsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mask, B * C, mh, mw, H, W, first);
+    const int pad = padded ? kPamrHalo : 0;
+    const long long total = (long long)B * C * (H + 2 * pad) * (W + 2 * pad);
+    pamr_upsample_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mask, B * C, mh, mw, H, W, pad, first);
     if (int e = acr::check_launch("pamr_upsample_kernel")) return e;
   }
   if (num_iter == 0) return 0;
@@ -426,12 +641,12 @@ extern "C" int acr_pamr_fwd(const float* x, const float* mask, int B, int K, int
       default: e = launch_affinity_reg<8>(x, B, K, H, W, dil, wgt, st); break;
     }
     if (e) return e;
-    return pamr_iterate(wgt, ping, pong, out, B, C, H, W, dil, num_iter, st);
+    return pamr_iterate(wgt, ping, pong, out, B, C, H, W, dil, num_iter, padded, st);
   }
   {
     dim3 grid((W + 255) / 256, H, B);
     pamr_affinity_kernel<<<grid, 256, 0, st>>>(x, K, H, W, dil, wgt);
     if (int e = acr::check_launch("pamr_affinity_kernel")) return e;
   }
-  return pamr_iterate(wgt, ping, pong, out, B, C, H, W, dil, num_iter, st);
+  return pamr_iterate(wgt, ping, pong, out, B, C, H, W, dil, num_iter, false, st);
 }
