@@ -3,7 +3,7 @@
 Public surface (mirrors the reference's names for this path):
     ACR, Attention, VisionTransformer          (model.py    <- DPT/ACR.py, models/vision_transformer.py)
     acr_consistency_loss, acr_total_loss       (losses.py   <- train_acr.py:140-168)
-    affinity_refine, infer_cam_image           (cam.py      <- infer_cam.py:145-215)
+    affinity_refine, infer_cam_image/_batch    (cam.py      <- infer_cam.py:145-215)
     save_cam_dict, pseudo_label, label_iou     (cam.py      <- infer_cam.py:227-228, evaluation.py:28-67)
     PAMR                                       (pamr.py     <- pamr.py)
     bilateralfilter_batch                      (bilateralfilter.py <- wrapper/bilateralfilter)
@@ -13,7 +13,7 @@ All compute goes through libacr_b200.so (csrc/, C ABI in include/acr_b200.h); th
 from . import _lib, ops  # noqa: F401
 from .model import ACR, Attention, Block, VisionTransformer  # noqa: F401
 from .losses import acr_consistency_loss, acr_total_loss, dense_crf_loss  # noqa: F401
-from .cam import affinity_refine, infer_cam_image, normalize_cam, pseudo_label, save_cam_dict, load_cam_dict, label_iou  # noqa: F401
+from .cam import affinity_refine, infer_cam_image, infer_cam_batch, normalize_cam, pseudo_label, save_cam_dict, load_cam_dict, label_iou  # noqa: F401
 from .pamr import PAMR  # noqa: F401
 from .train import Trainer, PolyOptimizer  # noqa: F401
 from .parallel import GradBuckets, shard_indices  # noqa: F401

@@ -91,15 +91,28 @@ def _lowres_pass(model, both, present_idx, n_present, start_layer, getam_func, a
     return patch_cam.detach(), cams
 
 
+def _lowres_pass_batch(model, both, idx, n, start_layer, getam_func, aff, t, normalize):
+    """_lowres_pass for M images at once.  both [2M,3,h,w] (flipped views first), idx [2M*n] class of every (view, image, copy);
+    n copies per image (images with fewer present classes carry dummy copies).  Returns (patch_cam [2M,Np,C], cams [2M,Np,n])."""
+    cls_rep, _, attn, patch_cam = model.forward_cam_batched(both, n, start_layer)
+    model.backward_for_getam_batched(cls_rep, idx)
+    cams = model.getam_batch(start_layer=start_layer, func=getam_func)           # [2M*n, Np]
+    cams = cams.view(both.shape[0], n, -1).transpose(1, 2).contiguous()           # [2M, Np, n]
+    if aff:
+        cams = affinity_refine(attn.detach(), cams, t=t, normalize=normalize)
+    return patch_cam.detach(), cams
+
+
 class _LowresGraph:
     """CUDA graph of _lowres_pass for one (model, input shape, number of present classes, options) key: the pass is ~270
     launches of small kernels at batch 2 and is CPU-launch bound when run eagerly (8.4 ms per image, 2.8 ms of GPU time)."""
 
-    def __init__(self, model, shape, n_present, args):
+    def __init__(self, model, shape, n_present, args, batch=False):
         dev = next(model.parameters()).device
         self.both = torch.empty(shape, device=dev)
-        self.idx = torch.zeros(n_present, device=dev, dtype=torch.long)
+        self.idx = torch.zeros(shape[0] * n_present if batch else n_present, device=dev, dtype=torch.long)
         self.model, self.n, self.args = model, n_present, args
+        self.fn = _lowres_pass_batch if batch else _lowres_pass
         self.graph = None
         self.calls = 0
         self.stream = torch.cuda.Stream(device=dev)
@@ -112,14 +125,14 @@ class _LowresGraph:
         if self.graph is None and self.calls <= 2:          # warm up eagerly on the capture stream (lazy inits, cuBLAS workspaces)
             self.stream.wait_stream(cur)
             with torch.cuda.stream(self.stream):
-                out = _lowres_pass(self.model, self.both, self.idx, self.n, *self.args)
+                out = self.fn(self.model, self.both, self.idx, self.n, *self.args)
             cur.wait_stream(self.stream)
             return out
         if self.graph is None:
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=self.stream):
-                self.out = _lowres_pass(self.model, self.both, self.idx, self.n, *self.args)
+                self.out = self.fn(self.model, self.both, self.idx, self.n, *self.args)
         self.graph.replay()
         return self.out
 
@@ -216,23 +229,73 @@ def infer_cam_image(model, img, label, out_size, scales=(1,), start_layer=9, get
     # only the present classes go to the host (what the reference keeps, infer_cam.py:217-228), through one pinned buffer
     if present:
         both = torch.stack([norm_cam.index_select(0, present_idx), patch_norm.index_select(0, present_idx)])     # [2,C',rows,cols]
-        host = _pinned(both.shape) if both.is_cuda else torch.empty(both.shape)
-        host.copy_(both, non_blocking=True)
-        if both.is_cuda:
-            torch.cuda.current_stream().synchronize()
-        host_np = host.numpy().copy()
+        host_np = _to_host(both)
     cam_dict = {ci: host_np[0, k] for k, ci in enumerate(present)}
     patch_cam_dict = {ci: host_np[1, k] for k, ci in enumerate(present)}
     return cam_dict, patch_cam_dict, norm_cam
 
 
-_PINNED = {}
+def _to_host(t):
+    """Device tensor -> numpy array through a pinned buffer of torch's caching host allocator.  The array is a VIEW of that
+    buffer and keeps it alive (no second host-side copy: np.copy of the 4.8 MB per image cost 1 ms, a third of the whole call);
+    the allocator recycles the block once the caller drops the arrays."""
+    if not t.is_cuda:
+        return t.detach().cpu().numpy()
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
 
 
-def _pinned(shape):
-    key = tuple(shape)
-    if key not in _PINNED:
-        if len(_PINNED) > 8:
-            _PINNED.clear()
-        _PINNED[key] = torch.empty(key, dtype=torch.float32, pin_memory=True)
-    return _PINNED[key]
+def infer_cam_batch(model, imgs, labels, out_size, scales=(1,), start_layer=9, getam_func="cam_grad_s", aff=True, t=1,
+                    normalize=False, cuda_graph=False):
+    """infer_cam_image for M images of one shape in ONE pass per scale (the reference loops over images, infer_cam.py:122-215):
+    both flips of all images go through the trunk as a batch of 2M, the blocks >= start_layer run on n copies per image
+    (n = the largest number of present classes in the batch; images with fewer classes carry dummy copies that are dropped),
+    one backward, one batched GETAM, one batched affinity contraction.  imgs [M,3,h,w], labels [M,C], out_size (rows, cols)
+    common to the batch.  Returns a list of (cam_dict, patch_cam_dict) per image, same contents as infer_cam_image."""
+    M, C = labels.shape
+    assert imgs.shape[0] == M
+    rows, cols = out_size
+    nblocks = len(model.pretrained.model.blocks)
+    assert 0 < start_layer < nblocks, "the batched path stops the backward at block start_layer"
+    lab_host = labels.tolist()                                   # one device->host read
+    present = [[ci for ci in range(C) if lab_host[m][ci] > 1e-5] for m in range(M)]
+    n = max(1, max(len(p) for p in present))
+    padded = [p + [p[0] if p else 0] * (n - len(p)) for p in present]            # dummy copies repeat a class; dropped below
+    idx_m = torch.tensor(padded, device=imgs.device, dtype=torch.long)           # [M,n]
+    idx = idx_m.repeat(2, 1).reshape(-1)                                          # sample (v, m), copy k -> class padded[m][k]
+    b, c, h, w = imgs.shape
+    sum_cam = torch.zeros(M, n, rows, cols, device=imgs.device)
+    sum_patch = torch.zeros(M, n, rows, cols, device=imgs.device)
+    lab_sel = labels.gather(1, idx_m).view(M, n, 1, 1)
+    for scale in scales:
+        inp = F.interpolate(imgs, size=(int(h * scale), int(w * scale)), mode="bilinear", align_corners=False)
+        ph, pw = int((h * scale) // 16), int((w * scale) // 16)
+        both = torch.cat([inp.flip(-1), inp], dim=0)             # hflip = 1 (flipped) first, then 2, as infer_cam.py:148-151
+        args = (start_layer, getam_func, aff, t, normalize)
+        if cuda_graph and imgs.is_cuda:
+            cache = model.__dict__.setdefault("_cam_graphs", {})
+            key = ("batch", tuple(both.shape), n) + args
+            if key not in cache:
+                if len(cache) >= 8:
+                    cache.clear()
+                cache[key] = _LowresGraph(model, tuple(both.shape), n, args, batch=True)
+            patch_cam, cams = cache[key].run(both, idx)
+        else:
+            patch_cam, cams = _lowres_pass_batch(model, both, idx, n, *args)
+        # patch CAM of the (padded) present classes, infer_cam.py:153-158: [2M,Np,C] -> [2,M,n,rows,cols]
+        pc = patch_cam.permute(0, 2, 1).reshape(2, M, C, ph, pw).gather(2, idx_m.view(1, M, n, 1, 1).expand(2, M, n, ph, pw))
+        pc = F.interpolate(pc.reshape(2 * M, n, ph, pw), [rows, cols], mode="bilinear", align_corners=False).view(2, M, n, rows, cols)
+        pc = pc * lab_sel
+        sum_patch += pc[0].flip(-1) + pc[1]
+        # GETAM maps, infer_cam.py:185-187
+        cm = cams.transpose(1, 2).reshape(2 * M * n, 1, ph, pw)
+        cm = F.interpolate(cm, (rows, cols), mode="bilinear", align_corners=True).view(2, M, n, rows, cols)
+        sum_cam += cm[0].flip(-1) + cm[1]
+    norm = torch.stack([normalize_cam(sum_cam[m], 1e-6) for m in range(M)])      # per-class min-max over the image, :202-209
+    pnorm = torch.stack([normalize_cam(sum_patch[m], 1e-5) for m in range(M)])
+    both_out = torch.stack([norm, pnorm])                                         # [2,M,n,rows,cols]
+    host_np = _to_host(both_out)
+    return [({ci: host_np[0, m, k] for k, ci in enumerate(present[m])}, {ci: host_np[1, m, k] for k, ci in enumerate(present[m])})
+            for m in range(M)]

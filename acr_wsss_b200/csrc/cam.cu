@@ -5,18 +5,21 @@
 
 namespace {
 
-// One thread per token j.  p/g: [L,H,N].  See acr_b200.h for `func`.
+// One thread per token j, blockIdx.y = sample.  p/g: [L,S,H,N] (S = 1 for the single-image entry).  See acr_b200.h for `func`.
 __global__ void __launch_bounds__(256)
-getam_row0_kernel(const float* __restrict__ p, const float* __restrict__ g, int L, int H, int N,
+getam_row0_kernel(const float* __restrict__ p, const float* __restrict__ g, int S, int L, int H, int N,
                   int start_layer, int func, int skip, float* __restrict__ cam_out, float* __restrict__ cam_rows) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int s = blockIdx.y;
   if (j >= N) return;
+  cam_out += (long long)s * (N - skip);
+  if (cam_rows) cam_rows += (long long)s * L * N;
   const float invH = 1.f / (float)H;
   float total = 0.f;
   for (int l = 0; l < L; ++l) {
     float pos_g = 0.f, pos_gp = 0.f;
     for (int h = 0; h < H; ++h) {
-      const long long o = ((long long)l * H + h) * N + j;
+      const long long o = (((long long)l * S + s) * H + h) * N + j;
       const float gv = g[o];
       pos_g += fmaxf(gv, 0.f);
       if (func >= 2) pos_gp += fmaxf(gv * p[o], 0.f);
@@ -68,7 +71,18 @@ extern "C" int acr_getam_row0(const float* p_row0, const float* g_row0, int L, i
   ACR_REQUIRE(start_layer >= 0 && start_layer < L, ACR_E_INVAL, "acr_getam_row0: start_layer %d outside [0,%d)", start_layer, L);
   ACR_REQUIRE(func >= 0 && func <= 3, ACR_E_INVAL, "acr_getam_row0: unknown func %d", func);
   ACR_REQUIRE(skip >= 1 && skip < N, ACR_E_INVAL, "acr_getam_row0: bad skip");
-  getam_row0_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p_row0, g_row0, L, H, N, start_layer, func, skip, cam_out, cam_rows);
+  getam_row0_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p_row0, g_row0, 1, L, H, N, start_layer, func, skip, cam_out, cam_rows);
+  return acr::check_launch("getam_row0_kernel");
+}
+
+extern "C" int acr_getam_row0_batch(const float* p_row0, const float* g_row0, int S, int L, int H, int N,
+                                    int start_layer, int func, int skip, float* cam_out, void* stream) {
+  ACR_REQUIRE(p_row0 && g_row0 && cam_out, ACR_E_INVAL, "acr_getam_row0_batch: null pointer");
+  ACR_REQUIRE(S > 0 && S <= 65535 && L > 0 && H > 0 && N > 1, ACR_E_INVAL, "acr_getam_row0_batch: bad shape");
+  ACR_REQUIRE(start_layer >= 0 && start_layer < L, ACR_E_INVAL, "acr_getam_row0_batch: start_layer %d outside [0,%d)", start_layer, L);
+  ACR_REQUIRE(func >= 0 && func <= 3, ACR_E_INVAL, "acr_getam_row0_batch: unknown func %d", func);
+  ACR_REQUIRE(skip >= 1 && skip < N, ACR_E_INVAL, "acr_getam_row0_batch: bad skip");
+  getam_row0_kernel<<<dim3((N + 255) / 256, S), 256, 0, (cudaStream_t)stream>>>(p_row0, g_row0, S, L, H, N, start_layer, func, skip, cam_out, nullptr);
   return acr::check_launch("getam_row0_kernel");
 }
 

@@ -456,6 +456,16 @@ class ACR(nn.Module):
             cam_list = [rows[l].view(1, 1, -1) for l in range(len(used))]
         return cls_cam, attn_list, cam_list
 
+    def getam_batch(self, start_layer=0, func="grad"):
+        """getam() for EVERY sample of the last (batched) forward / backward at once: [S, N-skip] (row s = getam(s, ...)[0][0]);
+        one kernel launch instead of S (batched CAM inference)."""
+        blocks = self.pretrained.model.blocks
+        skip = 2 if self.cur_backbone == "deitb16_distil_384" else 1
+        used = blocks[start_layer:]
+        p0 = torch.stack([blk.attn.get_attn_row0() for blk in used])               # [L',S,H,N]
+        g0 = torch.stack([blk.attn.get_attn_gradients_row0() for blk in used])
+        return ops.getam_row0_batch(p0, g0, 0, func, skip)
+
     def backward_for_getam(self, logit, start_layer=0):
         """Gradient pass that feeds getam().  The reference calls logit.backward(retain_graph=True) through the whole
         model and all parameters (infer_cam.py:173-179); only dP of blocks >= start_layer is ever read, so this stops

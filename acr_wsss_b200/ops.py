@@ -669,6 +669,17 @@ def getam_row0(p_row0, g_row0, start_layer=0, func="grad", skip=1, want_rows=Fal
     return (cam, rows) if want_rows else cam
 
 
+def getam_row0_batch(p_row0, g_row0, start_layer=0, func="grad", skip=1):
+    """p_row0/g_row0 [L,S,H,N] (S samples stacked over the L used blocks) -> cls_cam [S,N-skip]."""
+    _need_cuda(p_row0, g_row0)
+    L, S, H, N = p_row0.shape
+    p_row0 = p_row0.contiguous().float()
+    g_row0 = g_row0.contiguous().float()
+    cam = torch.empty(S, N - skip, device=p_row0.device, dtype=torch.float32)
+    _call("acr_getam_row0_batch", 1, _p(p_row0), _p(g_row0), S, L, H, N, int(start_layer), _GETAM_FUNCS[func], int(skip), _p(cam), _stream())
+    return cam
+
+
 def affinity_sum(attn, normalize=False):
     """attn [B,L,N,N] -> A [B,N-1,N-1] = sum_l attn[:,l,1:,1:] (infer_cam.py:164-165)."""
     _need_cuda(attn)

@@ -336,6 +336,18 @@ def run_ours(args):
                             "frac": cam_flops / (ms_cam / n_img * 1e-3) / 1e12 / peaks()["tflops_sustained"], "algorithmic_flop_per_image": cam_flops,
                             "note": "batch-2 / batch-6 GEMMs and ~270 launches per image: latency bound, replayed as a CUDA graph"},
                "workload": "infer_cam.py: ViT-B/16 448x448, 2 flips, 3 present classes, GETAM start_layer=10 + affinity refine, results copied to host"}
+        # the same workload through infer_cam_batch: 8 images per trunk pass (one backward, batched GETAM / affinity contraction)
+        from acr_wsss_b200 import infer_cam_batch
+        MB = 8
+        imgb = torch.cat([synth.images(1, S, seed=200 + rank * MB + i) for i in range(MB)]).to(dev)
+        labb = synth.labels(1, C, present=(3, 7, 14)).to(dev).repeat(MB, 1)
+        for _ in range(3):
+            infer_cam_batch(model, imgb, labb, (S, S), start_layer=10, getam_func="grad", cuda_graph=True)
+        ms_b = timed(lambda: infer_cam_batch(model, imgb, labb, (S, S), start_layer=10, getam_func="grad", cuda_graph=True), 4)
+        cam["batched"] = {"value": 4 * MB * world / (ms_b / 1e3), "unit": "img/s", "ms_per_image": ms_b / (4 * MB), "images_per_pass": MB,
+                          "roofline": {"bound": "tensor", "achieved": cam_flops / (ms_b / (4 * MB) * 1e-3) / 1e12, "peak": peaks()["tflops_sustained"],
+                                       "unit": "TFLOP/s", "frac": cam_flops / (ms_b / (4 * MB) * 1e-3) / 1e12 / peaks()["tflops_sustained"]},
+                          "workload": "infer_cam_batch: 8 images of the cfg1 workload per pass (2 flips x 8 images x 3 class copies), results copied to host"}
         # BASELINE.json configs[2]: multi-scale (0.5/1.0/1.5/2.0 + flip), affinity power t=2 (row-normalised), then PAMR on the CAMs
         from acr_wsss_b200 import PAMR
         pamr = PAMR(10, [1, 2, 4, 8, 12, 24]).to(dev)

@@ -173,6 +173,11 @@ int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, int B, int L
 int acr_getam_row0(const float* p_row0, const float* g_row0, int L, int H, int N,
                    int start_layer, int func, int skip,
                    float* cam_out, float* cam_rows, void* stream);
+/* The same for S (image, flip, class) samples at once (batched CAM inference, infer_cam.py:167-184 looped over images):
+ * p_row0/g_row0 [L,S,H,N] (the per-block row-0 tensors of a batch of S samples stacked over the L used blocks),
+ * cam_out [S,N-skip]. */
+int acr_getam_row0_batch(const float* p_row0, const float* g_row0, int S, int L, int H, int N,
+                         int start_layer, int func, int skip, float* cam_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (a9) Affinity refinement.  Replaces infer_cam.py:164-165 (patch_aff = sum_l attn[:,l,1:,1:]) and

@@ -330,6 +330,29 @@ def test_infer_cam_fp32_multiscale_full_backward(dev):
     _infer_check(dev, "infer_vitb_128_ms.npz", "fp32", FP32_TOL, truncate=False)
 
 
+def test_infer_cam_batch_matches_per_image(dev):
+    """infer_cam_batch (M images per trunk pass, one backward, batched GETAM / affinity contraction) == infer_cam_image per image,
+    for images with different numbers of present classes (dummy copies), two scales, on both precisions; also as a CUDA graph."""
+    from acr_wsss_b200 import infer_cam_image, infer_cam_batch, synth
+    sets = [(3, 7, 14), (1,), (0, 5)]
+    # (t = 2 with a row-normalised affinity flattens the maps; the per-class min-max normalisation then amplifies fp32 rounding
+    # differences between batch sizes to ~3e-3, so the exact comparison runs with the reference's t = 1 / un-normalised A)
+    for prec, tol, t_, nrm in (("fp32", 1e-4, 1, False), ("fp32", 1e-2, 2, True), ("bf16", 2e-2, 1, False)):
+        m, _ = _build(dev, 20, "vitb", prec, 2.0)
+        m.eval()
+        imgs = torch.cat([synth.images(1, 128, seed=10 + i) for i in range(len(sets))]).to(dev)
+        labels = torch.cat([synth.labels(1, 20, present=p) for p in sets]).to(dev)
+        kw = dict(scales=(1.0, 0.5), start_layer=10, getam_func="cam_grad_s", t=t_, normalize=nrm)
+        for graph in (False, True, True, True):              # eager, then two warm-ups + capture/replay
+            res = infer_cam_batch(m, imgs, labels, (40, 56), cuda_graph=graph, **kw)
+            assert len(res) == len(sets)
+            for i, p in enumerate(sets):
+                a, pa, _ = infer_cam_image(m, imgs[i:i + 1], labels[i:i + 1], (40, 56), **kw)
+                assert sorted(res[i][0]) == sorted(p) and sorted(res[i][1]) == sorted(p)
+                for c in p:
+                    assert rel_err(res[i][0][c], a[c]) < tol and rel_err(res[i][1][c], pa[c]) < tol, (prec, graph, i, c)
+
+
 # ------------------------------------------------------------------ (a10) PAMR
 def test_infer_cam_cuda_graph_matches_eager(dev):
     """cuda_graph=True: two eager warm-ups, capture, replays -- same CAMs as the eager path, also for a different image and
