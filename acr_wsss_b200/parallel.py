@@ -80,6 +80,23 @@ class GradBuckets:
             if not self._avg:
                 self.flat.div_(self.world)
 
+    def reduce_chunks(self, nchunks=4):
+        """All-reduce the flat buffer as `nchunks` back-to-back collectives and yield (start, end) as each one becomes
+        consumable: NCCL runs them in order on its own stream and `work.wait()` only makes the CURRENT stream wait, so the
+        consumer (the optimiser update of that slice) runs under the all-reduce of the following slices."""
+        n = self.flat.numel()
+        step = ((n + nchunks - 1) // nchunks + 127) // 128 * 128
+        spans = [(s, min(n, s + step)) for s in range(0, n, step)]
+        if self.world == 1:
+            yield from spans
+            return
+        works = [self._reduce(s, e) for s, e in spans]
+        for (s, e), w in zip(spans, works):
+            w.wait()
+            if not self._avg:
+                self.flat[s:e].div_(self.world)
+            yield s, e
+
     def finish(self):
         """Call after backward: reduce buckets whose hooks did not all fire (parameters without gradient this step,
         e.g. norm/head/bkg_token) and wait for every outstanding all-reduce."""

@@ -44,6 +44,28 @@ def _worker(rank, world, port, out):
     ok = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(grads[:-1], exp)) and float(grads[-1].abs().max()) == 0.0
     # grads are views into the flat buffer (zero-copy)
     ok = ok and all(p.grad.untyped_storage().data_ptr() == gb.flat.untyped_storage().data_ptr() for p in params)
+    # sliced all-reduce + sliced optimiser update (Trainer._reduce_and_update) == whole-buffer all-reduce + one update
+    from acr_wsss_b200.train import _FlatPolySGD
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 8), torch.nn.Linear(8, 4))
+    gb = GradBuckets(list(net.parameters()), hooks=False)          # CUDA-graph mode: no per-bucket hooks
+    net(x).pow(2).sum().backward()
+    local = gb.flat.clone()
+    opt = _FlatPolySGD(gb.params, gb.flat, gb.offsets, lr=0.1, wt_dec=0.5, max_step=10)
+    opt.set_lr_for_step()
+    spans = []
+    for s_, e_ in gb.reduce_chunks(3):
+        spans.append((s_, e_))
+        opt.update(s_, e_)
+    whole = local.clone()
+    dist.all_reduce(whole)
+    whole /= world
+    ok = ok and spans[0][0] == 0 and spans[-1][1] == gb.flat.numel() and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    ok = ok and torch.allclose(gb.flat, whole, atol=1e-6) and torch.allclose(opt.buf, whole, atol=1e-6)
+    # replicas stay identical after the update
+    chk = opt.flat_param.double().sum().reshape(1)
+    both = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(both, chk)
+    ok = ok and float((both[0] - both[1]).abs()) == 0.0
     shards = shard_indices(11, rank, world)
     out[rank] = (ok, shards)
     dist.destroy_process_group()
