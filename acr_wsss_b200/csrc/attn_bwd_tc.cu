@@ -3,8 +3,9 @@
 //   dP_h = dO_h V_h^T + G/H ;  dS_h = P_h * (dP_h - delta) ;  dV = P^T dO ; dK = dS^T Q * scale ; dQ = dS K * scale
 // (delta comes from bwd_delta_kernel + attn_mean_kernel<1>, attn_tc.cu).
 //
-// One CTA per (key tile j, head, image): K_j, V_j stationary, loop over query tiles i.  512 threads, five roles:
-//   warp 0      TMA producer: K, V once; per query tile Q_i, dO_i (three-stage ring)
+// Work item = (key tile j, head, image): K_j, V_j stationary, loop over query tiles i; a persistent grid of one CTA per SM
+// walks over the items.  512 threads, five roles:
+//   warp 0      TMA producer: K, V once per item; per query tile Q_i, dO_i (three-stage ring running across items)
 //   warp 1      MMA issuer (one thread): S = Q_i K_j^T, dP = dO_i V_j^T (SS, 128x128x64), then dV += P^T dO_i,
 //               dK += dS^T Q_i, dQ_i = dS K_j from the bf16 P / dS tiles the softmax warps publish in shared memory
 //   warps 2-3   row statistics (log2-domain LSE, delta) of the next query tile into shared memory
@@ -12,7 +13,8 @@
 //               registers in one go and hands tS/tDP back at once (sdp_free), so the scores of tile i+1 run on the tensor
 //               pipe UNDER the exponentials of tile i; P and dS stay in registers until the gradient MMAs of tile i-1 have
 //               released the single-buffered smem tiles (pds_free)
-//   warps 12-15 dQ drain: TMEM -> fp32 staging tile -> two cp.reduce.async.bulk.tensor (fp32 add) per tile
+//   warps 12-15 drain: per tile dQ from TMEM -> fp32 staging tile -> two cp.reduce.async.bulk.tensor (fp32 add); per item
+//               dK / dV from TMEM -> bf16 rows of d_qkv
 // The softmax warps therefore execute nothing but the element-wise chain (round 1's kernel spent ~75 % of their time in
 // barrier waits, the dQ hand-over and the exposed S/dP MMA latency: profiles/r01g_ncu_attn_bwd_full.txt).
 // Element-wise math uses the packed fp32x2 instructions (FFMA2 / FMUL2 / FADD2): 5 issue slots per element instead of 8.
@@ -33,7 +35,7 @@ struct BwdSmem {
   uint8_t ds[2][TILE_BYTES];       // same layout: read MN-major (A = dS^T / P^T) and K-major (A = dS)
   uint8_t dq[2][TILE_BYTES];       // fp32 staging of one dQ tile: [32-column half][q row][32 floats], SWIZZLE_128B
   float stat[2][2][BM];            // [tile parity][0: lse * log2(e), 1: delta][q row]
-  uint64_t kv_full, qdo_full[NST], qdo_empty[NST], stat_full[2], sdp_full, sdp_free, pds_full, pds_free, dq_full, dq_free, all_done;
+  uint64_t kv_full, kv_empty, dkv_free, qdo_full[NST], qdo_empty[NST], stat_full[2], sdp_full, sdp_free, pds_full, pds_free, dq_full, dq_free;
   uint32_t tmem_base;
 };
 static_assert(sizeof(BwdSmem) <= 232448, "BwdSmem exceeds the 227 KB dynamic shared memory limit");
@@ -45,7 +47,7 @@ constexpr int BWD_THREADS = 512;
 __device__ unsigned long long g_bwd_trace[4][16][8];      // [role][tile][event]
 #define BWD_TRACE(role, tile, ev)                                                                         \
   do {                                                                                                    \
-    if (blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z == 2 && (tile) < 16 && (threadIdx.x & 31) == 0) g_bwd_trace[role][tile][ev] = clock64(); \
+    if (blockIdx.x == 5 && (tile) < 16 && (threadIdx.x & 31) == 0) g_bwd_trace[role][tile][ev] = clock64(); \
   } while (0)
 #else
 #define BWD_TRACE(role, tile, ev) do { } while (0)
@@ -105,7 +107,7 @@ __device__ __forceinline__ void bwd_softmax_tile(BwdSmem& s, uint32_t tS, uint32
       // pipe is busy with the gradient MMAs of the previous tile until then anyway.
       tc::tc_fence_before();
       tc::mbar_arrive(&s.sdp_free);
-      if (half == 0 && row < 32) BWD_TRACE(1, (pds_par < 0 ? 0 : 15), 2);      // only tile 0 and "some later tile" (slot 15)
+      if (half == 0 && row < 32) BWD_TRACE(1, 15, 2);
     }
     if (!live) {
 #pragma unroll
@@ -196,9 +198,10 @@ struct SoftmaxArgs {
   uint32_t p_row, ds_row, swz;
 };
 
-// The query-tile loop of one softmax thread.
+// The query-tile loop of one softmax thread for one work item; T0 = tiles this CTA has processed before it (the mbarrier
+// parities run on the CTA-wide tile count).
 template <int GMODE, bool TAIL>
-__device__ __forceinline__ void bwd_softmax_loop(BwdSmem& s, const SoftmaxArgs& a) {
+__device__ __forceinline__ void bwd_softmax_loop(BwdSmem& s, const SoftmaxArgs& a, int T0) {
   const int row = a.row, N = a.N;
   const int wq = row & ~31;                            // first row of this warp's TMEM lane quadrant
   // Sign codes: 64 bytes of this thread's row per tile, straight from global memory (each byte is used by one thread of one
@@ -223,17 +226,18 @@ __device__ __forceinline__ void bwd_softmax_loop(BwdSmem& s, const SoftmaxArgs& 
       if (i + 1 < a.ntiles) load_codes(i + 1);
     }
     const int q0 = i * BM;
-    const int pds_par = (i > 0) ? ((i - 1) & 1) : -1;
+    const int T = T0 + i;
+    const int pds_par = (T > 0) ? ((T - 1) & 1) : -1;
     const int qi = q0 + row;
     const bool rows_live = q0 + wq < N;                // warp-uniform
     float lse2 = INFINITY, dlt = 0.f;
     if (rows_live) {
-      tc::mbar_wait(&s.stat_full[i & 1], (i >> 1) & 1);
-      lse2 = s.stat[i & 1][0][row];
-      dlt = s.stat[i & 1][1][row];
+      tc::mbar_wait(&s.stat_full[T & 1], (T >> 1) & 1);
+      lse2 = s.stat[T & 1][0][row];
+      dlt = s.stat[T & 1][1][row];
     }
     if (a.half == 0 && row < 32) BWD_TRACE(1, i, 0);
-    tc::mbar_wait(&s.sdp_full, i & 1);
+    tc::mbar_wait(&s.sdp_full, T & 1);
     tc::tc_fence_after();
     if (a.half == 0 && row < 32) BWD_TRACE(1, i, 1);
     if (!rows_live) {
@@ -274,18 +278,53 @@ __device__ __forceinline__ void bwd_softmax_loop(BwdSmem& s, const SoftmaxArgs& 
   }
 }
 
+// Work items of the persistent grid: (key tile, head*image).  Full key tiles first, then the thin last tiles (N = p*p+1 leaves
+// 17 valid keys in the last tile at 448x448: ~1/3 of the cost), dealt round-robin -- the thin ones starting from the CTAs that
+// got one full item less -- so every CTA first runs the <TAIL = false> loops and then the <TAIL = true> ones.
+struct Items {
+  int kt_full, nfull, nthin;
+  __device__ bool at(int c, int G, int k, int& kvt, int& hb, bool& tail) const {
+    const int nf = nfull > c ? (nfull - c + G - 1) / G : 0;
+    if (k < nf) {
+      const int f = c + k * G;
+      kvt = f % kt_full;
+      hb = f / kt_full;
+      tail = false;
+      return true;
+    }
+    k -= nf;
+    const int cr = G - 1 - c;
+    const int nt = nthin > cr ? (nthin - cr + G - 1) / G : 0;
+    if (k < nt) {
+      kvt = kt_full;
+      hb = cr + k * G;
+      tail = true;
+      return true;
+    }
+    return false;
+  }
+};
+
+// Persistent: one CTA per SM walks over its work items.  The Q/dO ring, the TMEM allocation and every barrier phase run on
+// across items, so an item's prologue (TMEM allocation, barrier init, first TMA round trips: 2400 cycles) and epilogue (last dQ
+// reduce, dK/dV write-out: 5000 cycles of a 30000-cycle CTA in the one-item-per-CTA version) are paid once per CTA or hidden
+// under the next item's first tiles.
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_dq,
                 const float* __restrict__ lse, const float* __restrict__ delta, const float* __restrict__ g_mean, long long g_bs,
-                long long g_ld, GCode gc, __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ g_row0, int N, int H, float scale,
+                long long g_ld, GCode gc, __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ g_row0, int N, int H, int HB, float scale,
                 float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   BwdSmem& s = *reinterpret_cast<BwdSmem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv0 = blockIdx.x * BN, h = blockIdx.y, b = blockIdx.z;
   const int ntiles = (N + BM - 1) / BM;
   const bool has_code = gc.ptr != nullptr;
+  const int G = gridDim.x, cta = blockIdx.x;
+  Items items;
+  items.kt_full = N / BN;
+  items.nfull = items.kt_full * HB;
+  items.nthin = (N % BN) ? HB : 0;
 
   if (warp == 0 && lane == 0) {
     if (tc::smem_u32(smem_raw) & 1023u) __trap();      // SWIZZLE_128B tiles need 1024-byte aligned shared memory
@@ -293,6 +332,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     tc::prefetch_tmap(&tmap_do);
     tc::prefetch_tmap(&tmap_dq);
     tc::mbar_init(&s.kv_full, 1);
+    tc::mbar_init(&s.kv_empty, 1);
+    tc::mbar_init(&s.dkv_free, 128);
     for (int i = 0; i < NST; ++i) {
       tc::mbar_init(&s.qdo_full[i], 1);
       tc::mbar_init(&s.qdo_empty[i], 1);
@@ -304,7 +345,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     tc::mbar_init(&s.pds_free, 1);
     tc::mbar_init(&s.dq_full, 1);
     tc::mbar_init(&s.dq_free, 128);
-    tc::mbar_init(&s.all_done, 1);
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc<512>(&s.tmem_base);
@@ -318,25 +358,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   if (warp < 4) {
     tc::reg_dealloc<REG_CTRL>();
     if (warp == 0) {
-      if (tc::elect_one()) {
-        tc::mbar_arrive_expect_tx(&s.kv_full, 2 * TILE_BYTES);
-        tc::tma_load_4d(s.k, &tmap_qkv, &s.kv_full, 0, H + h, kv0, b);
-        tc::tma_load_4d(s.v, &tmap_qkv, &s.kv_full, 0, 2 * H + h, kv0, b);
-      }
-      __syncwarp();
-      for (int i = 0; i < ntiles; ++i) {
-        const int st = i % NST;
-        tc::mbar_wait(&s.qdo_empty[st], ((i / NST) & 1) ^ 1);
+      int T = 0, kvt, hb;
+      bool tail;
+      for (int k = 0; items.at(cta, G, k, kvt, hb, tail); ++k) {
+        const int h = hb % H, b = hb / H, kv0 = kvt * BN;
+        tc::mbar_wait(&s.kv_empty, (k & 1) ^ 1);        // every MMA of the previous item has read K / V
         if (tc::elect_one()) {
-          tc::mbar_arrive_expect_tx(&s.qdo_full[st], 2 * TILE_BYTES);
-          tc::tma_load_4d(s.q[st], &tmap_qkv, &s.qdo_full[st], 0, h, i * BM, b);
-          tc::tma_load_4d(s.d_o[st], &tmap_do, &s.qdo_full[st], 0, h, i * BM, b);
+          tc::mbar_arrive_expect_tx(&s.kv_full, 2 * TILE_BYTES);
+          tc::tma_load_4d(s.k, &tmap_qkv, &s.kv_full, 0, H + h, kv0, b);
+          tc::tma_load_4d(s.v, &tmap_qkv, &s.kv_full, 0, 2 * H + h, kv0, b);
         }
         __syncwarp();
+        for (int i = 0; i < ntiles; ++i, ++T) {
+          const int st = T % NST;
+          tc::mbar_wait(&s.qdo_empty[st], ((T / NST) & 1) ^ 1);
+          if (tc::elect_one()) {
+            tc::mbar_arrive_expect_tx(&s.qdo_full[st], 2 * TILE_BYTES);
+            tc::tma_load_4d(s.q[st], &tmap_qkv, &s.qdo_full[st], 0, h, i * BM, b);
+            tc::tma_load_4d(s.d_o[st], &tmap_do, &s.qdo_full[st], 0, h, i * BM, b);
+          }
+          __syncwarp();
+        }
       }
     } else if (warp == 1) {
       // all 32 lanes walk the loop and wait on the barriers; one elected lane issues (see tc::elect_one)
-      tc::mbar_wait(&s.kv_full, 0);
       // Shared-memory descriptors are built once; a step along K (or to the next 64-wide block) is an addition to the
       // 16-byte-unit start-address field (no carry out of it: every tile lies below 256 KB).
       const uint64_t kd_k = tc::smem_desc_sw128(tc::smem_u32(s.k), 16, 1024);        // K, K-major   (B of S)
@@ -344,11 +389,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       const uint64_t kd_mn = tc::smem_desc_sw128(tc::smem_u32(s.k), 1024, 1024);     // K, MN-major  (B of dQ)
       const uint64_t pd_mn = tc::smem_desc_sw128(tc::smem_u32(s.p[0]), TILE_BYTES, 1024);    // P^T  (A of dV): two 64-wide M blocks 16 KB apart
       const uint64_t dsd_mn = tc::smem_desc_sw128(tc::smem_u32(s.ds[0]), TILE_BYTES, 1024);  // dS^T (A of dK)
-      auto issue_scores = [&](int i) {      // S = Q K^T, dP = dO V^T
-        const int st = i % NST;
-        tc::mbar_wait(&s.qdo_full[st], (i / NST) & 1);
+      auto issue_scores = [&](int T) {      // S = Q K^T, dP = dO V^T of the CTA's T-th tile
+        const int st = T % NST;
+        tc::mbar_wait(&s.qdo_full[st], (T / NST) & 1);
         tc::tc_fence_after();
-        BWD_TRACE(0, i, 0);
+        BWD_TRACE(0, T, 0);
         const uint64_t qd = tc::smem_desc_sw128(tc::smem_u32(s.q[st]), 16, 1024), dod = tc::smem_desc_sw128(tc::smem_u32(s.d_o[st]), 16, 1024);
         if (tc::elect_one()) {
 #pragma unroll
@@ -359,55 +404,65 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         }
         __syncwarp();
       };
-      issue_scores(0);
-      for (int i = 0; i < ntiles; ++i) {
-        const int st = i % NST;
-        if (i + 1 < ntiles) {                // scores of the next tile as soon as the softmax warps hold S/dP(i) in registers
-          tc::mbar_wait(&s.sdp_free, i & 1);
-          issue_scores(i + 1);
+      int T = 0, kvt, hb;
+      bool tail;
+      for (int k = 0; items.at(cta, G, k, kvt, hb, tail); ++k) {
+        tc::mbar_wait(&s.kv_full, k & 1);
+        if (T > 0) tc::mbar_wait(&s.sdp_free, (T - 1) & 1);      // the previous item's last tile has left tS / tDP
+        issue_scores(T);
+        for (int i = 0; i < ntiles; ++i, ++T) {
+          const int st = T % NST;
+          if (i + 1 < ntiles) {                // scores of the next tile as soon as the softmax warps hold S/dP of this one in registers
+            tc::mbar_wait(&s.sdp_free, T & 1);
+            issue_scores(T + 1);
+          }
+          const uint64_t qd_mn = tc::smem_desc_sw128(tc::smem_u32(s.q[st]), 1024, 1024), dod_mn = tc::smem_desc_sw128(tc::smem_u32(s.d_o[st]), 1024, 1024);
+          BWD_TRACE(0, T, 1);
+          tc::mbar_wait(&s.pds_full, T & 1);                          // P / dS published
+          BWD_TRACE(0, T, 2);
+          if (T >= 1) tc::mbar_wait(&s.dq_free, (T - 1) & 1);         // the previous dQ has left tDQ
+          if (i == 0 && k > 0) tc::mbar_wait(&s.dkv_free, (k - 1) & 1);   // dK / dV of the previous item have left TMEM
+          tc::tc_fence_after();
+          const uint32_t acc = (i > 0) ? 1u : 0u;
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < BM / 16; ++ks)      // dK += dS^T Q   (M = kv, K = q: 16 q rows = 2048 bytes per step)
+              tc::mma_ss_off(tDK, dsd_mn, ks * 128, qd_mn, ks * 128, IDESC_DQ, acc | (ks > 0));
+#pragma unroll
+            for (int ks = 0; ks < BM / 16; ++ks)      // dV += P^T dO
+              tc::mma_ss_off(tDV, pd_mn, ks * 128, dod_mn, ks * 128, IDESC_DQ, acc | (ks > 0));
+            tc::tc_commit(&s.pds_free);               // the shared-memory P / dS tiles and Q / dO are free again ...
+            tc::tc_commit(&s.qdo_empty[st]);
+#pragma unroll
+            for (int ks = 0; ks < BN / 16; ++ks)      // dQ_i = dS K   (A = dS out of TMEM: 16 keys = 8 columns per step; B = K MN-major)
+              tc::mma_ts_off(tDQ, tDS + ks * 8, kd_mn, ks * 128, IDESC_PV, ks > 0);
+            tc::tc_commit(&s.dq_full);                // ... and with dq_full so is tDS
+            if (i + 1 == ntiles) tc::tc_commit(&s.kv_empty);   // K / V may be replaced by the next item's
+          }
+          __syncwarp();
+          BWD_TRACE(0, T, 3);
         }
-        const uint64_t qd_mn = tc::smem_desc_sw128(tc::smem_u32(s.q[st]), 1024, 1024), dod_mn = tc::smem_desc_sw128(tc::smem_u32(s.d_o[st]), 1024, 1024);
-        BWD_TRACE(0, i, 1);
-        tc::mbar_wait(&s.pds_full, i & 1);                          // P / dS(i) published
-        BWD_TRACE(0, i, 2);
-        if (i >= 1) tc::mbar_wait(&s.dq_free, (i - 1) & 1);         // dQ(i-1) has left tDQ
-        tc::tc_fence_after();
-        const uint32_t acc = (i > 0) ? 1u : 0u;
-        if (tc::elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < BM / 16; ++ks)      // dK += dS^T Q   (M = kv, K = q: 16 q rows = 2048 bytes per step)
-            tc::mma_ss_off(tDK, dsd_mn, ks * 128, qd_mn, ks * 128, IDESC_DQ, acc | (ks > 0));
-#pragma unroll
-          for (int ks = 0; ks < BM / 16; ++ks)      // dV += P^T dO
-            tc::mma_ss_off(tDV, pd_mn, ks * 128, dod_mn, ks * 128, IDESC_DQ, acc | (ks > 0));
-          tc::tc_commit(&s.pds_free);               // the shared-memory P / dS tiles and Q / dO are free again ...
-          tc::tc_commit(&s.qdo_empty[st]);
-#pragma unroll
-          for (int ks = 0; ks < BN / 16; ++ks)      // dQ_i = dS K   (A = dS out of TMEM: 16 keys = 8 columns per step; B = K MN-major)
-            tc::mma_ts_off(tDQ, tDS + ks * 8, kd_mn, ks * 128, IDESC_PV, ks > 0);
-          tc::tc_commit(&s.dq_full);                // ... and with dq_full so is tDS
-          if (i + 1 == ntiles) tc::tc_commit(&s.all_done);
-        }
-        __syncwarp();
-        BWD_TRACE(0, i, 3);
       }
     } else {
-      // warps 2, 3: row statistics of query tile i -> s.stat[i & 1] (warp 2: log2-domain LSE, warp 3: delta)
+      // warps 2, 3: row statistics of the CTA's T-th tile -> s.stat[T & 1] (warp 2: log2-domain LSE, warp 3: delta)
       const int which = warp - 2;
-      const float* src = (which == 0 ? lse : delta) + ((size_t)b * H + h) * N;
-      for (int i = 0; i < ntiles; ++i) {
-        const int st = i & 1;
-        // slot reuse: the gradient MMAs of tile i-2 have retired, so its softmax read the statistics long ago
-        if (i >= 2) tc::mbar_wait(&s.qdo_empty[(i - 2) % NST], ((i - 2) / NST) & 1);
-        float v[4];
+      int T = 0, kvt, hb;
+      bool tail;
+      for (int k = 0; items.at(cta, G, k, kvt, hb, tail); ++k) {
+        const float* src = (which == 0 ? lse : delta) + (size_t)hb * N;       // [B,H,N]: hb = b*H + h
+        for (int i = 0; i < ntiles; ++i, ++T) {
+          // slot reuse: the gradient MMAs of tile T-2 have retired, so its softmax read the statistics long ago
+          if (T >= 2) tc::mbar_wait(&s.qdo_empty[(T - 2) % NST], ((T - 2) / NST) & 1);
+          float v[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int qi = i * BM + k * 32 + lane;
-          v[k] = (qi < N) ? __ldg(src + qi) : (which == 0 ? INFINITY : 0.f);      // rows past N: P = exp2(-inf) = 0
+          for (int q = 0; q < 4; ++q) {
+            const int qi = i * BM + q * 32 + lane;
+            v[q] = (qi < N) ? __ldg(src + qi) : (which == 0 ? INFINITY : 0.f);      // rows past N: P = exp2(-inf) = 0
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) s.stat[T & 1][which][q * 32 + lane] = (which == 0) ? v[q] * kLog2e : v[q];
+          tc::mbar_arrive(&s.stat_full[T & 1]);
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s.stat[st][which][k * 32 + lane] = (which == 0) ? v[k] * kLog2e : v[k];
-        tc::mbar_arrive(&s.stat_full[st]);
       }
     }
   } else if (warp < 12) {
@@ -417,8 +472,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const int half = we >> 2;                        // which 64-column (key) half
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const float invH = 1.f / (float)H;
-    const int colbase = kv0 + half * 64;
-    const bool tail = (kv0 + BN > N);
     const bool g_vec = (g_mean != nullptr) && ((g_ld & 3) == 0) && ((g_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(g_mean) & 15) == 0);
     float w_cls2 = 0.f, w_aff2 = 0.f;
     if (has_code) {
@@ -429,87 +482,105 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     // row start ^ swizzle term (see bwd_softmax_tile)
     const uint32_t swz = (uint32_t)(row & 7) << 4;
     const uint32_t p_row = (tc::smem_u32(s.p[half]) + row * 128) ^ swz, ds_row = (tc::smem_u32(s.ds[half]) + row * 128) ^ swz;
-    // one instantiation of the tile loop per (form of G, key-tail) pair, chosen once: with the choice inside the loop ptxas hoists
-    // the invariants of all six bodies and spills
-    const SoftmaxArgs sa{tS, tDP, tDS, lane_off, half, row, colbase, N, H, ntiles, b, h, g_mean, g_bs, g_ld, g_row0, gc.ptr, gc.bs, gc.ld, w_cls2, w_aff2, invH, scale_log2,
-                         p_row, ds_row, swz};
-    if (has_code) {
-      if (!tail) bwd_softmax_loop<3, false>(s, sa); else bwd_softmax_loop<3, true>(s, sa);
-    } else if (g_mean != nullptr) {
-      if (!tail && g_vec) bwd_softmax_loop<2, false>(s, sa); else bwd_softmax_loop<1, true>(s, sa);
-    } else {
-      if (!tail) bwd_softmax_loop<0, false>(s, sa); else bwd_softmax_loop<0, true>(s, sa);
-    }
-    // epilogue: dV, dK rows (lanes = keys) of this key tile once every MMA has retired
-    if (we == 0) BWD_TRACE(3, 0, 2);
-    tc::mbar_wait(&s.all_done, 0);
-    if (we == 0) BWD_TRACE(3, 0, 3);
-    tc::tc_fence_after();
-    const bool kv_ok = (kv0 + row) < N;
-    uint32_t pk[32], dk[32];
-    tc::tmem_ld32(tDV + lane_off + half * 32, pk);      // warp-collective: outside the per-row validity branch
-    tc::tmem_ld32(tDK + lane_off + half * 32, dk);
-    tc::tmem_ld_wait();
-    if (kv_ok) {
-      const size_t E = (size_t)H * HD;
-      __nv_bfloat16* dkp = d_qkv + (((size_t)b * N + kv0 + row) * 3 + 1) * E + (size_t)h * HD + half * 32;
-      __nv_bfloat16* dvp = d_qkv + (((size_t)b * N + kv0 + row) * 3 + 2) * E + (size_t)h * HD + half * 32;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 v, k;
-        v.x = tc::pack_bf16(__uint_as_float(pk[c * 8 + 0]), __uint_as_float(pk[c * 8 + 1]));
-        v.y = tc::pack_bf16(__uint_as_float(pk[c * 8 + 2]), __uint_as_float(pk[c * 8 + 3]));
-        v.z = tc::pack_bf16(__uint_as_float(pk[c * 8 + 4]), __uint_as_float(pk[c * 8 + 5]));
-        v.w = tc::pack_bf16(__uint_as_float(pk[c * 8 + 6]), __uint_as_float(pk[c * 8 + 7]));
-        k.x = tc::pack_bf16(__uint_as_float(dk[c * 8 + 0]) * scale, __uint_as_float(dk[c * 8 + 1]) * scale);
-        k.y = tc::pack_bf16(__uint_as_float(dk[c * 8 + 2]) * scale, __uint_as_float(dk[c * 8 + 3]) * scale);
-        k.z = tc::pack_bf16(__uint_as_float(dk[c * 8 + 4]) * scale, __uint_as_float(dk[c * 8 + 5]) * scale);
-        k.w = tc::pack_bf16(__uint_as_float(dk[c * 8 + 6]) * scale, __uint_as_float(dk[c * 8 + 7]) * scale);
-        reinterpret_cast<uint4*>(dvp)[c] = v;
-        reinterpret_cast<uint4*>(dkp)[c] = k;
+    // one instantiation of the tile loop per (form of G, key-tail) pair; the form of G is fixed per launch and a CTA runs all its
+    // full-tile items before its thin ones, so each loop below contains ONE body (with the choice inside the tile loop ptxas
+    // hoists the invariants of every body and spills)
+    int T = 0, k = 0, kvt, hb;
+    bool tail;
+    auto run = [&](auto body, bool want_tail) {
+      while (items.at(cta, G, k, kvt, hb, tail) && tail == want_tail) {
+        const SoftmaxArgs sa{tS, tDP, tDS, lane_off, half, row, kvt * BN + half * 64, N, H, ntiles, hb / H, hb % H, g_mean, g_bs, g_ld, g_row0,
+                             gc.ptr, gc.bs, gc.ld, w_cls2, w_aff2, invH, scale_log2, p_row, ds_row, swz};
+        body(sa, T);
+        T += ntiles;
+        ++k;
       }
+    };
+    if (has_code) {
+      run([&](const SoftmaxArgs& sa, int T0) { bwd_softmax_loop<3, false>(s, sa, T0); }, false);
+      run([&](const SoftmaxArgs& sa, int T0) { bwd_softmax_loop<3, true>(s, sa, T0); }, true);
+    } else if (g_mean != nullptr && g_vec) {
+      run([&](const SoftmaxArgs& sa, int T0) { bwd_softmax_loop<2, false>(s, sa, T0); }, false);
+      run([&](const SoftmaxArgs& sa, int T0) { bwd_softmax_loop<1, true>(s, sa, T0); }, true);
+    } else if (g_mean != nullptr) {
+      run([&](const SoftmaxArgs& sa, int T0) { bwd_softmax_loop<1, true>(s, sa, T0); }, false);
+      run([&](const SoftmaxArgs& sa, int T0) { bwd_softmax_loop<1, true>(s, sa, T0); }, true);
+    } else {
+      run([&](const SoftmaxArgs& sa, int T0) { bwd_softmax_loop<0, false>(s, sa, T0); }, false);
+      run([&](const SoftmaxArgs& sa, int T0) { bwd_softmax_loop<0, true>(s, sa, T0); }, true);
     }
   } else {
-    // dQ drain warpgroup: dQ of query tile i (rows = queries, 64 d columns) -> fp32 accumulator [B*H, N, 64] by two TMA
-    // reduce-adds of [128 x 32] fp32 SWIZZLE_128B tiles; rows past N are clipped by the tensor map
+    // drain warpgroup.  Per tile: dQ (rows = queries, 64 d columns) -> fp32 accumulator [B*H, N, 64] by two TMA reduce-adds of
+    // [128 x 32] fp32 SWIZZLE_128B tiles (rows past N are clipped by the tensor map).  Per item: dV, dK rows (lanes = keys) of
+    // the key tile -> d_qkv as bf16 once its last MMA has retired (the last dq_full of the item covers every earlier MMA).
     tc::reg_dealloc<REG_DRAIN>();
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const bool leader = (warp == 12 && lane == 0);
     const uint32_t dq_row = (tc::smem_u32(s.dq[0]) + row * 128) ^ ((uint32_t)(row & 7) << 4);      // row start ^ swizzle term
     uint32_t r[32];
-    for (int i = 0; i < ntiles; ++i) {
-      if (warp == 12) BWD_TRACE(2, i, 0);
-      tc::mbar_wait(&s.dq_full, i & 1);
-      tc::tc_fence_after();
-      if (warp == 12) BWD_TRACE(2, i, 1);
-      if (i > 0) {          // the reduce-add of the previous tile must have read the staging tile
-        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    int T = 0, kvt, hb;
+    bool tail;
+    for (int k = 0; items.at(cta, G, k, kvt, hb, tail); ++k) {
+      for (int i = 0; i < ntiles; ++i, ++T) {
+        if (warp == 12) BWD_TRACE(2, T, 0);
+        tc::mbar_wait(&s.dq_full, T & 1);
+        tc::tc_fence_after();
+        if (warp == 12) BWD_TRACE(2, T, 1);
+        if (T > 0) {          // the reduce-add of the previous tile must have read the staging tile
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync 3, 128;" ::: "memory");
+        }
+        if (warp == 12) BWD_TRACE(2, T, 2);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tc::tmem_ld32(tDQ + lane_off + c * 32, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            sts128((dq_row + c * TILE_BYTES) ^ (uint32_t)(e << 4), r[4 * e], r[4 * e + 1], r[4 * e + 2], r[4 * e + 3]);
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&s.dq_free);
+        tc::fence_proxy_async_smem();
         asm volatile("bar.sync 3, 128;" ::: "memory");
+        if (leader) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh)
+            asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tmap_dq)),
+                         "r"(tc::smem_u32(s.dq[hh])), "r"(hh * 32), "r"(i * BM), "r"(hb)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          BWD_TRACE(2, T, 3);
+        }
       }
-      if (warp == 12) BWD_TRACE(2, i, 2);
+      // dV / dK of this item
+      const int h = hb % H, b = hb / H, kv0 = kvt * BN;
+      const bool kv_ok = (kv0 + row) < N;
+      const size_t E = (size_t)H * HD;
+      __nv_bfloat16* base = d_qkv + ((size_t)b * N + min(kv0 + row, N - 1)) * 3 * E + (size_t)h * HD;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tc::tmem_ld32(tDQ + lane_off + c * 32, r);
+      for (int part = 0; part < 4; ++part) {           // dV cols 0-31, 32-63, dK cols 0-31, 32-63
+        const bool is_k = part >= 2;
+        tc::tmem_ld32((is_k ? tDK : tDV) + lane_off + (part & 1) * 32, r);      // warp-collective: outside the per-row validity branch
         tc::tmem_ld_wait();
+        if (kv_ok) {
+          const float sc = is_k ? scale : 1.f;
+          __nv_bfloat16* dst = base + (is_k ? 1 : 2) * E + (part & 1) * 32;
 #pragma unroll
-        for (int e = 0; e < 8; ++e)
-          sts128((dq_row + c * TILE_BYTES) ^ (uint32_t)(e << 4), r[4 * e], r[4 * e + 1], r[4 * e + 2], r[4 * e + 3]);
+          for (int c = 0; c < 4; ++c) {
+            uint4 v;
+            v.x = tc::pack_bf16(__uint_as_float(r[c * 8 + 0]) * sc, __uint_as_float(r[c * 8 + 1]) * sc);
+            v.y = tc::pack_bf16(__uint_as_float(r[c * 8 + 2]) * sc, __uint_as_float(r[c * 8 + 3]) * sc);
+            v.z = tc::pack_bf16(__uint_as_float(r[c * 8 + 4]) * sc, __uint_as_float(r[c * 8 + 5]) * sc);
+            v.w = tc::pack_bf16(__uint_as_float(r[c * 8 + 6]) * sc, __uint_as_float(r[c * 8 + 7]) * sc);
+            reinterpret_cast<uint4*>(dst)[c] = v;
+          }
+        }
       }
       tc::tc_fence_before();
-      tc::mbar_arrive(&s.dq_free);
-      tc::fence_proxy_async_smem();
-      asm volatile("bar.sync 3, 128;" ::: "memory");
-      if (leader) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
-          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(&tmap_dq)),
-                       "r"(tc::smem_u32(s.dq[hh])), "r"(hh * 32), "r"(i * BM), "r"(b * H + h)
-                       : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        BWD_TRACE(2, i, 3);
-      }
+      tc::mbar_arrive(&s.dkv_free);
     }
     // the TMA reduce-adds are asynchronous: they must complete before the CTA (and its shared memory) goes away
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -533,10 +604,16 @@ int launch_attn_bwd(const CUtensorMap& tmap_qkv, const CUtensorMap& tmap_do, con
   const size_t smem = sizeof(BwdSmem);
   static bool attr_set[64] = {false};
   if (int e = set_max_smem(attn_bwd_kernel, smem, attr_set)) return e;
+  static int sms[64] = {0};
+  int dev = 0;
+  ACR_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!sms[dev]) ACR_CUDA(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
   const int kt = (N + BN - 1) / BN;
-  dim3 grid(kt, H, B);
+  const long long nitems = (long long)kt * H * B;
+  const unsigned grid = (unsigned)(nitems < sms[dev] ? nitems : sms[dev]);      // persistent: one CTA per SM
   acr::KernelTimer kt_("attn_bwd_kernel", st);
-  attn_bwd_kernel<<<grid, BWD_THREADS, smem, st>>>(tmap_qkv, tmap_do, tmap_dq, lse, delta, g_mean, g_bs, g_ld, gc, d_qkv, g_row0, N, H,
+  attn_bwd_kernel<<<grid, BWD_THREADS, smem, st>>>(tmap_qkv, tmap_do, tmap_dq, lse, delta, g_mean, g_bs, g_ld, gc, d_qkv, g_row0, N, H, H * B,
                                                     scale, scale * kLog2e);
   return acr::check_launch("attn_bwd_kernel");
 }

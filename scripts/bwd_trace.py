@@ -43,8 +43,8 @@ L.acr_bwd_trace_read(buf)
 t = [[[buf[(r * 16 + i) * 8 + e] for e in range(8)] for i in range(16)] for r in range(4)]
 t0 = t[3][0][0]
 rel = lambda v: (v - t0) if v else None
-nt = (N + 127) // 128
-print(f"CTA (1,3,2), B={B} N={N} H={H}, G mode {mode}; cycles since CTA start; kernel end {rel(t[3][0][1])}, softmax loop done {rel(t[3][0][2])}, all_done seen {rel(t[3][0][3])}")
+nt = min(16, 2 * ((N + 127) // 128))
+print(f"CTA 5 (its first two work items), B={B} N={N} H={H}, G mode {mode}; cycles since CTA start; kernel end {rel(t[3][0][1])}, ")
 print("tile | MMA: scores issued, wait pds_full, pds_full seen, grads issued | softmax: wait sdp, sdp seen, pds_full arrive | drain: wait dq, dq seen, staged from, reduce issued")
 for i in range(nt):
     m, s, d = t[0][i], t[1][i], t[2][i]
