@@ -8,7 +8,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_longlong, c_size_t, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libacr_b200.so")
+LIB_PATH = os.environ.get("ACR_B200_LIB") or os.path.join(_HERE, "libacr_b200.so")      # override: A/B builds of the same ABI (scripts/)
 
 _lib = None
 
@@ -50,6 +50,9 @@ SIGNATURES = {
     "acr_getam_row0_batch": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "acr_affinity_sum": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "acr_affinity_refine": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "acr_affinity_refine_tc_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "acr_affinity_refine_tc": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "acr_patch_cam_tc": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "acr_pamr_workspace": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "acr_pamr_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              POINTER(c_int), c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -71,6 +74,8 @@ def lib():
                 "(or `make -C acr_wsss_b200/csrc`). There is no CPU fallback.")
         handle = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
+            if "ACR_B200_LIB" in os.environ and not hasattr(handle, name):
+                continue                # an older A/B build may lack newer entry points; calling one raises AttributeError
             fn = getattr(handle, name)  # AttributeError if the .so is stale
             fn.restype = res
             fn.argtypes = args

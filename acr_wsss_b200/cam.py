@@ -18,10 +18,12 @@ def affinity_refine(attn, cam, t=1, normalize=False):
     t=1, normalize=False is the reference (A is the plain sum over blocks, applied once, SURVEY Q7);
     t>1 / normalize=True is the generalisation named by the north star (row-normalised affinity power).
     """
-    A = ops.affinity_sum(attn, normalize)
     squeeze = cam.dim() == 2
     c3 = cam.unsqueeze(-1) if squeeze else cam
-    out = ops.affinity_apply(A, c3, t)
+    if c3.shape[-1] + int(bool(normalize)) <= 128:
+        out = ops.affinity_refine_tc(attn, c3, t, normalize)        # tensor cores: block sum + contraction + normalisation fused
+    else:                                                           # more classes than one UMMA tile: exact CUDA-core kernels
+        out = ops.affinity_apply(ops.affinity_sum(attn, normalize), c3, t)
     return out.squeeze(-1) if squeeze else out
 
 

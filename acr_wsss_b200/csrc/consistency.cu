@@ -9,9 +9,17 @@
 // Per-row partial |d| sums go to a scratch array and are folded by a second, single-CTA kernel in a
 // fixed order (deterministic; no float atomics).
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
+
+// read-only load as a volatile asm statement: the compiler keeps these in program order (see the barrier in the row loop)
+__device__ __forceinline__ float ld_nc(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 
 __device__ __forceinline__ int flip_token(int t, int p) {
   if (t == 0) return 0;
@@ -40,12 +48,14 @@ consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ 
                         unsigned char* __restrict__ c1, unsigned char* __restrict__ c2, long long c_ld,
                         float* __restrict__ partials) {
   extern __shared__ unsigned short pi_tab[];      // pi(j), j < N
+  __shared__ float s_part[kWarps][2];             // per warp: sum |d| of its cls rows (i = 0) and of its patch rows
   for (int j = threadIdx.x; j < N; j += blockDim.x) pi_tab[j] = (unsigned short)flip_token(j, p);
   __syncthreads();
   const int lane = threadIdx.x & 31;
+  float sum_cls = 0.f, sum_aff = 0.f;
   for (int rw = 0; rw < kRowsPerWarp; ++rw) {
   const long long row = (long long)blockIdx.x * kRowsPerCta + (long long)rw * kWarps + (threadIdx.x >> 5);      // (b*L + l)*N + i
-  if (row >= rows) return;
+  if (row >= rows) break;
   const int i = (int)(row % N);
   const long long img = row / N;               // b*L + l
   const int pi_i = pi_tab[i];
@@ -58,22 +68,27 @@ consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ 
   unsigned char* b2 = (kGrad == 2) ? c2 + (img * N + pi_i) * c_ld : nullptr;
 
   float acc = 0.f;
-  for (int j0 = 0; j0 < N; j0 += 32 * kUnroll) {
+  // full chunks of 32 * kUnroll columns run without bounds checks; the tail chunk (N = p*p+1) with them
+  auto chunk = [&](int j0, auto full_tag) {
+    constexpr bool kFull = decltype(full_tag)::value;
     float v1[kUnroll], v2[kUnroll];
     int pj[kUnroll];
 #pragma unroll
     for (int k = 0; k < kUnroll; ++k) {
       const int j = j0 + k * 32 + lane;
-      if (j < N) {
+      if (kFull || j < N) {
         pj[k] = pi_tab[j];
-        v1[k] = __ldg(r1 + j);
-        v2[k] = __ldg(r2 + pj[k]);
+        v1[k] = ld_nc(r1 + j);
+        v2[k] = ld_nc(r2 + pj[k]);
       }
     }
+    // keep all 2 * kUnroll loads in flight before the first store: ptxas otherwise sinks every load next to its use
+    // (load, compare, store, next load ...: 2.1 instead of 3.3 TB/s); a warp barrier is a scheduling fence for memory operations
+    __syncwarp();
 #pragma unroll
     for (int k = 0; k < kUnroll; ++k) {
       const int j = j0 + k * 32 + lane;
-      if (j < N) {
+      if (kFull || j < N) {
         float s = 0.f;
         unsigned char code = 0, ncode = 0;
         if (j > 0) {
@@ -93,7 +108,10 @@ consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ 
         }
       }
     }
-  }
+  };
+  int j0 = 0;
+  for (; j0 + 32 * kUnroll <= N; j0 += 32 * kUnroll) chunk(j0, std::true_type{});
+  if (j0 < N) chunk(j0, std::false_type{});
   if (kGrad == 2) {      // row padding [N, c_ld): consumers read whole 16-byte chunks of a row; keep them defined (= no gradient)
     for (long long j = N + lane; j < c_ld; j += 32) {
       b1[j] = 0;
@@ -101,19 +119,29 @@ consistency_rows_kernel(const float* __restrict__ a1, const float* __restrict__ 
     }
   }
   acc = acr::warp_sum(acc);
-  if (lane == 0) partials[row] = acc;
+  if (i == 0) sum_cls += acc; else sum_aff += acc;
+  }
+  // one (cls, aff) pair per CTA, summed in a fixed order: the finish kernel folds 2 * gridDim.x numbers instead of one per row
+  if (lane == 0) { s_part[threadIdx.x >> 5][0] = sum_cls; s_part[threadIdx.x >> 5][1] = sum_aff; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) v += s_part[w][threadIdx.x];
+    partials[2 * (long long)blockIdx.x + threadIdx.x] = v;
   }
 }
 
-// Folds the per-row partials: rows with i==0 feed cls_align, the rest aff_align.
+// Folds the per-CTA (cls, aff) partials in a fixed order (deterministic; no float atomics).
 __global__ void __launch_bounds__(1024)
-consistency_finish_kernel(const float* __restrict__ partials, long long rows, int N,
+consistency_finish_kernel(const float2* __restrict__ partials, int nparts,
                           double inv_cls, double inv_aff, float* __restrict__ loss2) {
   __shared__ double s_cls[32], s_aff[32];
   double c = 0.0, a = 0.0;
-  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
-    const float v = partials[r];
-    if (r % N == 0) c += (double)v; else a += (double)v;
+  for (int r = threadIdx.x; r < nparts; r += blockDim.x) {
+    const float2 v = partials[r];
+    c += (double)v.x;
+    a += (double)v.y;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -179,6 +207,6 @@ extern "C" int acr_consistency_fwd_bwd(const float* attn1, const float* attn2, i
     consistency_rows_kernel<0><<<grid, kWarps * 32, smem, st>>>(attn1, attn2, rows, N, p, w_cls, w_aff, nullptr, nullptr, 0, nullptr, nullptr, 0, partials);
   }
   if (int e = acr::check_launch("consistency_rows_kernel")) return e;
-  consistency_finish_kernel<<<1, 1024, 0, st>>>(partials, rows, N, 1.0 / cnt_cls, 1.0 / cnt_aff, loss2);
+  consistency_finish_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const float2*>(partials), (int)grid, 1.0 / cnt_cls, 1.0 / cnt_aff, loss2);
   return acr::check_launch("consistency_finish_kernel");
 }

@@ -378,8 +378,14 @@ class ACR(nn.Module):
         x_patch = layer_4[:, 1:, :]
         x_cls = self.cls_head(x_cls)
         x_patch_cls = self.cls_head(x_patch.mean(dim=1))
-        x_patch_cam = F.relu(self.cls_head(x_patch))
+        x_patch_cam = self._patch_cam(x_patch)
         return x_cls, x_patch_cls, attn, x_patch_cam
+
+    def _patch_cam(self, x_patch):
+        """relu(cls_head(x_patch)), DPT/ACR.py:133-134, on the tensor cores (csrc/refine_tc.cu) when the tokens live on a GPU."""
+        if x_patch.is_cuda and x_patch.dtype == torch.float32 and x_patch.stride(2) == 1 and self.cls_head.out_features <= 128:
+            return ops.patch_cam(x_patch, self.cls_head.weight, self.cls_head.bias)
+        return F.relu(self.cls_head(x_patch))
 
     def forward_cam_batched(self, x, replicas, start_layer):
         """forward_cam with the blocks >= start_layer run on `replicas` identical copies of every sample (batched GETAM,
@@ -411,7 +417,7 @@ class ACR(nn.Module):
         with torch.no_grad():
             x_patch = layer_4[::replicas, 1:, :]
             x_patch_cls = self.cls_head(x_patch.mean(dim=1))
-            x_patch_cam = F.relu(self.cls_head(x_patch))
+            x_patch_cam = self._patch_cam(x_patch)
         return x_cls, x_patch_cls, stack, x_patch_cam
 
     def backward_for_getam_batched(self, x_cls, classes):

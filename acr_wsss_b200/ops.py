@@ -703,6 +703,53 @@ def affinity_apply(A, cam, t=1):
     return out
 
 
+def affinity_refine_tc(attn, cam, t=1, normalize=False):
+    """attn [B,L,N,N], cam [B,N-1,C] -> (sum_l attn[:,l,1:,1:])^t cam on the tensor cores (infer_cam.py:164-165,184): the block sum,
+    the contraction for all classes and the row normalisation in one tcgen05 kernel per power (csrc/refine_tc.cu)."""
+    _need_cuda(attn, cam)
+    B, L, N, _ = attn.shape
+    C = cam.shape[-1]
+    attn = attn.contiguous().float()
+    cam = cam.contiguous().float()
+    out = torch.empty_like(cam)
+    nbytes = _lib.lib().acr_affinity_refine_tc_workspace(B, N, C, int(t))
+    ws = torch.empty(nbytes, device=attn.device, dtype=torch.uint8) if nbytes else None
+    _call("acr_affinity_refine_tc", int(t), _p(attn), B, L, N, _p(cam), C, int(t), int(bool(normalize)), _p(out), _p(ws), nbytes, _stream())
+    return out
+
+
+class _PatchCam(torch.autograd.Function):
+    """relu(tokens . W^T + b) through acr_patch_cam_tc; the backward (nobody on the reference path uses it: infer_cam.py:158
+    detaches the result at once) is the plain closed form."""
+
+    @staticmethod
+    def forward(ctx, tokens, weight, bias):
+        B, M, E = tokens.shape
+        C = weight.shape[0]
+        out = torch.empty(B, M, C, device=tokens.device, dtype=torch.float32)
+        w = weight.detach().contiguous().float()
+        bv = None if bias is None else bias.detach().contiguous().float()
+        _call("acr_patch_cam_tc", 1, _p(tokens), tokens.stride(0), tokens.stride(1), B, M, E, _p(w), _p(bv), C, 1, _p(out), _stream())
+        ctx.save_for_backward(tokens, weight, out)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        tokens, weight, out = ctx.saved_tensors
+        dz = dy * (out > 0)
+        dx = dz @ weight.float()
+        dw = dz.flatten(0, 1).t() @ tokens.flatten(0, 1)
+        return dx, dw.to(weight.dtype), (dz.sum((0, 1)) if ctx.has_bias else None)
+
+
+def patch_cam(tokens, weight, bias):
+    """DPT/ACR.py:133-134: x_patch_cam = relu(cls_head(x_patch)), tokens [B,M,E] fp32 (any batch / row strides, unit inner stride)."""
+    _need_cuda(tokens, weight)
+    assert tokens.dtype == torch.float32 and tokens.stride(2) == 1
+    return _PatchCam.apply(tokens, weight, bias)
+
+
 # ----------------------------------------------------------------------------------------------
 # (a10) PAMR, (a11) bilateral
 # ----------------------------------------------------------------------------------------------

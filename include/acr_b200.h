@@ -189,6 +189,22 @@ int acr_affinity_sum(const float* attn, int B, int L, int N, int normalize, floa
 int acr_affinity_refine(const float* A, const float* cam, int B, int Np, int C, int t,
                         float* out, float* tmp, void* stream);
 
+/* The same two steps fused and on the tensor cores (sm_100a, tcgen05 / TMEM; north star item 3):
+ *   out [B,Np,C] = A^t cam with A = sum_l attn[:,l,1:,1:] summed while it is read (never materialised for t = 1);
+ *   normalize != 0 divides every application by the row sums of A (= row-normalised affinity power).
+ * fp32 operands are split into bf16 hi + lo parts (3 MMAs, fp32 accumulate): relative error ~2^-16.
+ * C + (normalize ? 1 : 0) <= 128.  workspace: acr_affinity_refine_tc_workspace() bytes, 256-byte aligned, only for t > 1. */
+size_t acr_affinity_refine_tc_workspace(int B, int N, int C, int t);
+int acr_affinity_refine_tc(const float* attn, int B, int L, int N, const float* cam, int C, int t, int normalize,
+                           float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Patch CAM on the tensor cores: out [B,M,C] = (relu)(tokens . weight^T + bias).  Replaces
+ * F.relu(self.cls_head(x_patch)), DPT/ACR.py:133-134 (x_patch = layer_4[:,1:,:]).
+ * tokens: fp32, element (b,i,k) at tokens + b*tok_batch_stride + i*tok_row_stride + k (pass the pointer to token 1);
+ * weight [C,E] and bias [C] (nullable) as nn.Linear stores them; C <= 128.  Same bf16 hi/lo split as above. */
+int acr_patch_cam_tc(const float* tokens, long long tok_batch_stride, long long tok_row_stride, int B, int M, int E,
+                     const float* weight, const float* bias, int C, int relu, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (a10) PAMR.  Replaces PAMR.forward, pamr.py:125-144, including the bilinear (align_corners=True)
  * up-sampling of the mask (pamr.py:126): x [B,K,H,W] image, mask [B,C,mh,mw], dilations_host[nd] on
