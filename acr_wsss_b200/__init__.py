@@ -12,7 +12,7 @@ All compute goes through libacr_b200.so (csrc/, C ABI in include/acr_b200.h); th
 """
 from . import _lib, ops  # noqa: F401
 from .model import ACR, Attention, Block, VisionTransformer  # noqa: F401
-from .losses import acr_consistency_loss, acr_total_loss, dense_crf_loss  # noqa: F401
+from .losses import acr_consistency_loss, acr_total_loss, dense_crf_loss, dense_crf_loss_from_patch_logits  # noqa: F401
 from .cam import affinity_refine, infer_cam_image, infer_cam_batch, normalize_cam, pseudo_label, save_cam_dict, load_cam_dict, label_iou  # noqa: F401
 from .pamr import PAMR  # noqa: F401
 from .train import Trainer, PolyOptimizer  # noqa: F401

@@ -16,19 +16,36 @@
 // the splat additions (float atomics here; differences are ~1e-7 relative), and filtering all K planes in one
 // pass (the planes are independent and the filter is linear; the reference loops K times with value_size=1).
 //
-// Data layout in HBM (per image, carved from the caller's workspace):
-//   ckey  [6*HW] 3 x u32   packed int16 key of every (pixel, remainder) candidate
-//   bary  [6*HW] f32       barycentric weight of the candidate
-//   table [cap]  i32       open-addressing hash: representative candidate index or -1 (cap = pow2 >= 12*HW)
-//   rep   [6*HW] i32       candidate -> representative candidate; later overwritten by vertex id + 1
-//   vid   [6*HW] i32       representative candidate -> dense vertex id
-//   vcand [6*HW] i32       vertex id -> representative candidate
-//   nbr   [6][6*HW] int2   blur neighbours (vertex id + 1; 0 = missing)
-//   val0/val1 [(6*HW+1) * K] f32   lattice values, vertex-major with the K planes contiguous; slot 0 = zeros
+// Six launches per batch of up to 8 images (grid.z = image); round 1 needed 13 launches + 16 memsets and 450 us at N = 8, K = 21:
+//   embed      per pixel: 6 candidate keys + barycentric weights, written plane-major (candidate c = r*HWp + pixel, so every
+//              store is coalesced); the same threads clear the hash table and the vertex counter
+//   insert     per candidate; neighbouring pixels mostly fall on the same lattice vertex, so a warp first groups its lanes by
+//              key (__match_any_sync on a 32-bit hash, verified against the group leader's key) and only leaders probe the table
+//   prepare    one persistent launch for three independent jobs: blur neighbours of every vertex (2 table lookups per
+//              (vertex, axis)), candidate -> vertex id + 1, zeroing of the value arrays
+//   splat      a CTA sorts the 768 (pixel, remainder) pairs of its 16 x 8 pixel block by vertex in shared memory (integer atomics
+//              only) and issues ONE red.global.add.v4.f32 per (vertex, 4 planes) (K padded to a multiple of 4: 16-byte value rows)
+//   blur       all d+1 passes in one launch: one 8-CTA cluster per image, cluster barriers between the passes, values read
+//              through L2 (ld.global.cg: the ping-pong buffers are rewritten by other CTAs of the cluster)
+//   slice      per (pixel, 4 planes): six 128-bit gathers, same accumulation order as the reference
+//
+// Data layout in HBM (per image, carved from the caller's workspace; nc = 6*HWp candidates, HWp = HW rounded up to 4):
+//   ka,kb,kc [nc] u32      packed int16 key of every candidate (k0|k1<<16, k2|k3<<16, k4)
+//   bary  [nc] f32         barycentric weight of the candidate
+//   table [cap]  i32       open-addressing hash: representative candidate index or -1 (cap = pow2 >= 1.25*nc)
+//   rep   [nc] i32         candidate -> representative candidate; `offs` = vertex id + 1 is a separate array
+//   vid   [nc] i32         representative candidate -> dense vertex id
+//   vcand [nc] i32         vertex id -> representative candidate
+//   nbr   [6][nc] int2     blur neighbours (vertex id + 1; 0 = missing)
+//   val0/val1 [(nc+1) * Kp] f32   lattice values, vertex-major with the Kp = roundup(K, 4) planes contiguous; slot 0 = zeros
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <cmath>
+#include <mutex>
 #include <vector>
 #include <type_traits>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -44,6 +61,28 @@ __device__ __forceinline__ T* img_ptr(T* base, size_t stride_bytes, int n) {
 
 struct Scales { float s[D5]; };
 
+// per-image arrays (pointers of image 0; image n lives `ws` bytes further)
+struct Lattice {
+  uint32_t *ka, *kb, *kc;
+  float* bary;
+  int *table, *rep, *offs, *vid, *vcand, *counter;
+  int2* nbr;
+  float *val0, *val1;
+  uint32_t cap;
+  size_t ws;
+  int nc, Kp;
+};
+__device__ __forceinline__ Lattice for_image(const Lattice& l, int n) {
+  Lattice r = l;
+  r.ka = img_ptr(l.ka, l.ws, n); r.kb = img_ptr(l.kb, l.ws, n); r.kc = img_ptr(l.kc, l.ws, n);
+  r.bary = img_ptr(l.bary, l.ws, n);
+  r.table = img_ptr(l.table, l.ws, n); r.rep = img_ptr(l.rep, l.ws, n); r.offs = img_ptr(l.offs, l.ws, n);
+  r.vid = img_ptr(l.vid, l.ws, n); r.vcand = img_ptr(l.vcand, l.ws, n); r.counter = img_ptr(l.counter, l.ws, n);
+  r.nbr = img_ptr(l.nbr, l.ws, n);
+  r.val0 = img_ptr(l.val0, l.ws, n); r.val1 = img_ptr(l.val1, l.ws, n);
+  return r;
+}
+
 __device__ __forceinline__ Key pack_key(const short* k) {
   Key r;
   r.a = (uint32_t)(uint16_t)k[0] | ((uint32_t)(uint16_t)k[1] << 16);
@@ -57,23 +96,28 @@ __device__ __forceinline__ void unpack_key(const Key& r, short* k) {
   k[4] = (short)(r.c & 0xffff);
 }
 __device__ __forceinline__ bool key_eq(const Key& x, const Key& y) { return x.a == y.a && x.b == y.b && x.c == y.c; }
-__device__ __forceinline__ uint32_t key_hash(const short* k) {
-  uint64_t r = 0;
-#pragma unroll
-  for (int i = 0; i < D5; ++i) { r += (uint64_t)(int64_t)k[i]; r *= 1664525ull; }
-  return (uint32_t)(r ^ (r >> 32));
+// 32-bit mix of the packed key (the reference's multiplicative hash, permutohedral.cpp:42-49, costs five 64-bit multiplies per
+// probe; the hash function is free to choose -- results are indexed by key)
+__device__ __forceinline__ uint32_t key_hash(const Key& key) {
+  uint32_t h = key.a * 0x9E3779B1u;
+  h = (h ^ (h >> 15)) + key.b * 0x85EBCA77u;
+  h = (h ^ (h >> 13)) + key.c * 0xC2B2AE3Du;
+  h ^= h >> 16;
+  return h * 0x27D4EB2Fu;
 }
+__device__ __forceinline__ Key load_key(const Lattice& l, int c) { return Key{l.ka[c], l.kb[c], l.kc[c]}; }
 
-// Step 1: per pixel, lattice coordinates -> 6 candidate keys + barycentric weights.
+// Step 1: per pixel, lattice coordinates -> 6 candidate keys + barycentric weights (plane-major: candidate r*HWp + pixel).
 __global__ void __launch_bounds__(256)
-lattice_embed_kernel(const float* __restrict__ image, int H, int W, int HWpad, float sigmargb, float sigmaxy, Scales sc,
-                     Key* __restrict__ ckey, float* __restrict__ bary_out, size_t ws) {
+lattice_embed_kernel(const float* __restrict__ image, int H, int W, int HWpad, float sigmargb, float sigmaxy, Scales sc, Lattice lat0) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int HW = H * W;
+  const Lattice lat = for_image(lat0, blockIdx.z);
+  // the hash table and the vertex counter of this image are cleared by the same launch
+  for (uint32_t e = idx; e < lat.cap; e += gridDim.x * blockDim.x) lat.table[e] = -1;
+  if (idx == 0) *lat.counter = 0;
   if (idx >= HWpad) return;
   image += (size_t)blockIdx.z * 3 * HW;
-  ckey = img_ptr(ckey, ws, blockIdx.z);
-  bary_out = img_ptr(bary_out, ws, blockIdx.z);
   const int px = idx % W, py = idx / W;
   float f[D5];
   if (idx < HW) {
@@ -155,199 +199,331 @@ lattice_embed_kernel(const float* __restrict__ image, int H, int W, int HWpad, f
       const int canon = (rk <= D5 - r) ? r : r - D6;     // canonical[r*(d+1) + rk]
       key[i] = (short)((int)rem0[i] + canon);
     }
-    ckey[(size_t)idx * D6 + r] = pack_key(key);
-    bary_out[(size_t)idx * D6 + r] = bary[r];
+    const Key k = pack_key(key);
+    const size_t c = (size_t)r * HWpad + idx;
+    lat.ka[c] = k.a; lat.kb[c] = k.b; lat.kc[c] = k.c;
+    lat.bary[c] = bary[r];
   }
 }
 
 // Step 2: insert every candidate; the CAS winner of a slot becomes the representative and draws a dense id.
-__global__ void __launch_bounds__(256)
-lattice_insert_kernel(const Key* __restrict__ ckey, int ncand, int* __restrict__ table, uint32_t mask,
-                      int* __restrict__ rep, int* __restrict__ vid, int* __restrict__ vcand, int* __restrict__ counter, size_t ws) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncand) return;
-  ckey = img_ptr(ckey, ws, blockIdx.z); table = img_ptr(table, ws, blockIdx.z); rep = img_ptr(rep, ws, blockIdx.z);
-  vid = img_ptr(vid, ws, blockIdx.z); vcand = img_ptr(vcand, ws, blockIdx.z); counter = img_ptr(counter, ws, blockIdx.z);
-  const Key k = ckey[c];
-  short ks[D5];
-  unpack_key(k, ks);
-  uint32_t h = key_hash(ks) & mask;
+__device__ __forceinline__ int lattice_insert(const Lattice& lat, const Key& k, uint32_t h, int c) {
+  const uint32_t mask = lat.cap - 1;
+  h &= mask;
   while (true) {
-    int e = ((volatile int*)table)[h];
+    int e = ((volatile int*)lat.table)[h];
     if (e == -1) {
-      e = atomicCAS(&table[h], -1, c);
+      e = atomicCAS(&lat.table[h], -1, c);
       if (e == -1) {
-        const int id = atomicAdd(counter, 1);
-        vid[c] = id;
-        vcand[id] = c;
-        rep[c] = c;
-        return;
+        const int id = atomicAdd(lat.counter, 1);
+        lat.vid[c] = id;
+        lat.vcand[id] = c;
+        return c;
       }
     }
-    if (key_eq(ckey[e], k)) { rep[c] = e; return; }
+    if (key_eq(load_key(lat, e), k)) return e;
     h = (h + 1) & mask;
   }
 }
 
-// Step 3: candidate -> (vertex id + 1).
 __global__ void __launch_bounds__(256)
-lattice_offset_kernel(int* __restrict__ rep, const int* __restrict__ vid, int ncand, size_t ws) {
+lattice_insert_kernel(Lattice lat0) {
+  const Lattice lat = for_image(lat0, blockIdx.z);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncand) return;
-  rep = img_ptr(rep, ws, blockIdx.z); vid = img_ptr(vid, ws, blockIdx.z);
-  rep[c] = vid[rep[c]] + 1;
+  const int lane = threadIdx.x & 31;
+  const bool valid = c < lat.nc;
+  Key k{0u, 0u, 0u};
+  uint32_t h = 0x80000000u | (uint32_t)lane;          // lanes past the end: a group of their own, never inserted
+  if (valid) { k = load_key(lat, c); h = key_hash(k) & 0x7fffffffu; }
+  // lanes of a warp are consecutive pixels of one remainder plane: most of them share a vertex.  Group by hash, check the key
+  // against the group leader's; only leaders (and the rare hash-equal, key-different lane) walk the table.
+  const unsigned peers = __match_any_sync(0xffffffffu, h);
+  const int leader = __ffs(peers) - 1;
+  const Key kl{__shfl_sync(0xffffffffu, k.a, leader), __shfl_sync(0xffffffffu, k.b, leader), __shfl_sync(0xffffffffu, k.c, leader)};
+  const bool own = valid && (lane == leader || !key_eq(k, kl));
+  int res = -1;
+  if (own) res = lattice_insert(lat, k, h, c);
+  __syncwarp();
+  const int lead_res = __shfl_sync(0xffffffffu, res, leader);
+  if (valid) lat.rep[c] = own ? res : lead_res;
 }
 
-__device__ __forceinline__ int lattice_find(const Key* __restrict__ ckey, const int* __restrict__ table, uint32_t mask,
-                                            const int* __restrict__ vid, const short* ks) {
+__device__ __forceinline__ int lattice_find(const Lattice& lat, const short* ks) {
   const Key k = pack_key(ks);
-  uint32_t h = key_hash(ks) & mask;
+  const uint32_t mask = lat.cap - 1;
+  uint32_t h = key_hash(k) & 0x7fffffffu & mask;
   while (true) {
-    const int e = table[h];
+    const int e = lat.table[h];
     if (e == -1) return 0;
-    if (key_eq(ckey[e], k)) return vid[e] + 1;
+    if (key_eq(load_key(lat, e), k)) return lat.vid[e] + 1;
     h = (h + 1) & mask;
   }
 }
 
-// Step 4: blur neighbours of every vertex along each of the d+1 axes.  One thread per (vertex, axis).
+// Step 3 (one persistent launch, three independent jobs): blur neighbours of every vertex along each of the d+1 axes,
+// candidate -> vertex id + 1, zero-fill of the value arrays (val0 entirely, slot 0 of val1).
 __global__ void __launch_bounds__(256)
-lattice_neighbors_kernel(const Key* __restrict__ ckey, const int* __restrict__ table, uint32_t mask,
-                         const int* __restrict__ vid, const int* __restrict__ vcand, const int* __restrict__ counter,
-                         int stride, int2* __restrict__ nbr, size_t ws) {
-  ckey = img_ptr(ckey, ws, blockIdx.z); table = img_ptr(table, ws, blockIdx.z); vid = img_ptr(vid, ws, blockIdx.z);
-  vcand = img_ptr(vcand, ws, blockIdx.z); counter = img_ptr(counter, ws, blockIdx.z); nbr = img_ptr(nbr, ws, blockIdx.z);
-  const int M = *counter;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int v = t / D6, j = t % D6;
-  if (v >= M) return;
-  short key[D5], n1[D5], n2[D5];
-  unpack_key(ckey[vcand[v]], key);
+lattice_prepare_kernel(Lattice lat0) {
+  const Lattice lat = for_image(lat0, blockIdx.z);
+  const int M = *lat.counter;
+  const int nthreads = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  int* nbr1 = reinterpret_cast<int*>(lat.nbr);
+  for (int t = t0; t < M * D6 * 2; t += nthreads) {      // one table lookup per thread step: (vertex, axis, side)
+    const int side = t & 1, vj = t >> 1;
+    const int v = vj / D6, j = vj - v * D6;
+    short key[D5], nk[D5];
+    unpack_key(load_key(lat, lat.vcand[v]), key);
 #pragma unroll
-  for (int k = 0; k < D5; ++k) { n1[k] = key[k] - 1; n2[k] = key[k] + 1; }
+    for (int k = 0; k < D5; ++k) nk[k] = side ? key[k] + 1 : key[k] - 1;
 #pragma unroll
-  for (int k = 0; k < D5; ++k)
-    if (k == j) { n1[k] = key[k] + D5; n2[k] = key[k] - D5; }
-  int2 r;
-  r.x = lattice_find(ckey, table, mask, vid, n1);
-  r.y = lattice_find(ckey, table, mask, vid, n2);
-  nbr[(size_t)j * stride + v] = r;
-}
-
-__global__ void __launch_bounds__(256)
-zero_values_kernel(float* __restrict__ v0, float* __restrict__ v1, const int* __restrict__ counter, int K, size_t ws) {
-  v0 = img_ptr(v0, ws, blockIdx.z); v1 = img_ptr(v1, ws, blockIdx.z); counter = img_ptr(counter, ws, blockIdx.z);
-  const long long n = ((long long)(*counter) + 1) * K;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    v0[i] = 0.f;
-    v1[i] = 0.f;
+    for (int k = 0; k < D5; ++k)
+      if (k == j) nk[k] = side ? key[k] - D5 : key[k] + D5;
+    nbr1[2 * ((size_t)j * lat.nc + v) + side] = lattice_find(lat, nk);
   }
+  for (int c = t0; c < lat.nc; c += nthreads) lat.offs[c] = lat.vid[lat.rep[c]] + 1;
+  const long long nz = ((long long)M + 1) * lat.Kp / 4;
+  float4* z0 = reinterpret_cast<float4*>(lat.val0);
+  for (long long i = t0; i < nz; i += nthreads) z0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t0 < lat.Kp) lat.val1[t0] = 0.f;
 }
 
-constexpr int kPixTile = 32;
+__device__ __forceinline__ void red_add_v4(float* addr, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
-// Splat: block = 32 pixels; planes staged through smem so that both the plane-major input reads and the
-// vertex-major value updates are coalesced.
+constexpr int kPixTile = 128;      // pixels per CTA (splat: 16 x 8 block of the image; slice: 128 consecutive pixels)
+constexpr int kTileW = 16, kTileH = 8;
+constexpr int kSlotProbes = 8;
+
+// Splat.  A CTA owns a 16 x 8 block of pixels: its 768 (pixel, remainder) pairs fall on ~100-200 distinct lattice vertices.  Float
+// atomics at L2 bounded the first version (50 M of them for N = 8, K = 21), and shared-memory float atomics are CAS loops (4x
+// slower still, measured), so the pairs are SORTED by vertex inside the CTA with integer shared-memory atomics only:
+//   1. input planes -> shared memory, transposed to tile4[pixel][quad] (float4 = 4 consecutive planes; odd row stride);
+//   2. every pair finds its vertex's slot in a small open-addressing table (atomicCAS) and draws a position in the slot (atomicAdd);
+//   3. exclusive scan of the slot counts, pairs scattered to order[] (counting sort);
+//   4. one work item per (occupied slot, quad) sums its pairs from the tile and issues ONE red.global.add.v4.f32.
+// Pairs that find no slot within kSlotProbes probes add to global memory directly (rare).
+constexpr int kSplatSlots = 256;     // = blockDim (the scan below is one element per thread)
 __global__ void __launch_bounds__(256)
-lattice_splat_kernel(const float* __restrict__ in, int K, int HW, const int* __restrict__ offs,
-                     const float* __restrict__ bary, float* __restrict__ values, size_t ws) {
-  extern __shared__ float tile[];   // [kPixTile][K+1]
+lattice_splat_kernel(const float* __restrict__ in, int K, int H, int W, int HWpad, Lattice lat0) {
+  extern __shared__ float4 smem4[];                    // tile4[kPixTile][Qs], then the int / float arrays below
+  __shared__ int skey[kSplatSlots], scount[kSplatSlots], sstart[kSplatSlots], socc[kSplatSlots], warp_tot[8], warp_occ[8], n_occ;
+  const Lattice lat = for_image(lat0, blockIdx.z);
+  const int HW = H * W, Kp = lat.Kp, Q = Kp / 4;
   in += (size_t)blockIdx.z * K * HW;
-  offs = img_ptr(offs, ws, blockIdx.z); bary = img_ptr(bary, ws, blockIdx.z); values = img_ptr(values, ws, blockIdx.z);
-  const int p0 = blockIdx.x * kPixTile;
-  const int KP = K + 1;
-  for (int e = threadIdx.x; e < K * kPixTile; e += blockDim.x) {
-    const int k = e / kPixTile, p = e % kPixTile;
-    tile[p * KP + k] = (p0 + p < HW) ? __ldg(in + (size_t)k * HW + p0 + p) : 0.f;
+  const int Qs = Q | 1;                                 // odd row stride (in float4): conflict-free 128-bit stores
+  const float* tile = reinterpret_cast<const float*>(smem4);
+  int* slot = reinterpret_cast<int*>(smem4 + (size_t)Qs * kPixTile);      // [D6 * kPixTile]: slot of the pair, -1 = none
+  int* pos = slot + D6 * kPixTile;                                        // position inside the slot
+  int* order = pos + D6 * kPixTile;                                       // pair indices sorted by slot
+  float* wts = reinterpret_cast<float*>(order + D6 * kPixTile);
+  const int tiles_x = (W + kTileW - 1) / kTileW;
+  const int x0 = (blockIdx.x % tiles_x) * kTileW, y0 = (blockIdx.x / tiles_x) * kTileH;
+  skey[threadIdx.x] = 0;
+  scount[threadIdx.x] = 0;
+  for (int e = threadIdx.x; e < Q * kPixTile; e += blockDim.x) {      // four coalesced plane reads -> one 16-byte store
+    const int q = e / kPixTile, p = e - q * kPixTile;
+    const int x = x0 + (p % kTileW), y = y0 + (p / kTileW);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (4 * q + j < K && x < W && y < H) ? __ldg(in + (size_t)(4 * q + j) * HW + (size_t)y * W + x) : 0.f;
+    smem4[p * Qs + q] = make_float4(v[0], v[1], v[2], v[3]);
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int p = w; p < kPixTile; p += nw) {
-    const int pix = p0 + p;
-    if (pix >= HW) break;
-#pragma unroll
-    for (int r = 0; r < D6; ++r) {
-      const int o = __ldg(offs + (size_t)pix * D6 + r);
-      const float wt = __ldg(bary + (size_t)pix * D6 + r);
-      float* dst = values + (size_t)o * K;
-      for (int k = lane; k < K; k += 32) atomicAdd(dst + k, __fmul_rn(wt, tile[p * KP + k]));
+  for (int w = threadIdx.x; w < D6 * kPixTile; w += blockDim.x) {
+    const int p = w % kPixTile, r = w / kPixTile;
+    const int x = x0 + (p % kTileW), y = y0 + (p / kTileW);
+    int sl = -1;
+    float wt = 0.f;
+    if (x < W && y < H) {
+      const int pix = y * W + x;
+      const int o = __ldg(lat.offs + (size_t)r * HWpad + pix);
+      wt = __ldg(lat.bary + (size_t)r * HWpad + pix);
+      const uint32_t h = ((uint32_t)o * 0x9E3779B1u) >> 7;
+      for (int t = 0; t < kSlotProbes; ++t) {
+        const int i = (int)((h + t) & (uint32_t)(kSplatSlots - 1));
+        const int prev = atomicCAS(&skey[i], 0, o);
+        if (prev == 0 || prev == o) { sl = i; break; }
+      }
+      if (sl >= 0) {
+        pos[w] = atomicAdd(&scount[sl], 1);
+      } else {                                          // table neighbourhood full: this pair adds to global memory itself
+        for (int k = 0; k < K; ++k) atomicAdd(lat.val0 + (size_t)o * Kp + k, wt * tile[(p * Qs + (k >> 2)) * 4 + (k & 3)]);
+      }
     }
+    slot[w] = sl;
+    wts[w] = wt;
+  }
+  __syncthreads();
+  {   // exclusive scan of scount (one slot per thread) and compaction of the occupied slots
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int c = scount[threadIdx.x];
+    int v = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += n;
+    }
+    const unsigned occ = __ballot_sync(0xffffffffu, c > 0);
+    if (lane == 31) warp_tot[wp] = v;
+    if (lane == 0) warp_occ[wp] = __popc(occ);
+    __syncthreads();
+    int base = 0, obase = 0;
+    for (int i = 0; i < wp; ++i) { base += warp_tot[i]; obase += warp_occ[i]; }
+    sstart[threadIdx.x] = base + v - c;
+    if (c > 0) socc[obase + __popc(occ & ((1u << lane) - 1u))] = threadIdx.x;
+    if (threadIdx.x == blockDim.x - 1) n_occ = obase + __popc(occ);
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < D6 * kPixTile; w += blockDim.x) {
+    const int sl = slot[w];
+    if (sl >= 0) order[sstart[sl] + pos[w]] = w;
+  }
+  __syncthreads();
+  const int nitems = n_occ * Q;
+  for (int w = threadIdx.x; w < nitems; w += blockDim.x) {
+    const int sidx = socc[w / Q], q = w % Q;
+    const int beg = sstart[sidx], n = scount[sidx];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < n; ++j) {
+      const int pw = order[beg + j];
+      const float wt = wts[pw];
+      const float4 x = smem4[(pw % kPixTile) * Qs + q];
+      acc.x = fmaf(wt, x.x, acc.x); acc.y = fmaf(wt, x.y, acc.y); acc.z = fmaf(wt, x.z, acc.z); acc.w = fmaf(wt, x.w, acc.w);
+    }
+    red_add_v4(lat.val0 + (size_t)skey[sidx] * Kp + 4 * q, acc);
   }
 }
 
-// One blur pass along axis j: new = old + 0.5 * (old[n1] + old[n2]).  One thread per (vertex, plane).
-__global__ void __launch_bounds__(256)
-lattice_blur_kernel(const float* __restrict__ oldv, float* __restrict__ newv, const int2* __restrict__ nbr,
-                    const int* __restrict__ counter, int K, size_t ws) {
-  oldv = img_ptr(oldv, ws, blockIdx.z); newv = img_ptr(newv, ws, blockIdx.z); nbr = img_ptr(nbr, ws, blockIdx.z);
-  counter = img_ptr(counter, ws, blockIdx.z);
-  const long long M = *counter;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < M * K; t += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(t / K), k = (int)(t % K);
-    const int2 nb = __ldg(nbr + v);
-    const float a = oldv[(size_t)nb.x * K + k], b = oldv[(size_t)nb.y * K + k];
-    newv[(size_t)(v + 1) * K + k] = __fadd_rn(oldv[(size_t)(v + 1) * K + k], __fmul_rn(0.5f, __fadd_rn(a, b)));
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// All d+1 blur passes of one image: new = old + 0.5 * (old[n1] + old[n2]) along axis j, j = 0..d in turn.  One cluster of
+// kBlurCtas CTAs per image; the passes are separated by cluster barriers (release / acquire at cluster scope), and the values
+// are read with ld.global.cg because the buffer a pass reads was written by other CTAs one pass earlier.
+constexpr int kBlurCtas = 8, kBlurThreads = 1024, kBlurIlp = 4;
+__global__ void __launch_bounds__(kBlurThreads)
+lattice_blur_kernel(Lattice lat0) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const Lattice lat = for_image(lat0, blockIdx.z);
+  const long long M = *lat.counter;
+  const int Q = lat.Kp / 4;
+  const long long total = M * Q;
+  const int nthreads = kBlurCtas * kBlurThreads, t0 = (int)cluster.block_rank() * kBlurThreads + threadIdx.x;
+  float* oldv = lat.val0;
+  float* newv = lat.val1;
+  for (int j = 0; j < D6; ++j) {
+    const int2* nbr = lat.nbr + (size_t)j * lat.nc;
+    // the chain neighbour ids -> three gathers is pure L2 latency: kBlurIlp independent (vertex, 4 planes) items per thread in flight
+    for (long long t = t0; t < total; t += (long long)kBlurIlp * nthreads) {
+      size_t self[kBlurIlp], n1[kBlurIlp], n2[kBlurIlp];
+      bool ok[kBlurIlp];
+#pragma unroll
+      for (int u = 0; u < kBlurIlp; ++u) {
+        const long long tt = t + (long long)u * nthreads;
+        ok[u] = tt < total;
+        const int v = ok[u] ? (int)(tt / Q) : 0, q = ok[u] ? (int)(tt - (long long)v * Q) : 0;
+        const int2 nb = __ldg(nbr + v);
+        self[u] = (size_t)(v + 1) * lat.Kp + 4 * q;
+        n1[u] = (size_t)nb.x * lat.Kp + 4 * q;
+        n2[u] = (size_t)nb.y * lat.Kp + 4 * q;
+      }
+      float4 a[kBlurIlp], b[kBlurIlp], c[kBlurIlp];
+#pragma unroll
+      for (int u = 0; u < kBlurIlp; ++u) {
+        a[u] = ldcg4(oldv + n1[u]);
+        b[u] = ldcg4(oldv + n2[u]);
+        c[u] = ldcg4(oldv + self[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < kBlurIlp; ++u) {
+        float4 o;
+        o.x = __fadd_rn(c[u].x, __fmul_rn(0.5f, __fadd_rn(a[u].x, b[u].x)));
+        o.y = __fadd_rn(c[u].y, __fmul_rn(0.5f, __fadd_rn(a[u].y, b[u].y)));
+        o.z = __fadd_rn(c[u].z, __fmul_rn(0.5f, __fadd_rn(a[u].z, b[u].z)));
+        o.w = __fadd_rn(c[u].w, __fmul_rn(0.5f, __fadd_rn(a[u].w, b[u].w)));
+        if (ok[u]) *reinterpret_cast<float4*>(newv + self[u]) = o;
+      }
+    }
+    __threadfence();
+    cluster.sync();
+    float* t = oldv; oldv = newv; newv = t;
   }
 }
 
+// Slice: out = alpha * sum_r bary_r * values[vertex_r], accumulated in the reference's order.  A group of G lanes (G = 8, 16 or 32
+// >= Kp/4) serves one pixel: its six vertex ids / weights are loaded once per lane (broadcast inside the group) and every lane
+// gathers 16 bytes of each vertex row, so a row is read with contiguous requests; neighbouring pixels share vertices (L1 hits).
 __global__ void __launch_bounds__(256)
-lattice_slice_kernel(const float* __restrict__ values, int K, int HW, const int* __restrict__ offs,
-                     const float* __restrict__ bary, float alpha, float* __restrict__ out, size_t ws) {
-  extern __shared__ float tile[];   // [kPixTile][K+1]
+lattice_slice_kernel(const float* __restrict__ values_img0, int K, int HW, int HWpad, float alpha, float* __restrict__ out, Lattice lat0) {
+  extern __shared__ float4 smem4[];   // tile4[Kp/4][kPixTile]
+  const Lattice lat = for_image(lat0, blockIdx.z);
+  const float* values = img_ptr(values_img0, lat.ws, blockIdx.z);
   out += (size_t)blockIdx.z * K * HW;
-  values = img_ptr(values, ws, blockIdx.z); offs = img_ptr(offs, ws, blockIdx.z); bary = img_ptr(bary, ws, blockIdx.z);
   const int p0 = blockIdx.x * kPixTile;
-  const int KP = K + 1;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int p = w; p < kPixTile; p += nw) {
-    const int pix = p0 + p;
-    if (pix >= HW) break;
-    int o[D6];
-    float wt[D6];
+  const int Q = lat.Kp / 4;
+  const int G = Q <= 8 ? 8 : (Q <= 16 ? 16 : 32), ppw = 32 / G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = lane % G, lp = lane / G;
+  constexpr int kPixPerWarp = kPixTile / 8;
+  for (int qq = q; qq < Q; qq += G) {                  // (one trip unless K > 128)
+    for (int it = 0; it < kPixPerWarp / ppw; ++it) {
+      const int p = warp * kPixPerWarp + it * ppw + lp;
+      const int pix = p0 + p;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pix < HW) {
+        int o[D6];
+        float wt[D6];
 #pragma unroll
-    for (int r = 0; r < D6; ++r) {
-      o[r] = __ldg(offs + (size_t)pix * D6 + r);
-      wt[r] = __fmul_rn(__ldg(bary + (size_t)pix * D6 + r), alpha);
-    }
-    for (int k = lane; k < K; k += 32) {
-      float s = 0.f;
+        for (int r = 0; r < D6; ++r) {
+          o[r] = __ldg(lat.offs + (size_t)r * HWpad + pix);
+          wt[r] = __fmul_rn(__ldg(lat.bary + (size_t)r * HWpad + pix), alpha);
+        }
+        float4 v[D6];
 #pragma unroll
-      for (int r = 0; r < D6; ++r) s = __fadd_rn(s, __fmul_rn(wt[r], values[(size_t)o[r] * K + k]));
-      tile[p * KP + k] = s;
+        for (int r = 0; r < D6; ++r) v[r] = __ldg(reinterpret_cast<const float4*>(values + (size_t)o[r] * lat.Kp + 4 * qq));
+#pragma unroll
+        for (int r = 0; r < D6; ++r) {
+          s.x = __fadd_rn(s.x, __fmul_rn(wt[r], v[r].x));
+          s.y = __fadd_rn(s.y, __fmul_rn(wt[r], v[r].y));
+          s.z = __fadd_rn(s.z, __fmul_rn(wt[r], v[r].z));
+          s.w = __fadd_rn(s.w, __fmul_rn(wt[r], v[r].w));
+        }
+      }
+      smem4[qq * kPixTile + p] = s;
     }
   }
   __syncthreads();
+  const float* tile = reinterpret_cast<const float*>(smem4);
   for (int e = threadIdx.x; e < K * kPixTile; e += blockDim.x) {
-    const int k = e / kPixTile, p = e % kPixTile;
-    if (p0 + p < HW) out[(size_t)k * HW + p0 + p] = tile[p * KP + k];
+    const int k = e / kPixTile, p = e - k * kPixTile;
+    if (p0 + p < HW) out[(size_t)k * HW + p0 + p] = tile[((k >> 2) * kPixTile + p) * 4 + (k & 3)];
   }
 }
 
-struct Carve {
-  Key* ckey; float* bary; int* table; int* rep; int* vid; int* vcand; int2* nbr; float* val0; float* val1; int* counter;
-  uint32_t cap;
-  size_t total;
-};
-
-Carve carve(void* base, int K, int H, int W) {
-  Carve c{};
+Lattice carve(void* base, int K, int H, int W) {
+  Lattice c{};
   const size_t HW = ((size_t)H * W + 3) / 4 * 4, nc = HW * D6;   // incl. the reference's phantom pad pixels
   uint32_t cap = 1;
-  while (cap < 2 * nc) cap <<= 1;
+  while (cap < nc + nc / 4) cap <<= 1;      // worst case (every candidate a distinct vertex): load factor <= 0.8
   c.cap = cap;
+  c.nc = (int)nc;
+  c.Kp = (K + 3) / 4 * 4;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += acr::align_up(bytes, 256); return (char*)base + o; };
   c.counter = (int*)take(256);
-  c.ckey = (Key*)take(nc * sizeof(Key));
+  c.ka = (uint32_t*)take(nc * sizeof(uint32_t));
+  c.kb = (uint32_t*)take(nc * sizeof(uint32_t));
+  c.kc = (uint32_t*)take(nc * sizeof(uint32_t));
   c.bary = (float*)take(nc * sizeof(float));
   c.table = (int*)take((size_t)cap * sizeof(int));
   c.rep = (int*)take(nc * sizeof(int));
+  c.offs = (int*)take(nc * sizeof(int));
   c.vid = (int*)take(nc * sizeof(int));
   c.vcand = (int*)take(nc * sizeof(int));
   c.nbr = (int2*)take(nc * D6 * sizeof(int2));
-  c.val0 = (float*)take((nc + 1) * K * sizeof(float));
-  c.val1 = (float*)take((nc + 1) * K * sizeof(float));
-  c.total = off;
+  c.val0 = (float*)take((nc + 1) * c.Kp * sizeof(float));
+  c.val1 = (float*)take((nc + 1) * c.Kp * sizeof(float));
+  c.ws = off;
   return c;
 }
 
@@ -358,7 +534,7 @@ constexpr int kBilateralBatch = 8;
 
 extern "C" size_t acr_bilateral_workspace(int N, int K, int H, int W) {
   if (N <= 0 || K <= 0 || H <= 0 || W <= 0) return 0;
-  return carve(nullptr, K, H, W).total * (size_t)(N < kBilateralBatch ? N : kBilateralBatch);
+  return carve(nullptr, K, H, W).ws * (size_t)(N < kBilateralBatch ? N : kBilateralBatch);
 }
 
 extern "C" int acr_bilateral_batch(const float* images, const float* ins, float* outs,
@@ -369,7 +545,7 @@ extern "C" int acr_bilateral_batch(const float* images, const float* ins, float*
   ACR_REQUIRE(sigmargb > 0.f && sigmaxy > 0.f, ACR_E_INVAL, "acr_bilateral_batch: sigma <= 0");
   ACR_REQUIRE((long long)H * W * D6 < (1ll << 28), ACR_E_INVAL, "acr_bilateral_batch: image too large");
   ACR_REQUIRE(((uintptr_t)workspace & 255) == 0, ACR_E_ALIGN, "acr_bilateral_batch: workspace not 256-byte aligned");
-  const Carve c = carve(workspace, K, H, W);
+  const Lattice c = carve(workspace, K, H, W);
   ACR_REQUIRE(workspace_bytes >= acr_bilateral_workspace(N, K, H, W), ACR_E_NOMEM, "acr_bilateral_batch: workspace too small (%zu < %zu)",
               workspace_bytes, acr_bilateral_workspace(N, K, H, W));
   cudaStream_t st = (cudaStream_t)stream;
@@ -380,47 +556,82 @@ extern "C" int acr_bilateral_batch(const float* images, const float* ins, float*
   for (int i = 0; i < D5; ++i) sc.s[i] = (float)(1.0 / std::sqrt((double)((i + 2) * (i + 1))) * inv_std_dev);  // :170-171
   const float alpha = 1.0f / (1.0f + powf(2.f, -(float)D5));                   // :568
 
-  const size_t smem = (size_t)kPixTile * (K + 1) * sizeof(float);
-  ACR_REQUIRE(smem <= 48 * 1024, ACR_E_INVAL, "acr_bilateral_batch: K=%d too large", K);
-  const size_t ws = c.total;
+  const size_t smem = (size_t)kPixTile * c.Kp * sizeof(float);      // slice: output tile
+  ACR_REQUIRE(smem <= 48 * 1024, ACR_E_INVAL, "acr_bilateral_batch: K=%d too large (<= %d planes)", K, 48 * 1024 / (kPixTile * 4));
+  // splat: input tile + four per-pair arrays
+  const size_t smem_splat = (size_t)kPixTile * ((c.Kp / 4) | 1) * 16 + (size_t)D6 * kPixTile * 4 * sizeof(int);
+  {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    ACR_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+      ACR_CUDA(cudaFuncSetAttribute(lattice_splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      attr_set[dev] = true;
+    }
+  }
+  const int splat_tiles = ((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
   for (int n0 = 0; n0 < N; n0 += kBilateralBatch) {
     const int nb = (N - n0 < kBilateralBatch) ? N - n0 : kBilateralBatch;
     const float* img = images + (size_t)n0 * 3 * HW;
     const float* in = ins + (size_t)n0 * K * HW;
     float* out = outs + (size_t)n0 * K * HW;
-    for (int i = 0; i < nb; ++i) {
-      ACR_CUDA(cudaMemsetAsync((char*)c.table + ws * i, 0xff, (size_t)c.cap * sizeof(int), st));
-      ACR_CUDA(cudaMemsetAsync((char*)c.counter + ws * i, 0, sizeof(int), st));
-    }
-    lattice_embed_kernel<<<dim3((HWpad + 255) / 256, 1, nb), 256, 0, st>>>(img, H, W, HWpad, sigmargb, sigmaxy, sc, c.ckey, c.bary, ws);
+    lattice_embed_kernel<<<dim3((HWpad + 255) / 256, 1, nb), 256, 0, st>>>(img, H, W, HWpad, sigmargb, sigmaxy, sc, c);
     if (int e = acr::check_launch("lattice_embed_kernel")) return e;
-    lattice_insert_kernel<<<dim3((nc + 255) / 256, 1, nb), 256, 0, st>>>(c.ckey, nc, c.table, c.cap - 1, c.rep, c.vid, c.vcand, c.counter, ws);
+    lattice_insert_kernel<<<dim3((nc + 255) / 256, 1, nb), 256, 0, st>>>(c);
     if (int e = acr::check_launch("lattice_insert_kernel")) return e;
-    lattice_neighbors_kernel<<<dim3((nc * D6 + 255) / 256, 1, nb), 256, 0, st>>>(c.ckey, c.table, c.cap - 1, c.vid, c.vcand, c.counter, nc, c.nbr, ws);
-    if (int e = acr::check_launch("lattice_neighbors_kernel")) return e;
-    lattice_offset_kernel<<<dim3((nc + 255) / 256, 1, nb), 256, 0, st>>>(c.rep, c.vid, nc, ws);
-    if (int e = acr::check_launch("lattice_offset_kernel")) return e;
-    zero_values_kernel<<<dim3(148, 1, nb), 256, 0, st>>>(c.val0, c.val1, c.counter, K, ws);
-    if (int e = acr::check_launch("zero_values_kernel")) return e;
-    lattice_splat_kernel<<<dim3((HW + kPixTile - 1) / kPixTile, 1, nb), 256, smem, st>>>(in, K, HW, c.rep, c.bary, c.val0, ws);
+    lattice_prepare_kernel<<<dim3(148 * 4, 1, nb), 256, 0, st>>>(c);
+    if (int e = acr::check_launch("lattice_prepare_kernel")) return e;
+    lattice_splat_kernel<<<dim3(splat_tiles, 1, nb), 256, smem_splat, st>>>(in, K, H, W, HWpad, c);
     if (int e = acr::check_launch("lattice_splat_kernel")) return e;
-    float* cur = c.val0;
-    float* nxt = c.val1;
-    for (int j = 0; j < D6; ++j) {
-      lattice_blur_kernel<<<dim3(148, 1, nb), 256, 0, st>>>(cur, nxt, c.nbr + (size_t)j * nc, c.counter, K, ws);
+    {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(kBlurCtas, 1, nb);
+      cfg.blockDim = dim3(kBlurThreads);
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = kBlurCtas;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      ACR_CUDA(cudaLaunchKernelEx(&cfg, lattice_blur_kernel, c));
       if (int e = acr::check_launch("lattice_blur_kernel")) return e;
-      float* t = cur; cur = nxt; nxt = t;
     }
-    lattice_slice_kernel<<<dim3((HW + kPixTile - 1) / kPixTile, 1, nb), 256, smem, st>>>(cur, K, HW, c.rep, c.bary, alpha, out, ws);
+    // d+1 = 6 passes (an even number): the result is back in val0
+    lattice_slice_kernel<<<dim3((HW + kPixTile - 1) / kPixTile, 1, nb), 256, smem, st>>>(c.val0, K, HW, HWpad, alpha, out, c);
     if (int e = acr::check_launch("lattice_slice_kernel")) return e;
     if (lattice_size_host) {
       for (int i = 0; i < nb; ++i)
-        ACR_CUDA(cudaMemcpyAsync(lattice_size_host + n0 + i, (char*)c.counter + ws * i, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ACR_CUDA(cudaMemcpyAsync(lattice_size_host + n0 + i, (char*)c.counter + c.ws * i, sizeof(int), cudaMemcpyDeviceToHost, st));
       ACR_CUDA(cudaStreamSynchronize(st));
     }
   }
   return 0;
 }
+
+// SWIG-shaped host entry (bilateralfilter.cpp:42-55): HOST buffers in, HOST buffer out.  The device buffers, the lattice workspace
+// and the stream are cached per device and only grow (the reference allocates and frees its lattice on every call).
+namespace {
+struct HostCache {
+  float *img = nullptr, *in = nullptr, *out = nullptr;
+  void* ws = nullptr;
+  size_t img_b = 0, io_b = 0, ws_b = 0;
+  cudaStream_t st = nullptr;
+};
+std::mutex g_host_mutex;
+HostCache g_host_cache[64];
+
+cudaError_t grow(void** p, size_t* have, size_t need) {
+  if (*have >= need) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *have = 0;
+  cudaError_t e = cudaMalloc(p, need);
+  if (e == cudaSuccess) *have = need;
+  return e;
+}
+}  // namespace
 
 extern "C" void bilateralfilter_batch_b200(const float* images_host, int len_images, const float* ins_host, int len_ins,
                                            float* outs_host, int len_outs,
@@ -431,31 +642,24 @@ extern "C" void bilateralfilter_batch_b200(const float* images_host, int len_ima
     acr::set_error("bilateralfilter_batch_b200: buffer lengths do not match N=%d K=%d H=%d W=%d", N, K, H, W);
     return;
   }
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || dev < 0 || dev >= 64) { acr::set_error("bilateralfilter_batch_b200: cudaGetDevice: %s", cudaGetErrorString(e)); return; }
+  std::lock_guard<std::mutex> lock(g_host_mutex);
+  HostCache& hc = g_host_cache[dev];
+  auto fail = [&](const char* what) { acr::set_error("bilateralfilter_batch_b200: %s: %s", what, cudaGetErrorString(e)); };
+  if (!hc.st && (e = cudaStreamCreateWithFlags(&hc.st, cudaStreamNonBlocking)) != cudaSuccess) { hc.st = nullptr; return fail("cudaStreamCreate"); }
   const size_t ws_bytes = acr_bilateral_workspace(N, K, H, W);
-  float *d_img = nullptr, *d_in = nullptr, *d_out = nullptr;
-  void* d_ws = nullptr;
-  cudaError_t e = cudaSuccess;
-  cudaStream_t st = nullptr;
-  auto fail = [&](const char* what) {
-    acr::set_error("bilateralfilter_batch_b200: %s: %s", what, cudaGetErrorString(e));
-    cudaFree(d_img); cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws);
-    if (st) cudaStreamDestroy(st);
-  };
-  if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) { st = nullptr; return fail("cudaStreamCreate"); }
-  if ((e = cudaMalloc(&d_img, (size_t)len_images * 4)) != cudaSuccess) return fail("cudaMalloc(images)");
-  if ((e = cudaMalloc(&d_in, (size_t)len_ins * 4)) != cudaSuccess) return fail("cudaMalloc(ins)");
-  if ((e = cudaMalloc(&d_out, (size_t)len_outs * 4)) != cudaSuccess) return fail("cudaMalloc(outs)");
-  if ((e = cudaMalloc(&d_ws, ws_bytes)) != cudaSuccess) return fail("cudaMalloc(workspace)");
-  if ((e = cudaMemcpyAsync(d_img, images_host, (size_t)len_images * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D images");
-  if ((e = cudaMemcpyAsync(d_in, ins_host, (size_t)len_ins * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("H2D ins");
-  const int rc = acr_bilateral_batch(d_img, d_in, d_out, N, K, H, W, sigmargb, sigmaxy, d_ws, ws_bytes, nullptr, st);
-  if (rc != 0) {
-    cudaFree(d_img); cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws); cudaStreamDestroy(st);
-    return;   // error string already set
-  }
-  if ((e = cudaMemcpyAsync(outs_host, d_out, (size_t)len_outs * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return fail("D2H outs");
-  if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail("synchronize");
-  cudaFree(d_img); cudaFree(d_in); cudaFree(d_out); cudaFree(d_ws);
-  cudaStreamDestroy(st);
+  size_t in_b = hc.io_b, out_b = hc.io_b;
+  if ((e = grow((void**)&hc.img, &hc.img_b, (size_t)len_images * 4)) != cudaSuccess) return fail("cudaMalloc(images)");
+  if ((e = grow((void**)&hc.in, &in_b, (size_t)len_ins * 4)) != cudaSuccess) { hc.io_b = 0; return fail("cudaMalloc(ins)"); }
+  if ((e = grow((void**)&hc.out, &out_b, (size_t)len_outs * 4)) != cudaSuccess) { hc.io_b = 0; return fail("cudaMalloc(outs)"); }
+  hc.io_b = in_b < out_b ? in_b : out_b;
+  if ((e = grow(&hc.ws, &hc.ws_b, ws_bytes)) != cudaSuccess) return fail("cudaMalloc(workspace)");
+  if ((e = cudaMemcpyAsync(hc.img, images_host, (size_t)len_images * 4, cudaMemcpyHostToDevice, hc.st)) != cudaSuccess) return fail("H2D images");
+  if ((e = cudaMemcpyAsync(hc.in, ins_host, (size_t)len_ins * 4, cudaMemcpyHostToDevice, hc.st)) != cudaSuccess) return fail("H2D ins");
+  if (acr_bilateral_batch(hc.img, hc.in, hc.out, N, K, H, W, sigmargb, sigmaxy, hc.ws, hc.ws_b, nullptr, hc.st) != 0) return;   // error string already set
+  if ((e = cudaMemcpyAsync(outs_host, hc.out, (size_t)len_outs * 4, cudaMemcpyDeviceToHost, hc.st)) != cudaSuccess) return fail("D2H outs");
+  if ((e = cudaStreamSynchronize(hc.st)) != cudaSuccess) return fail("synchronize");
   acr::set_error("");
 }

@@ -35,16 +35,17 @@ class _DenseCRF(torch.autograd.Function):
     @staticmethod
     def forward(ctx, images, seg, roi, sigma_rgb, sigma_xy):
         N = seg.shape[0]
-        s = seg * roi
+        s = seg if roi is None else seg * roi               # roi None = all ones (no extra passes over the K planes)
         AS = ops.bilateral_filter(images, s, sigma_rgb, sigma_xy)
         ctx.save_for_backward(AS, roi)
         ctx.N = N
-        return -(s * AS).sum() / N
+        return -torch.dot(s.reshape(-1), AS.reshape(-1)) / N
 
     @staticmethod
     def backward(ctx, g):
         AS, roi = ctx.saved_tensors
-        return None, -2.0 * g * AS * roi / ctx.N, None, None, None
+        gs = AS * (-2.0 * g / ctx.N)
+        return None, (gs if roi is None else gs * roi), None, None, None
 
 
 def dense_crf_loss(images, segmentations, rois, weight, sigma_rgb, sigma_xy, scale_factor):
@@ -57,3 +58,16 @@ def dense_crf_loss(images, segmentations, rois, weight, sigma_rgb, sigma_xy, sca
                         recompute_scale_factor=True)
     roi = F.interpolate(rois.unsqueeze(1), scale_factor=scale_factor, recompute_scale_factor=True)
     return weight * _DenseCRF.apply(images, seg, roi, sigma_rgb, sigma_xy * scale_factor)
+
+
+def dense_crf_loss_from_patch_logits(images, logits, weight, sigma_rgb, sigma_xy, scale_factor=0.5):
+    """dense_crf_loss(images, softmax([0, bilinear(logits -> image size)]), ones, ...) for scale_factor = 0.5 without the
+    full-resolution tensors: the probabilities at half resolution come from one fused kernel (ops.crf_head) and the ROI of ones
+    drops out.  images [N,3,S,S] in 0..255, logits [N,P*P,C] patch-token logits (channel-last).  Same value and gradient as the
+    composition (tests/test_gpu_parity.py::test_dense_crf_from_patch_logits_matches_composition)."""
+    assert scale_factor == 0.5, "the fused head implements the rloss-scale 0.5 of the COCO recipe (infer_cam.py:58-65)"
+    S = images.shape[-1]
+    assert images.shape[-2] == S
+    images = F.interpolate(images, scale_factor=scale_factor, recompute_scale_factor=True)
+    seg = ops.crf_head(logits, S)
+    return weight * _DenseCRF.apply(images, seg, None, sigma_rgb, sigma_xy * scale_factor)

@@ -750,6 +750,41 @@ def patch_cam(tokens, weight, bias):
     return _PatchCam.apply(tokens, weight, bias)
 
 
+class _CrfHead(torch.autograd.Function):
+    """Patch-token logits [B,P*P,C] -> probabilities [B,C+1,S/2,S/2] the dense-CRF term filters (csrc/crf_head.cu): bilinear
+    up-sampling to SxS, softmax over [background = 0, classes], bilinear down-sampling by 0.5, fused."""
+
+    @staticmethod
+    def forward(ctx, logits, S):
+        B, PP, C = logits.shape
+        P = int(round(PP ** 0.5))
+        assert P * P == PP and S % 2 == 0
+        logits = logits.contiguous().float()
+        seg = torch.empty(B, C + 1, S // 2, S // 2, device=logits.device, dtype=torch.float32)
+        _call("acr_crf_head_fwd", 1, _p(logits), B, P, C, S, _p(seg), _stream())
+        ctx.save_for_backward(logits)
+        ctx.dims = (B, P, C, S)
+        return seg
+
+    @staticmethod
+    def backward(ctx, g_seg):
+        (logits,) = ctx.saved_tensors
+        B, P, C, S = ctx.dims
+        d_up = torch.empty(B, C, S, S, device=logits.device, dtype=torch.float32)
+        _call("acr_crf_head_bwd", 1, _p(logits), _p(g_seg.contiguous().float()), B, P, C, S, _p(d_up), _stream())
+        if S <= 512:      # gather form of the bilinear backward (the library's scatters with atomics: 16.6 ms at [8,80,448,448])
+            d_patch = torch.empty(B, C, P, P, device=logits.device, dtype=torch.float32)
+            _call("acr_bilinear_up_bwd", 1, _p(d_up), B * C, P, S, _p(d_patch), _stream())
+        else:
+            d_patch = torch.ops.aten.upsample_bilinear2d_backward(d_up, [S, S], [B, C, P, P], False, None, None)
+        return d_patch.flatten(2).transpose(1, 2), None
+
+
+def crf_head(logits, S):
+    _need_cuda(logits)
+    return _CrfHead.apply(logits, S)
+
+
 # ----------------------------------------------------------------------------------------------
 # (a10) PAMR, (a11) bilateral
 # ----------------------------------------------------------------------------------------------
@@ -781,7 +816,7 @@ def bilateral_filter(images, ins, sigmargb, sigmaxy, return_lattice_size=False):
     ws = torch.empty(wsb + 256, device=ins.device, dtype=torch.uint8)
     off = (-ws.data_ptr()) % 256
     msz = (ctypes.c_int * N)() if return_lattice_size else None
-    _call("acr_bilateral_batch", 14, _p(images), _p(ins), _p(outs), N, K, H, W, float(sigmargb), float(sigmaxy),
+    _call("acr_bilateral_batch", 6 * ((N + 7) // 8), _p(images), _p(ins), _p(outs), N, K, H, W, float(sigmargb), float(sigmaxy),
                                               ctypes.c_void_p(ws.data_ptr() + off), wsb, msz, _stream())
     if return_lattice_size:
         return outs, list(msz)

@@ -202,16 +202,20 @@ class Trainer:
     def _dense_crf_term(self, img, cls_list):
         """DenseCRF regulariser (losses.dense_crf_loss over this repo's permutohedral filter) for the step's first view."""
         import torch.nn.functional as F
-        from .losses import dense_crf_loss
+        from .losses import dense_crf_loss, dense_crf_loss_from_patch_logits
         o = self.dense_crf
         B, _, S, _ = img.shape
         p = S // 16
         layer_4 = self.model.pretrained.activations["4"][:B]                  # view 1 (both views ran as one batch of 2B)
         logits = self.model.cls_head(layer_4[:, 1:, :])                         # [B, p*p, C] patch-token logits (DPT/ACR.py:133-134)
+        ori = (img * o["std"] + o["mean"]).clamp(0.0, 255.0)
+        if o["scale"] == 0.5 and S % 2 == 0 and img.is_cuda:
+            # up-sampling, softmax over [background, classes] and the rloss down-scaling as one kernel: the [B,C+1,S,S] tensors
+            # of the composition below (0.5 GB each at 448x448, C = 80, six passes forward and backward) never exist
+            return dense_crf_loss_from_patch_logits(ori, logits, o["weight"], o["sigma_rgb"], o["sigma_xy"], o["scale"])
         logits = logits.permute(0, 2, 1).reshape(B, -1, p, p)
         logits = F.interpolate(logits, (S, S), mode="bilinear", align_corners=False)
         seg = torch.softmax(torch.cat([torch.zeros_like(logits[:, :1]), logits], dim=1), dim=1)      # K = C + 1, background first
-        ori = (img * o["std"] + o["mean"]).clamp(0.0, 255.0)
         roi = torch.ones(B, S, S, device=img.device)
         return dense_crf_loss(ori, seg, roi, o["weight"], o["sigma_rgb"], o["sigma_xy"], o["scale"])
 

@@ -206,6 +206,20 @@ int acr_patch_cam_tc(const float* tokens, long long tok_batch_stride, long long 
                      const float* weight, const float* bias, int C, int relu, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Head of the dense-CRF regulariser (BASELINE configs[3]; call shape myTool.py:825-857, loop train_acr_coco.py:137-165):
+ * the probabilities the bilateral filter sees, straight from the patch-token logits.
+ *   logits [B,P*P,C] fp32 channel-last (cls_head(layer_4[:,1:]), DPT/ACR.py:133-134)
+ *   seg    [B,C+1,S/2,S/2] = bilinear_down_0.5( softmax_k([0, bilinear_up(logits -> SxS)]) ), both align_corners=False
+ * Backward: g_seg [B,C+1,S/2,S/2] -> d_up [B,C,S,S] = gradient with respect to the up-sampled logits (fold it to patch
+ * resolution with the bilinear backward).  S even.
+ * ------------------------------------------------------------------------------------------ */
+int acr_crf_head_fwd(const float* logits, int B, int P, int C, int S, float* seg, void* stream);
+int acr_crf_head_bwd(const float* logits, const float* g_seg, int B, int P, int C, int S, float* d_up, void* stream);
+/* Backward of F.interpolate(x [planes,P,P] -> [planes,S,S], mode='bilinear', align_corners=False) without atomics:
+ * d_patch [planes,P,P] = sum over the up-sampled pixels of their two-by-two tap weights times d_up [planes,S,S].  P <= S <= 512. */
+int acr_bilinear_up_bwd(const float* d_up, int planes, int P, int S, float* d_patch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (a10) PAMR.  Replaces PAMR.forward, pamr.py:125-144, including the bilinear (align_corners=True)
  * up-sampling of the mask (pamr.py:126): x [B,K,H,W] image, mask [B,C,mh,mw], dilations_host[nd] on
  * the HOST (1 <= nd <= 8).  out [B,C,H,W].  workspace: acr_pamr_workspace() bytes (affinity planes +

@@ -693,6 +693,40 @@ def test_densecrf_loss_k81_matches_reference_filter(dev):
     assert rel_err(t2n(seg.grad), t2n(seg2.grad)) < 1e-5
 
 
+@pytest.mark.parametrize("B,P,C", [(2, 4, 5), (1, 7, 80), (2, 3, 1)])
+def test_dense_crf_from_patch_logits_matches_composition(dev, B, P, C):
+    """The fused head of the dense-CRF term (ops.crf_head: bilinear up-sampling of the patch logits, softmax over [background,
+    classes], rloss down-scaling) against the library composition the reference-shaped path uses: probabilities, the loss and its
+    gradient with respect to the patch logits."""
+    import torch.nn.functional as F
+    from acr_wsss_b200 import ops, synth, dense_crf_loss, dense_crf_loss_from_patch_logits
+    S = 16 * P
+    g = torch.Generator().manual_seed(P * C)
+    z = (torch.randn(B, P * P, C, generator=g) * 2.0).to(dev)
+    img = synth.smooth_rgb(B, S, S, seed=1).to(dev)
+
+    def composed(zz):
+        up = F.interpolate(zz.permute(0, 2, 1).reshape(B, C, P, P), (S, S), mode="bilinear", align_corners=False)
+        return torch.softmax(torch.cat([torch.zeros_like(up[:, :1]), up], dim=1), dim=1)
+
+    z1 = z.clone().requires_grad_(True)
+    seg_ref = F.interpolate(composed(z1), scale_factor=0.5, mode="bilinear", align_corners=False, recompute_scale_factor=True)
+    z2 = z.clone().requires_grad_(True)
+    seg = ops.crf_head(z2, S)
+    assert rel_err(t2n(seg), t2n(seg_ref)) < 1e-5
+    cot = torch.randn(seg.shape, generator=g).to(dev)
+    (seg_ref * cot).sum().backward()
+    (seg * cot).sum().backward()
+    assert rel_err(t2n(z2.grad), t2n(z1.grad)) < 1e-4
+    # the whole term (fused head + filter) against dense_crf_loss on the composed full-resolution probabilities
+    z3, z4 = z.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    l_ref = dense_crf_loss(img, composed(z3), torch.ones(B, S, S, device=dev), 1e-3, 15.0, 100.0, 0.5)
+    l_new = dense_crf_loss_from_patch_logits(img, z4, 1e-3, 15.0, 100.0, 0.5)
+    assert abs(float(l_new) - float(l_ref)) <= 1e-4 * abs(float(l_ref))
+    l_ref.backward(); l_new.backward()
+    assert rel_err(t2n(z4.grad), t2n(z3.grad)) < 1e-3       # (splat order: float atomics)
+
+
 def test_trainer_dense_crf_term_cfg4_graph_matches_eager(dev):
     """configs[3] step (C = 80 classes, K = 81 planes through the bilateral dense-CRF term) as Trainer runs it: the CUDA-graph
     step equals the eager composition, the term is finite and contributes a gradient to cls_head."""
