@@ -510,9 +510,8 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
 // =============================================================================================
 // Backward.  dP_h = dO_h V_h^T + G/H ; dS_h = P_h * (dP_h - delta) ; delta[q] = sum_j P_h[q,j] dP_h[q,j]
 //   = dO_q . O_q + (1/H) sum_j P_h[q,j] G[q,j]   (the second term is what the affinity gradient adds).
-// Kernels: bwd_delta_kernel (dO.O) -> attn_mean_kernel<1> (+ P.G/H) -> attn_bwd_kernel (per (kv tile, h, b): K_j, V_j
-// stationary, loop over q tiles; everything is computed TRANSPOSED (rows = keys) so that P^T and dS^T are the
-// TMEM A operands of the dV / dK MMAs; dQ tiles are reduced across kv tiles with fp32 atomics) -> bwd_dq_convert_kernel.
+// Kernels: bwd_delta_kernel (dO.O, zero-fill of the dQ accumulator) -> attn_mean_kernel<1> (+ P.G/H) -> attn_bwd_kernel
+// (attn_bwd_tc.cu: persistent, rows = queries, dQ tiles reduced across kv tiles by TMA reduce-adds) -> bwd_dq_convert_kernel.
 // =============================================================================================
 namespace {
 
@@ -571,323 +570,6 @@ bwd_dq_convert_kernel(const float* __restrict__ dq_acc, __nv_bfloat16* __restric
   v.z = tc::pack_bf16(y.x * scale, y.y * scale);
   v.w = tc::pack_bf16(y.z * scale, y.w * scale);
   *reinterpret_cast<uint4*>(d_qkv + (((size_t)b * N + n) * 3 + 0) * ((size_t)H * HD) + (size_t)h * HD + c * 8) = v;
-}
-
-struct BwdSmem {
-  uint8_t k[TILE_BYTES];
-  uint8_t v[TILE_BYTES];
-  uint8_t q[2][TILE_BYTES];
-  uint8_t d_o[2][TILE_BYTES];
-  uint8_t p[2][2][TILE_BYTES];       // [buffer][kv block of 64][q row][64 kv] bf16 P tile, SWIZZLE_128B rows (one row per thread)
-  uint8_t ds[2][2][TILE_BYTES];      // dS tile, same layout: read MN-major (A = dS^T / P^T) and K-major (A = dS)
-  uint64_t kv_full, qdo_full[2], qdo_empty[2], sdp_full, pds_full, dq_full;
-  uint32_t tmem_base;
-};
-
-// Softmax-backward of one thread's share of a tile: query row `row`, 64 key columns starting at `colbase`.
-// grow == nullptr <=> no affinity gradient was given (warp-uniform).
-// GMODE: 0 no affinity gradient, 1 fp32 rows (scalar loads), 2 fp32 rows (128-bit loads), 3 sign codes (`grow` then points
-// at bytes and `invH` carries 2*w*scale/H of this row).
-// zero `n` 16-byte chunks (from chunk c0) of this thread's row in the swizzled P and dS tiles
-__device__ __forceinline__ void bwd_zero_chunks(uint8_t* prow, uint8_t* drow, int row, int c0, int n) {
-  for (int cc = c0; cc < c0 + n; ++cc) {
-    const int pos = (cc ^ (row & 7)) << 4;
-    *reinterpret_cast<uint4*>(prow + pos) = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(drow + pos) = make_uint4(0u, 0u, 0u, 0u);
-  }
-}
-
-template <int GMODE, bool TAIL>
-__device__ __forceinline__ void bwd_tile_body(BwdSmem& s, int buf, uint32_t tS, uint32_t tDP, uint32_t lane_off, int half, int row,
-                                              int colbase, int N, const float* __restrict__ grow, float invH, float scale_log2,
-                                              float lse2, float dlt, float* __restrict__ rd_row0) {
-  constexpr bool HAS_G = GMODE != 0;
-  uint32_t rs[32], rd[32];
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    if (TAIL && colbase + c * 32 >= N) {             // 32 key columns entirely past N (uniform over the warp): P = dS = 0
-      bwd_zero_chunks(s.p[buf][half] + row * 128, s.ds[buf][half] + row * 128, row, c * 4, 4);
-      continue;
-    }
-    tc::tmem_ld32(tS + lane_off + half * 64 + c * 32, rs);
-    tc::tmem_ld32(tDP + lane_off + half * 64 + c * 32, rd);
-    float g[32];
-    if (GMODE == 3) {
-#pragma unroll
-      for (int v = 0; v < 2; ++v) {
-        const uint4 t = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(grow) + c * 32) + v);
-        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) g[v * 16 + j * 4 + k] = ACR_CODE_F(w[j], k);
-      }
-    } else if (GMODE == 2) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(grow + c * 32) + e);
-        g[4 * e] = t.x; g[4 * e + 1] = t.y; g[4 * e + 2] = t.z; g[4 * e + 3] = t.w;
-      }
-    } else if (GMODE == 1) {
-#pragma unroll
-      for (int e = 0; e < 32; ++e) g[e] = (!TAIL || colbase + c * 32 + e < N) ? __ldg(grow + c * 32 + e) : 0.f;
-    }
-    tc::tmem_ld_wait();
-    uint32_t pk[16], dk[16];
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      float pv[2], dv[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int cc = c * 32 + 2 * e + u;
-        float p = tc::fast_exp2(fmaf(__uint_as_float(rs[2 * e + u]), scale_log2, -lse2));
-        if (TAIL && colbase + cc >= N) p = 0.f;
-        float dp = __uint_as_float(rd[2 * e + u]);
-        if (HAS_G) { dp = fmaf(g[2 * e + u], invH, dp); rd[2 * e + u] = __float_as_uint(dp); }
-        pv[u] = p;
-        dv[u] = p * (dp - dlt);
-      }
-      pk[e] = tc::pack_bf16(pv[0], pv[1]);
-      dk[e] = tc::pack_bf16(dv[0], dv[1]);
-    }
-    if (rd_row0 != nullptr) {                       // row 0 of dP_h (one thread of one tile): what the reference's hook keeps
-      for (int e = 0; e < 32; ++e)
-        if (colbase + c * 32 + e < N) rd_row0[c * 32 + e] = __uint_as_float(rd[e]);
-    }
-    // this thread's row of block `half`: 16-byte chunk j at position j ^ (row & 7)
-    uint8_t* prow = s.p[buf][half] + row * 128;
-    uint8_t* drow = s.ds[buf][half] + row * 128;
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int pos = ((c * 4 + cc) ^ (row & 7)) << 4;
-      *reinterpret_cast<uint4*>(prow + pos) = make_uint4(pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
-      *reinterpret_cast<uint4*>(drow + pos) = make_uint4(dk[cc * 4 + 0], dk[cc * 4 + 1], dk[cc * 4 + 2], dk[cc * 4 + 3]);
-    }
-  }
-}
-
-// One CTA per (key tile j, head, image); K_j, V_j stationary, loop over query tiles i.  Rows (TMEM lanes) = queries:
-//   S = Q_i K_j^T, dP = dO_i V_j^T  (SS MMAs)  ->  per thread: one query row, 64 key columns:
-//   P = exp2(S*c - lse_row), dP += G[row, cols]/H (row-contiguous loads), dS = P*(dP - delta_row)
-//   P, dS -> bf16 rows of two swizzled smem tiles, then
-//   dV += P^T dO (A = P tile read MN-major), dK += dS^T Q (A = dS tile MN-major), dQ_i = dS K_j (A = dS tile K-major).
-// MMA issue order: the scores of tile i+1 are issued BEFORE the gradient MMAs of tile i, so the softmax warps of tile
-// i+1 only wait for 2 of the 5 MMAs; dQ tiles are reduced over key tiles with vectorised fp32 reductions.
-__global__ void __launch_bounds__(384, 1)
-attn_bwd_kernel_r1(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                const __grid_constant__ CUtensorMap tmap_dq, const float* __restrict__ lse, const float* __restrict__ delta, const float* __restrict__ g_mean, long long g_bs,
-                long long g_ld, GCode gc, __nv_bfloat16* __restrict__ d_qkv, float* __restrict__ dq_acc, float* __restrict__ g_row0,
-                int N, int H, float scale, float scale_log2) {
-  extern __shared__ uint8_t smem_raw[];
-  BwdSmem& s = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv0 = blockIdx.x * BN, h = blockIdx.y, b = blockIdx.z;
-  const int ntiles = (N + BM - 1) / BM;
-
-  if (warp == 0 && lane == 0) {
-    tc::prefetch_tmap(&tmap_qkv);
-    tc::prefetch_tmap(&tmap_do);
-    tc::prefetch_tmap(&tmap_dq);
-    tc::mbar_init(&s.kv_full, 1);
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.qdo_full[i], 1); tc::mbar_init(&s.qdo_empty[i], 1); }
-    tc::mbar_init(&s.sdp_full, 1);
-    tc::mbar_init(&s.pds_full, 256);
-    tc::mbar_init(&s.dq_full, 1);
-    tc::fence_barrier_init();
-  }
-  if (warp == 2) tc::tmem_alloc<512>(&s.tmem_base);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem = s.tmem_base;
-  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
-
-  if (warp == 0) {
-    tc::reg_dealloc<40>();
-    if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&s.kv_full, 2 * TILE_BYTES);
-      tc::tma_load_4d(s.k, &tmap_qkv, &s.kv_full, 0, H + h, kv0, b);
-      tc::tma_load_4d(s.v, &tmap_qkv, &s.kv_full, 0, 2 * H + h, kv0, b);
-      for (int i = 0; i < ntiles; ++i) {
-        const int st = i & 1;
-        tc::mbar_wait(&s.qdo_empty[st], ((i >> 1) & 1) ^ 1);
-        tc::mbar_arrive_expect_tx(&s.qdo_full[st], 2 * TILE_BYTES);
-        tc::tma_load_4d(s.q[st], &tmap_qkv, &s.qdo_full[st], 0, h, i * BM, b);
-        tc::tma_load_4d(s.d_o[st], &tmap_do, &s.qdo_full[st], 0, h, i * BM, b);
-      }
-    }
-  } else if (warp == 1) {
-    tc::reg_dealloc<40>();
-    if (lane == 0) {
-      tc::mbar_wait(&s.kv_full, 0);
-      const uint32_t k_addr = tc::smem_u32(s.k), v_addr = tc::smem_u32(s.v);
-      auto issue_scores = [&](int i) {      // S = Q K^T, dP = dO V^T
-        const int st = i & 1;
-        tc::mbar_wait(&s.qdo_full[st], (i >> 1) & 1);
-        tc::tc_fence_after();
-        const uint32_t q_addr = tc::smem_u32(s.q[st]), do_addr = tc::smem_u32(s.d_o[st]);
-#pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-          tc::mma_ss(tS, tc::smem_desc_sw128(q_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(k_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
-#pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks)
-          tc::mma_ss(tDP, tc::smem_desc_sw128(do_addr + ks * 32, 16, 1024), tc::smem_desc_sw128(v_addr + ks * 32, 16, 1024), IDESC_S, ks > 0);
-        tc::tc_commit(&s.sdp_full);
-      };
-      issue_scores(0);
-      for (int i = 0; i < ntiles; ++i) {
-        const int st = i & 1;
-        const uint32_t q_addr = tc::smem_u32(s.q[st]), do_addr = tc::smem_u32(s.d_o[st]);
-        const uint32_t p_addr = tc::smem_u32(s.p[st][0]), ds_addr = tc::smem_u32(s.ds[st][0]);
-        // pds_full(i): softmax warps consumed S/dP(i) and dQ(i-1), and published the P / dS smem tiles of buffer i&1
-        tc::mbar_wait(&s.pds_full, i & 1);
-        if (i + 1 < ntiles) issue_scores(i + 1);       // scores of the next tile first: shortens the softmax critical path
-        tc::tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < BM / 16; ++ks)      // dV += P^T dO   (A = P tile MN-major: M = kv, K = q; two 64-wide M blocks 16 KB apart)
-          tc::mma_ss(tDV, tc::smem_desc_sw128(p_addr + ks * 2048, TILE_BYTES, 1024), tc::smem_desc_sw128(do_addr + ks * 2048, 1024, 1024),
-                     IDESC_DQ, (i > 0) || (ks > 0));
-#pragma unroll
-        for (int ks = 0; ks < BM / 16; ++ks)      // dK += dS^T Q
-          tc::mma_ss(tDK, tc::smem_desc_sw128(ds_addr + ks * 2048, TILE_BYTES, 1024), tc::smem_desc_sw128(q_addr + ks * 2048, 1024, 1024),
-                     IDESC_DQ, (i > 0) || (ks > 0));
-#pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks)      // dQ_i = dS K   (A = dS tile K-major: block ks/4, 32-byte k step; B = K MN-major)
-          tc::mma_ss(tDQ, tc::smem_desc_sw128(ds_addr + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024),
-                     tc::smem_desc_sw128(k_addr + ks * 2048, 1024, 1024), IDESC_PV, ks > 0);
-        tc::tc_commit(&s.dq_full);
-        tc::tc_commit(&s.qdo_empty[st]);
-      }
-    }
-  } else if (warp < 4) {
-    tc::reg_dealloc<40>();
-  } else {
-    tc::reg_alloc<232>();
-    const int we = warp - 4;
-    const int row = (warp & 3) * 32 + lane;          // query row inside the tile (TMEM lane)
-    const int half = we >> 2;                        // which 64-column (key) half
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const float invH = 1.f / (float)H;
-    const int colbase = kv0 + half * 64;
-    const bool tail = (kv0 + BN > N);
-    const bool g_vec = (g_mean != nullptr) && ((g_ld & 3) == 0) && ((g_bs & 3) == 0) && ((reinterpret_cast<uintptr_t>(g_mean) & 15) == 0);
-    const float* stat_l = lse + ((size_t)b * H + h) * N;
-    const float* stat_d = delta + ((size_t)b * H + h) * N;
-    uint32_t rs[32];
-    // dQ of query tile t (rows = queries, this thread: 32 of the 64 d columns of one row) -> fp32 accumulator [B*H,N,64].
-    // Staged in the P tile of buffer t&1 -- free once the gradient MMAs of tile t have retired (dq_full(t)) and until the
-    // softmax of tile t+2 -- as two [128 x 32] fp32 SWIZZLE_128B tiles and added by two TMA reduce-adds
-    // (cp.reduce.async.bulk.tensor).  The 2048 scattered RED.128 per tile this replaces cost 13 % of the kernel (half-used
-    // L2 sectors); rows past N are clipped by the tensor map.
-    const bool dq_leader = (we == 0 && lane == 0);
-    auto push_dq = [&](int t) {
-      uint8_t* drow = s.p[t & 1][half] + row * 128;
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        *reinterpret_cast<uint4*>(drow + ((e ^ (row & 7)) << 4)) = make_uint4(rs[4 * e], rs[4 * e + 1], rs[4 * e + 2], rs[4 * e + 3]);
-      tc::fence_proxy_async_smem();
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (dq_leader) {
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
-          asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                           reinterpret_cast<uint64_t>(&tmap_dq)),
-                       "r"(tc::smem_u32(s.p[t & 1][hh])), "r"(hh * 32), "r"(t * BM), "r"(b * H + h)
-                       : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-    };
-    float lse_n = (row < N) ? __ldg(stat_l + row) : INFINITY;   // natural-log LSE; scaled to log2 at use
-    float dlt_n = (row < N) ? __ldg(stat_d + row) : 0.f;
-    for (int i = 0; i < ntiles; ++i) {
-      const int q0 = i * BM;
-      const int qi = q0 + row;
-      const float lse2 = lse_n * kLog2e, dlt = dlt_n;
-      if (i + 1 < ntiles) {                          // row statistics of the next tile, off the critical path
-        const int qn = qi + BM;
-        lse_n = (qn < N) ? __ldg(stat_l + qn) : INFINITY;
-        dlt_n = (qn < N) ? __ldg(stat_d + qn) : 0.f;
-      }
-      // rows past N read a clamped (valid) row: their P is 0, so the value is irrelevant, and the branch on the
-      // presence of G stays warp-uniform (the tile body contains warp-collective tcgen05.ld)
-      const float* grow = (g_mean != nullptr) ? g_mean + (size_t)b * g_bs + (size_t)min(qi, N - 1) * g_ld + colbase : nullptr;
-      const unsigned char* crow = (gc.ptr != nullptr) ? gc.ptr + (size_t)b * gc.bs + (size_t)min(qi, N - 1) * gc.ld + colbase : nullptr;
-      float* rd_row0 = (g_row0 != nullptr && qi == 0) ? g_row0 + ((size_t)b * H + h) * N + colbase : nullptr;
-      tc::mbar_wait(&s.sdp_full, i & 1);
-      tc::tc_fence_after();
-      if (i >= 2) {       // the TMA reduce of dQ(i-2) read its staging copy out of P[i&1]: it must be done before P(i) is written
-        if (dq_leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-      }
-      // specialised bodies (uniform branches): affinity gradient present / key tail tile
-      if (q0 + (warp & 3) * 32 >= N) {
-        // all 32 query rows of this warp lie past N (last query tile): nothing to compute, the tiles just need finite
-        // values there (they meet zero-filled dO / Q rows in the gradient MMAs)
-        bwd_zero_chunks(s.p[i & 1][half] + row * 128, s.ds[i & 1][half] + row * 128, row, 0, 8);
-      } else if (crow != nullptr) {
-        const float w2 = gcode_weight(gc, qi, invH);
-        const float* cp = reinterpret_cast<const float*>(crow);
-        if (!tail) bwd_tile_body<3, false>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, cp, w2, scale_log2, lse2, dlt, rd_row0);
-        else bwd_tile_body<3, true>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, cp, w2, scale_log2, lse2, dlt, rd_row0);
-      } else if (grow != nullptr) {
-        if (!tail && g_vec) bwd_tile_body<2, false>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, grow, invH, scale_log2, lse2, dlt, rd_row0);
-        else bwd_tile_body<1, true>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, grow, invH, scale_log2, lse2, dlt, rd_row0);
-      } else {
-        if (!tail) bwd_tile_body<0, false>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, nullptr, invH, scale_log2, lse2, dlt, rd_row0);
-        else bwd_tile_body<0, true>(s, i & 1, tS, tDP, lane_off, half, row, colbase, N, nullptr, invH, scale_log2, lse2, dlt, rd_row0);
-      }
-      tc::fence_proxy_async_smem();
-      // dQ of the PREVIOUS query tile (its MMAs ran under this tile's softmax) must leave TMEM before pds_full(i)
-      // lets the MMA warp overwrite tDQ; the global reductions themselves are issued after the arrive.
-      if (i > 0) {
-        tc::mbar_wait(&s.dq_full, (i - 1) & 1);
-        tc::tc_fence_after();
-        tc::tmem_ld32(tDQ + lane_off + half * 32, rs);
-        tc::tmem_ld_wait();
-      }
-      tc::tc_fence_before();
-      tc::mbar_arrive(&s.pds_full);
-      if (i > 0) push_dq(i - 1);
-    }
-    tc::mbar_wait(&s.dq_full, (ntiles - 1) & 1);
-    tc::tc_fence_after();
-    tc::tmem_ld32(tDQ + lane_off + half * 32, rs);
-    tc::tmem_ld_wait();
-    push_dq(ntiles - 1);
-    // epilogue: dV, dK rows (lanes = keys) of this key tile; all MMAs are complete (the last dq_full covered them)
-    const bool kv_ok = (kv0 + row) < N;
-    uint32_t rd[32];
-    tc::tmem_ld32(tDV + lane_off + half * 32, rs);      // warp-collective: outside the per-row validity branch
-    tc::tmem_ld32(tDK + lane_off + half * 32, rd);
-    tc::tmem_ld_wait();
-    if (kv_ok) {
-      const size_t E = (size_t)H * HD;
-      __nv_bfloat16* dkp = d_qkv + (((size_t)b * N + kv0 + row) * 3 + 1) * E + (size_t)h * HD + half * 32;
-      __nv_bfloat16* dvp = d_qkv + (((size_t)b * N + kv0 + row) * 3 + 2) * E + (size_t)h * HD + half * 32;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 v, k;
-        v.x = tc::pack_bf16(__uint_as_float(rs[c * 8 + 0]), __uint_as_float(rs[c * 8 + 1]));
-        v.y = tc::pack_bf16(__uint_as_float(rs[c * 8 + 2]), __uint_as_float(rs[c * 8 + 3]));
-        v.z = tc::pack_bf16(__uint_as_float(rs[c * 8 + 4]), __uint_as_float(rs[c * 8 + 5]));
-        v.w = tc::pack_bf16(__uint_as_float(rs[c * 8 + 6]), __uint_as_float(rs[c * 8 + 7]));
-        k.x = tc::pack_bf16(__uint_as_float(rd[c * 8 + 0]) * scale, __uint_as_float(rd[c * 8 + 1]) * scale);
-        k.y = tc::pack_bf16(__uint_as_float(rd[c * 8 + 2]) * scale, __uint_as_float(rd[c * 8 + 3]) * scale);
-        k.z = tc::pack_bf16(__uint_as_float(rd[c * 8 + 4]) * scale, __uint_as_float(rd[c * 8 + 5]) * scale);
-        k.w = tc::pack_bf16(__uint_as_float(rd[c * 8 + 6]) * scale, __uint_as_float(rd[c * 8 + 7]) * scale);
-        reinterpret_cast<uint4*>(dvp)[c] = v;
-        reinterpret_cast<uint4*>(dkp)[c] = k;
-      }
-    }
-    // the TMA reduce-adds are asynchronous: they must complete before the CTA (and its shared memory) goes away
-    if (dq_leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc<512>(tmem);
-  }
 }
 
 }  // namespace
@@ -952,20 +634,8 @@ extern "C" int acr_attn_bwd_bf16(const void* qkv, const void* out, const float* 
     attn_mean_kernel<1><<<grid, MEAN_THREADS, smem, st>>>(tmap_qkv, lse, const_cast<float*>(g_mean), g_batch_stride, g_row_stride, gc, delta, N, H, scale_log2);
     if (int e = acr::check_launch("attn_mean_kernel<1>")) return e;
   }
-  static const bool use_r1 = getenv("ACR_BWD_R1") != nullptr;      // round-1 kernel, kept for A/B measurements only
-  if (use_r1) {
-    const size_t smem = sizeof(BwdSmem) + 1024;
-    static bool attr_set[64] = {false};
-    if (int e = set_max_smem(attn_bwd_kernel_r1, smem, attr_set)) return e;
-    dim3 grid(kt, H, B);
-    acr::KernelTimer kt_("attn_bwd_kernel", st);
-    attn_bwd_kernel_r1<<<grid, 384, smem, st>>>(tmap_qkv, tmap_do, tmap_dq, lse, delta, g_mean, g_batch_stride, g_row_stride, gc, (__nv_bfloat16*)d_qkv, dq_acc, g_row0,
-                                             N, H, scale, scale_log2);
-    if (int e = acr::check_launch("attn_bwd_kernel_r1")) return e;
-  } else {
-    if (int e = launch_attn_bwd(tmap_qkv, tmap_do, tmap_dq, lse, delta, g_mean, g_batch_stride, g_row_stride, gc, (__nv_bfloat16*)d_qkv, g_row0, B, N, H, scale, st))
-      return e;
-  }
+  if (int e = launch_attn_bwd(tmap_qkv, tmap_do, tmap_dq, lse, delta, g_mean, g_batch_stride, g_row_stride, gc, (__nv_bfloat16*)d_qkv, g_row0, B, N, H, scale, st))
+    return e;
   const long long nconv = (long long)rows * (HD / 8);
   bwd_dq_convert_kernel<<<(unsigned)((nconv + 255) / 256), 256, 0, st>>>(dq_acc, (__nv_bfloat16*)d_qkv, B, N, H, scale);
   return acr::check_launch("bwd_dq_convert_kernel");

@@ -206,7 +206,28 @@ def measure_refine(dev, pk):
         alg = 2 * N * K * Sz * Sz * 4 + N * 3 * Sz * Sz * 4                                  # planes in + out, image in
         res[key] = {"workload": f"bilateral filter N={N} K={K} {Sz}x{Sz}, sigma_rgb 15, sigma_xy 50", "ms": ms, "algorithmic_bytes": alg,
                     "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg / ms / 1e6 / pk["hbm_gbs"]}}
-    del flush
+    # north star (2): the consistency loss in the mode the training step uses (sign codes), cfg2 shape
+    g = torch.Generator(device="cuda").manual_seed(0)
+    Bc, Lc, Nc = 8, 12, N_TOK
+    a1 = torch.softmax(torch.randn(Bc, Lc, Nc, Nc, device=dev, generator=g), -1)
+    a2 = torch.softmax(torch.randn(Bc, Lc, Nc, Nc, device=dev, generator=g), -1)
+    ms = timeit(lambda: ops.consistency_codes(a1, a2, S // 16))
+    alg = 10 * Bc * Lc * Nc * Nc                                                             # both stacks read once (fp32), one code byte per element written for each
+    res["consistency_codes_cfg2"] = {"workload": f"all-pairs consistency loss + sign-code gradient, B={Bc} L={Lc} N={Nc}", "ms": ms, "algorithmic_bytes": alg,
+                                     "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg / ms / 1e6 / pk["hbm_gbs"]}}
+    del a2
+    # north star (3): the CAM contractions on the tensor cores (csrc/refine_tc.cu).  They are streams of their A operand
+    # (0.4 FLOP per byte), so the roofline that bounds them is HBM; the tensor-pipe share is in profiles/ (ncu).
+    for key, Bv in {"affinity_refine_tc_cfg1": 2, "affinity_refine_tc_batch8": 16}.items():
+        attn = a1[:Bv] if Bv <= Bc else torch.softmax(torch.randn(Bv, Lc, Nc, Nc, device=dev, generator=g), -1)
+        cam = torch.rand(Bv, Nc - 1, 3, device=dev, generator=g)
+        ms = timeit(lambda: ops.affinity_refine_tc(attn, cam, 1, False))
+        alg = 4 * Bv * Lc * (Nc - 1) ** 2 + 2 * 4 * Bv * (Nc - 1) * 3
+        res[key] = {"workload": f"sum_l attn[:,l,1:,1:] . cam (3 classes), {Bv} views of 448x448 (tcgen05, bf16 hi/lo split)", "ms": ms, "algorithmic_bytes": alg,
+                    "flop": 2 * Bv * (Nc - 1) ** 2 * 3,
+                    "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": alg / ms / 1e6 / pk["hbm_gbs"]}}
+        del attn
+    del flush, a1
     return res
 
 

@@ -14,3 +14,14 @@ a1 = torch.softmax(torch.randn(8, 12, 785, 785, device=dev, generator=g), -1); a
 ops.consistency_codes(a1, a2, 28)
 ops.consistency_fwd_bwd(a1, a2, 28, 100.0, 100.0)
 torch.cuda.synchronize()
+# round 2: the tensor-core CAM contractions (cfg1 shapes) and the fused dense-CRF head (cfg4 shapes)
+attn = torch.softmax(torch.randn(2, 12, 785, 785, device=dev, generator=g), -1)
+cam = torch.rand(2, 784, 3, device=dev, generator=g)
+ops.affinity_refine_tc(attn, cam, 1, False)
+tok = torch.randn(2, 785, 768, device=dev, generator=g)
+with torch.no_grad():
+    ops.patch_cam(tok[:, 1:], torch.randn(20, 768, device=dev, generator=g) * 0.05, torch.zeros(20, device=dev))
+z = (torch.randn(8, 784, 80, device=dev, generator=g) * 2.0).requires_grad_(True)
+seg = ops.crf_head(z, 448)
+seg.backward(torch.randn(seg.shape, device=dev, generator=g))
+torch.cuda.synchronize()
