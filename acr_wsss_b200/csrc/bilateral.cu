@@ -16,7 +16,7 @@
 // the splat additions (float atomics here; differences are ~1e-7 relative), and filtering all K planes in one
 // pass (the planes are independent and the filter is linear; the reference loops K times with value_size=1).
 //
-// Six launches per batch of up to 8 images (grid.z = image); round 1 needed 13 launches + 16 memsets and 450 us at N = 8, K = 21:
+// Eleven launches per batch of up to 8 images (grid.z = image); round 1 needed 13 launches + 16 memsets and 450 us at N = 8, K = 21:
 //   embed      per pixel: 6 candidate keys + barycentric weights, written plane-major (candidate c = r*HWp + pixel, so every
 //              store is coalesced); the same threads clear the hash table and the vertex counter
 //   insert     per candidate; neighbouring pixels mostly fall on the same lattice vertex, so a warp first groups its lanes by
@@ -25,8 +25,7 @@
 //              (vertex, axis)), candidate -> vertex id + 1, zeroing of the value arrays
 //   splat      a CTA sorts the 768 (pixel, remainder) pairs of its 16 x 8 pixel block by vertex in shared memory (integer atomics
 //              only) and issues ONE red.global.add.v4.f32 per (vertex, 4 planes) (K padded to a multiple of 4: 16-byte value rows)
-//   blur       all d+1 passes in one launch: one 8-CTA cluster per image, cluster barriers between the passes, values read
-//              through L2 (ld.global.cg: the ping-pong buffers are rewritten by other CTAs of the cluster)
+//   blur       d+1 passes, one launch each, (vertex, 4 planes) items with 4 independent gather chains per thread
 //   slice      per (pixel, 4 planes): six 128-bit gathers, same accumulation order as the reference
 //
 // Data layout in HBM (per image, carved from the caller's workspace; nc = 6*HWp candidates, HWp = HW rounded up to 4):
@@ -39,13 +38,10 @@
 //   nbr   [6][nc] int2     blur neighbours (vertex id + 1; 0 = missing)
 //   val0/val1 [(nc+1) * Kp] f32   lattice values, vertex-major with the Kp = roundup(K, 4) planes contiguous; slot 0 = zeros
 #include "common.cuh"
-#include <cooperative_groups.h>
 #include <cmath>
 #include <mutex>
 #include <vector>
 #include <type_traits>
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -293,7 +289,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, const float4& v) {
 
 constexpr int kPixTile = 128;      // pixels per CTA (splat: 16 x 8 block of the image; slice: 128 consecutive pixels)
 constexpr int kTileW = 16, kTileH = 8;
-constexpr int kSlotProbes = 8;
+constexpr int kSlotProbes = 32;
 
 // Splat.  A CTA owns a 16 x 8 block of pixels: its 768 (pixel, remainder) pairs fall on ~100-200 distinct lattice vertices.  Float
 // atomics at L2 bounded the first version (50 M of them for N = 8, K = 21), and shared-memory float atomics are CAS loops (4x
@@ -303,7 +299,7 @@ constexpr int kSlotProbes = 8;
 //   3. exclusive scan of the slot counts, pairs scattered to order[] (counting sort);
 //   4. one work item per (occupied slot, quad) sums its pairs from the tile and issues ONE red.global.add.v4.f32.
 // Pairs that find no slot within kSlotProbes probes add to global memory directly (rare).
-constexpr int kSplatSlots = 256;     // = blockDim (the scan below is one element per thread)
+constexpr int kSplatSlots = 1024;    // >= the 768 pairs of a tile, so the table never fills up; 4 slots per thread in the scan
 __global__ void __launch_bounds__(256)
 lattice_splat_kernel(const float* __restrict__ in, int K, int H, int W, int HWpad, Lattice lat0) {
   extern __shared__ float4 smem4[];                    // tile4[kPixTile][Qs], then the int / float arrays below
@@ -312,15 +308,13 @@ lattice_splat_kernel(const float* __restrict__ in, int K, int H, int W, int HWpa
   const int HW = H * W, Kp = lat.Kp, Q = Kp / 4;
   in += (size_t)blockIdx.z * K * HW;
   const int Qs = Q | 1;                                 // odd row stride (in float4): conflict-free 128-bit stores
-  const float* tile = reinterpret_cast<const float*>(smem4);
   int* slot = reinterpret_cast<int*>(smem4 + (size_t)Qs * kPixTile);      // [D6 * kPixTile]: slot of the pair, -1 = none
   int* pos = slot + D6 * kPixTile;                                        // position inside the slot
   int* order = pos + D6 * kPixTile;                                       // pair indices sorted by slot
   float* wts = reinterpret_cast<float*>(order + D6 * kPixTile);
   const int tiles_x = (W + kTileW - 1) / kTileW;
   const int x0 = (blockIdx.x % tiles_x) * kTileW, y0 = (blockIdx.x / tiles_x) * kTileH;
-  skey[threadIdx.x] = 0;
-  scount[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < kSplatSlots; i += blockDim.x) { skey[i] = 0; scount[i] = 0; }
   for (int e = threadIdx.x; e < Q * kPixTile; e += blockDim.x) {      // four coalesced plane reads -> one 16-byte store
     const int q = e / kPixTile, p = e - q * kPixTile;
     const int x = x0 + (p % kTileW), y = y0 + (p / kTileW);
@@ -347,32 +341,40 @@ lattice_splat_kernel(const float* __restrict__ in, int K, int H, int W, int HWpa
       }
       if (sl >= 0) {
         pos[w] = atomicAdd(&scount[sl], 1);
-      } else {                                          // table neighbourhood full: this pair adds to global memory itself
-        for (int k = 0; k < K; ++k) atomicAdd(lat.val0 + (size_t)o * Kp + k, wt * tile[(p * Qs + (k >> 2)) * 4 + (k & 3)]);
+      } else {                                          // table neighbourhood full (rare): this pair adds to global memory itself
+        for (int q = 0; q < Q; ++q) {
+          const float4 x = smem4[p * Qs + q];
+          red_add_v4(lat.val0 + (size_t)o * Kp + 4 * q, make_float4(wt * x.x, wt * x.y, wt * x.z, wt * x.w));
+        }
       }
     }
     slot[w] = sl;
     wts[w] = wt;
   }
   __syncthreads();
-  {   // exclusive scan of scount (one slot per thread) and compaction of the occupied slots
+  {   // exclusive scan of scount (4 consecutive slots per thread) and compaction of the occupied slots
+    constexpr int PER = kSplatSlots / 256;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const int c = scount[threadIdx.x];
-    int v = c;
+    int c[PER], tot = 0, occ = 0;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) { c[u] = scount[threadIdx.x * PER + u]; tot += c[u]; occ += c[u] > 0; }
+    int v = tot, vo = occ;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int n = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += n;
+      const int n = __shfl_up_sync(0xffffffffu, v, o), no = __shfl_up_sync(0xffffffffu, vo, o);
+      if (lane >= o) { v += n; vo += no; }
     }
-    const unsigned occ = __ballot_sync(0xffffffffu, c > 0);
-    if (lane == 31) warp_tot[wp] = v;
-    if (lane == 0) warp_occ[wp] = __popc(occ);
+    if (lane == 31) { warp_tot[wp] = v; warp_occ[wp] = vo; }
     __syncthreads();
-    int base = 0, obase = 0;
+    int base = v - tot, obase = vo - occ;
     for (int i = 0; i < wp; ++i) { base += warp_tot[i]; obase += warp_occ[i]; }
-    sstart[threadIdx.x] = base + v - c;
-    if (c > 0) socc[obase + __popc(occ & ((1u << lane) - 1u))] = threadIdx.x;
-    if (threadIdx.x == blockDim.x - 1) n_occ = obase + __popc(occ);
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      sstart[threadIdx.x * PER + u] = base;
+      base += c[u];
+      if (c[u] > 0) socc[obase++] = threadIdx.x * PER + u;
+    }
+    if (threadIdx.x == blockDim.x - 1) n_occ = obase;
   }
   __syncthreads();
   for (int w = threadIdx.x; w < D6 * kPixTile; w += blockDim.x) {
@@ -395,58 +397,50 @@ lattice_splat_kernel(const float* __restrict__ in, int K, int H, int W, int HWpa
   }
 }
 
-__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-
-// All d+1 blur passes of one image: new = old + 0.5 * (old[n1] + old[n2]) along axis j, j = 0..d in turn.  One cluster of
-// kBlurCtas CTAs per image; the passes are separated by cluster barriers (release / acquire at cluster scope), and the values
-// are read with ld.global.cg because the buffer a pass reads was written by other CTAs one pass earlier.
-constexpr int kBlurCtas = 8, kBlurThreads = 1024, kBlurIlp = 4;
-__global__ void __launch_bounds__(kBlurThreads)
-lattice_blur_kernel(Lattice lat0) {
-  cg::cluster_group cluster = cg::this_cluster();
+// One blur pass along axis j: new = old + 0.5 * (old[n1] + old[n2]).  Work item = (vertex, 4 planes); the chain neighbour ids ->
+// three gathers is pure L2 latency, so every thread keeps kBlurIlp independent items in flight.  One launch per pass over the whole
+// GPU: a single launch with one 8-CTA cluster per image and cluster barriers between the passes was measured as well -- no faster
+// on small lattices (75 vs 78 us at 15 k vertices) and 64 of 148 SMs wide on large ones (noise images: 300 k vertices per image).
+constexpr int kBlurIlp = 4;
+__global__ void __launch_bounds__(256)
+lattice_blur_kernel(const float* __restrict__ old0, float* __restrict__ new0, int j, Lattice lat0) {
   const Lattice lat = for_image(lat0, blockIdx.z);
+  const float* oldv = img_ptr(old0, lat.ws, blockIdx.z);
+  float* newv = img_ptr(new0, lat.ws, blockIdx.z);
   const long long M = *lat.counter;
   const int Q = lat.Kp / 4;
   const long long total = M * Q;
-  const int nthreads = kBlurCtas * kBlurThreads, t0 = (int)cluster.block_rank() * kBlurThreads + threadIdx.x;
-  float* oldv = lat.val0;
-  float* newv = lat.val1;
-  for (int j = 0; j < D6; ++j) {
-    const int2* nbr = lat.nbr + (size_t)j * lat.nc;
-    // the chain neighbour ids -> three gathers is pure L2 latency: kBlurIlp independent (vertex, 4 planes) items per thread in flight
-    for (long long t = t0; t < total; t += (long long)kBlurIlp * nthreads) {
-      size_t self[kBlurIlp], n1[kBlurIlp], n2[kBlurIlp];
-      bool ok[kBlurIlp];
+  const int nthreads = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int2* nbr = lat.nbr + (size_t)j * lat.nc;
+  for (long long t = t0; t < total; t += (long long)kBlurIlp * nthreads) {
+    size_t self[kBlurIlp], n1[kBlurIlp], n2[kBlurIlp];
+    bool ok[kBlurIlp];
 #pragma unroll
-      for (int u = 0; u < kBlurIlp; ++u) {
-        const long long tt = t + (long long)u * nthreads;
-        ok[u] = tt < total;
-        const int v = ok[u] ? (int)(tt / Q) : 0, q = ok[u] ? (int)(tt - (long long)v * Q) : 0;
-        const int2 nb = __ldg(nbr + v);
-        self[u] = (size_t)(v + 1) * lat.Kp + 4 * q;
-        n1[u] = (size_t)nb.x * lat.Kp + 4 * q;
-        n2[u] = (size_t)nb.y * lat.Kp + 4 * q;
-      }
-      float4 a[kBlurIlp], b[kBlurIlp], c[kBlurIlp];
-#pragma unroll
-      for (int u = 0; u < kBlurIlp; ++u) {
-        a[u] = ldcg4(oldv + n1[u]);
-        b[u] = ldcg4(oldv + n2[u]);
-        c[u] = ldcg4(oldv + self[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < kBlurIlp; ++u) {
-        float4 o;
-        o.x = __fadd_rn(c[u].x, __fmul_rn(0.5f, __fadd_rn(a[u].x, b[u].x)));
-        o.y = __fadd_rn(c[u].y, __fmul_rn(0.5f, __fadd_rn(a[u].y, b[u].y)));
-        o.z = __fadd_rn(c[u].z, __fmul_rn(0.5f, __fadd_rn(a[u].z, b[u].z)));
-        o.w = __fadd_rn(c[u].w, __fmul_rn(0.5f, __fadd_rn(a[u].w, b[u].w)));
-        if (ok[u]) *reinterpret_cast<float4*>(newv + self[u]) = o;
-      }
+    for (int u = 0; u < kBlurIlp; ++u) {
+      const long long tt = t + (long long)u * nthreads;
+      ok[u] = tt < total;
+      const int v = ok[u] ? (int)(tt / Q) : 0, q = ok[u] ? (int)(tt - (long long)v * Q) : 0;
+      const int2 nb = __ldg(nbr + v);
+      self[u] = (size_t)(v + 1) * lat.Kp + 4 * q;
+      n1[u] = (size_t)nb.x * lat.Kp + 4 * q;
+      n2[u] = (size_t)nb.y * lat.Kp + 4 * q;
     }
-    __threadfence();
-    cluster.sync();
-    float* t = oldv; oldv = newv; newv = t;
+    float4 a[kBlurIlp], b[kBlurIlp], c[kBlurIlp];
+#pragma unroll
+    for (int u = 0; u < kBlurIlp; ++u) {
+      a[u] = __ldg(reinterpret_cast<const float4*>(oldv + n1[u]));
+      b[u] = __ldg(reinterpret_cast<const float4*>(oldv + n2[u]));
+      c[u] = __ldg(reinterpret_cast<const float4*>(oldv + self[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < kBlurIlp; ++u) {
+      float4 o;
+      o.x = __fadd_rn(c[u].x, __fmul_rn(0.5f, __fadd_rn(a[u].x, b[u].x)));
+      o.y = __fadd_rn(c[u].y, __fmul_rn(0.5f, __fadd_rn(a[u].y, b[u].y)));
+      o.z = __fadd_rn(c[u].z, __fmul_rn(0.5f, __fadd_rn(a[u].z, b[u].z)));
+      o.w = __fadd_rn(c[u].w, __fmul_rn(0.5f, __fadd_rn(a[u].w, b[u].w)));
+      if (ok[u]) *reinterpret_cast<float4*>(newv + self[u]) = o;
+    }
   }
 }
 
@@ -584,19 +578,13 @@ extern "C" int acr_bilateral_batch(const float* images, const float* ins, float*
     lattice_splat_kernel<<<dim3(splat_tiles, 1, nb), 256, smem_splat, st>>>(in, K, H, W, HWpad, c);
     if (int e = acr::check_launch("lattice_splat_kernel")) return e;
     {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(kBlurCtas, 1, nb);
-      cfg.blockDim = dim3(kBlurThreads);
-      cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = kBlurCtas;
-      at[0].val.clusterDim.y = 1;
-      at[0].val.clusterDim.z = 1;
-      cfg.attrs = at;
-      cfg.numAttrs = 1;
-      ACR_CUDA(cudaLaunchKernelEx(&cfg, lattice_blur_kernel, c));
-      if (int e = acr::check_launch("lattice_blur_kernel")) return e;
+      float* cur = c.val0;
+      float* nxt = c.val1;
+      for (int j = 0; j < D6; ++j) {
+        lattice_blur_kernel<<<dim3(148 * 2, 1, nb), 256, 0, st>>>(cur, nxt, j, c);
+        if (int e = acr::check_launch("lattice_blur_kernel")) return e;
+        float* t = cur; cur = nxt; nxt = t;
+      }
     }
     // d+1 = 6 passes (an even number): the result is back in val0
     lattice_slice_kernel<<<dim3((HW + kPixTile - 1) / kPixTile, 1, nb), 256, smem, st>>>(c.val0, K, HW, HWpad, alpha, out, c);

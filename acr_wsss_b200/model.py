@@ -449,7 +449,8 @@ class ACR(nn.Module):
         infer_cam.py:180-184); pass full=True on the fp32 path to get the reference's full [1,N,N] maps.
         """
         blocks = self.pretrained.model.blocks
-        skip = 2 if self.cur_backbone == "deitb16_distil_384" else 1
+        skip = 1      # (2 for the distilled DeiT variant, DPT/ACR.py:210-211: a hybrid/distilled backbone is outside the hot path --
+        #               the constructor rejects it; the kernels keep the `skip` argument)
         attn_list = [blk.attn.attn_mean for blk in blocks]
         used = blocks[start_layer:]          # only these reach the result (DPT/ACR.py:208-209), so only they need a gradient
         p0 = torch.stack([blk.attn.get_attn_row0()[batch] for blk in used])              # [L',H,N]
@@ -466,7 +467,7 @@ class ACR(nn.Module):
         """getam() for EVERY sample of the last (batched) forward / backward at once: [S, N-skip] (row s = getam(s, ...)[0][0]);
         one kernel launch instead of S (batched CAM inference)."""
         blocks = self.pretrained.model.blocks
-        skip = 2 if self.cur_backbone == "deitb16_distil_384" else 1
+        skip = 1
         used = blocks[start_layer:]
         p0 = torch.stack([blk.attn.get_attn_row0() for blk in used])               # [L',S,H,N]
         g0 = torch.stack([blk.attn.get_attn_gradients_row0() for blk in used])

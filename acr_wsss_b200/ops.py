@@ -816,7 +816,7 @@ def bilateral_filter(images, ins, sigmargb, sigmaxy, return_lattice_size=False):
     ws = torch.empty(wsb + 256, device=ins.device, dtype=torch.uint8)
     off = (-ws.data_ptr()) % 256
     msz = (ctypes.c_int * N)() if return_lattice_size else None
-    _call("acr_bilateral_batch", 6 * ((N + 7) // 8), _p(images), _p(ins), _p(outs), N, K, H, W, float(sigmargb), float(sigmaxy),
+    _call("acr_bilateral_batch", 11 * ((N + 7) // 8), _p(images), _p(ins), _p(outs), N, K, H, W, float(sigmargb), float(sigmaxy),
                                               ctypes.c_void_p(ws.data_ptr() + off), wsb, msz, _stream())
     if return_lattice_size:
         return outs, list(msz)

@@ -32,4 +32,10 @@ for (N, K, S) in ([] if 'pamr' in sys.argv else [(1, 21, 224), (8, 21, 224), (8,
     alg = 2 * N * K * S * S * 4 + N * 3 * S * S * 4
     res[f"bilateral_N{N}_K{K}_us"] = round(t, 1); res[f"bilateral_N{N}_K{K}_GBs"] = round(alg / t / 1e3, 1)
     _, m = ops.bilateral_filter(img, ins, 15.0, 50.0, return_lattice_size=True); res[f"bilateral_N{N}_K{K}_M"] = m[0]
+if 'pamr' not in sys.argv:      # worst case for the lattice: white-noise images (what the synthetic training batches are), every pixel its own vertices
+    img = (torch.randn(8, 3, 224, 224, generator=torch.Generator().manual_seed(0)) * 58.0 + 120.0).clamp(0, 255).to(dev)
+    ins = synth.probabilities(8, 81, 224, 224, seed=0).to(dev)
+    t = timeit(lambda: ops.bilateral_filter(img, ins, 15.0, 50.0))
+    res["bilateral_noise_N8_K81_us"] = round(t, 1)
+    _, m = ops.bilateral_filter(img, ins, 15.0, 50.0, return_lattice_size=True); res["bilateral_noise_N8_K81_M"] = m[0]
 print(json.dumps(res))
