@@ -19,18 +19,36 @@ def shard_indices(n_items, rank, world_size):
 
 
 class GradBuckets:
-    def __init__(self, params, bucket_bytes=64 << 20, process_group=None, hooks=True):
+    def __init__(self, params, bucket_bytes=64 << 20, process_group=None, hooks=True, sharded=None):
+        """sharded: optional collection of parameters whose optimiser state may be SHARDED across ranks (the trunk's Linear
+        weights: the training step only reads their bf16 copies).  They are laid out first, in one region padded to a multiple
+        of world x 128 elements (`shard_end`); `reduce_sharded()` then reduce-scatters that region and all-reduces the rest."""
         self.params = [p for p in params if p.requires_grad]
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         order = list(reversed(self.params))
+        self.shard_end = 0
+        if sharded:
+            ids = {id(p) for p in sharded}
+            order = [p for p in order if id(p) in ids] + [p for p in order if id(p) not in ids]
+            nshard = sum(1 for p in order if id(p) in ids)
         # every tensor starts at a multiple of 128 elements: 16-byte alignment of fp32 AND bf16 views of the same layout
         # (cuBLAS drops to much slower kernels for unaligned operands)
         self.offsets = {}
         total = 0
-        for p in order:
+        for i, p in enumerate(order):
+            if sharded and i == nshard:
+                unit = 128 * self.world
+                total = (total + unit - 1) // unit * unit        # every rank's shard starts on a 128-element boundary
+                self.shard_end = total
             self.offsets[p] = total
             total += (p.numel() + 127) // 128 * 128
+        if sharded and nshard == len(order):
+            unit = 128 * self.world
+            total = (total + unit - 1) // unit * unit
+            self.shard_end = total
+        self.grad_shard = None
         dev = order[0].device
         self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.buckets = []            # (start, end, n_params)
@@ -96,6 +114,47 @@ class GradBuckets:
             if not self._avg:
                 self.flat[s:e].div_(self.world)
             yield s, e
+
+    def shard_range(self):
+        """[start, end) of this rank's slice of the sharded region."""
+        n = self.shard_end // self.world
+        return self.rank * n, (self.rank + 1) * n
+
+    def reduce_sharded(self):
+        """Gradient exchange for a sharded optimiser: reduce-scatter (mean) of the sharded region -- this rank's slice of the
+        averaged gradients lands in `grad_shard` -- and an all-reduce (mean) of the small replicated rest.  Moves (W-1)/W of the
+        buffer once instead of twice.  gloo (CPU tests) has neither reduce_scatter nor AVG: all-reduce + slice there."""
+        s, e = self.shard_range()
+        if self.grad_shard is None:
+            self.grad_shard = torch.empty(e - s, device=self.flat.device, dtype=torch.float32)
+        if self.world == 1:
+            self.grad_shard.copy_(self.flat[s:e])
+            return
+        big, small = self.flat[:self.shard_end], self.flat[self.shard_end:]
+        if self._avg:
+            w1 = dist.reduce_scatter_tensor(self.grad_shard, big, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            w2 = dist.all_reduce(small, op=dist.ReduceOp.AVG, group=self.group, async_op=True) if small.numel() else None
+            w1.wait()
+            if w2 is not None:
+                w2.wait()
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.div_(self.world)
+            self.grad_shard.copy_(self.flat[s:e])
+
+    def all_gather_shards(self, full):
+        """In-place all-gather: every rank contributes its slice [shard_range) of `full[:shard_end]` (any dtype)."""
+        if self.world == 1:
+            return
+        s, e = self.shard_range()
+        region = full[:self.shard_end]
+        if self._avg:       # nccl: the in-place form (send buffer = this rank's slice of the receive buffer)
+            dist.all_gather_into_tensor(region, region[s:e], group=self.group)
+        else:
+            parts = [torch.empty(e - s, dtype=full.dtype, device=full.device) for _ in range(self.world)]
+            dist.all_gather(parts, region[s:e].clone(), group=self.group)
+            for r, part in enumerate(parts):
+                region[r * (e - s):(r + 1) * (e - s)].copy_(part)
 
     def finish(self):
         """Call after backward: reduce buckets whose hooks did not all fire (parameters without gradient this step,

@@ -63,12 +63,15 @@ class _FlatPolySGD:
         self.neg_lr.fill_(-self.lr0 * mult)
         self.global_step += 1
 
-    def update(self, s=0, e=None):           # graph-capturable; [s, e): the slice of the flat buffers to update (default: all)
+    def update(self, s=0, e=None, grad=None):
+        """graph-capturable; [s, e): the slice of the flat buffers to update (default: all); grad: the gradients of that slice when
+        they do not live in the flat gradient buffer (reduce-scattered slice of a sharded optimiser)."""
         e = self.flat_param.numel() if e is None else e
+        g = self.flat_grad[s:e] if grad is None else grad
         if self.flat_param.is_cuda:
-            ops.sgd_momentum_step(self.flat_param[s:e], self.flat_grad[s:e], self.buf[s:e], self.flat_param16[s:e], self.mom, self.neg_lr)
+            ops.sgd_momentum_step(self.flat_param[s:e], g, self.buf[s:e], self.flat_param16[s:e], self.mom, self.neg_lr)
         else:                   # CPU unit tests of the host logic (gloo)
-            self.buf[s:e].mul_(self.mom).add_(self.flat_grad[s:e])
+            self.buf[s:e].mul_(self.mom).add_(g)
             self.flat_param[s:e].addcmul_(self.buf[s:e], self.neg_lr)
             self.flat_param16[s:e].copy_(self.flat_param[s:e])
 
@@ -110,8 +113,23 @@ class Trainer:
                 for t in list(model.parameters()) + list(model.buffers()):
                     dist.broadcast(t.data, 0)
         self.graph = (self.dev.type == "cuda") if cuda_graph is None else bool(cuda_graph)
+        import os
+        # Sharded optimiser (several ranks, bf16 trunk): the training step reads the trunk's Linear weights only through their
+        # persistent bf16 copies, so their fp32 masters and momentum need to be current on ONE rank each.  Gradients of that region
+        # are reduce-scattered, every rank updates its 1/W slice and the bf16 copies are all-gathered: 3/4 of the all-reduce's
+        # bytes, and the HBM-bound optimiser kernel shrinks W-fold.  The small rest (LayerNorm, embeddings, cls_head) stays
+        # replicated behind an all-reduce.  ACR_SHARDED_OPT=0 restores the plain all-reduce + full update.
+        big = []
+        if self.graph and self.world > 1 and getattr(model, "precision", "fp32") == "bf16" and os.environ.get("ACR_SHARDED_OPT", "1") != "0":
+            for mod in model.pretrained.model.blocks.modules():
+                if isinstance(mod, torch.nn.Linear) and mod.weight.requires_grad:
+                    big.append(mod.weight)
+                    if mod.bias is not None and mod.bias.requires_grad:
+                        big.append(mod.bias)
+        self.sharded = len(big) > 0
+        self._master_stale = False
         # parameters the ACR path never reaches get no gradient in the reference either
-        self.buckets = GradBuckets(list(model.parameters()), bucket_bytes, hooks=not self.graph)
+        self.buckets = GradBuckets(list(model.parameters()), bucket_bytes, hooks=not self.graph, sharded=big or None)
         if self.graph:
             self.opt = _FlatPolySGD(self.buckets.params, self.buckets.flat, self.buckets.offsets, lr, wt_dec, max_step)
             if getattr(model, "precision", "fp32") == "bf16":
@@ -120,7 +138,6 @@ class Trainer:
             self.opt = PolyOptimizer(model.parameters(), lr=lr, weight_decay=wt_dec, max_step=max_step)
         # weights loaded AFTER construction (model.load / load_state_dict copy into the flat master buffer in place) must
         # reach the persistent bf16 copy the trunk's Linear layers read
-        import os
         # slices of the gradient all-reduce -> optimiser pipeline.  Measured on 2 x B200: 1 / 2 / 4 / 8 slices = 13.97 / 13.83 / 14.01 /
         # 14.07 ms per step (13.43 on one GPU): the HBM-bound optimiser kernel does not overlap the NCCL kernels in practice.
         self.reduce_chunks = int(os.environ.get("ACR_AR_CHUNKS", "1"))
@@ -140,11 +157,22 @@ class Trainer:
         """Re-cast the fp32 master weights into the persistent bf16 copy (normally refreshed inside the optimiser step only).
         Call after writing to the parameters by hand; load_state_dict() does it through a post-hook."""
         if self.graph and hasattr(self.opt, "flat_param16"):
+            self.sync_master()
             self.opt.flat_param16.copy_(self.opt.flat_param)
+
+    def sync_master(self):
+        """Sharded optimiser only: make every rank's fp32 master weights current again (each rank updates only its slice of the
+        trunk's Linear weights during training).  Call before reading the parameters in fp32: state_dict() / checkpoints,
+        evaluation or CAM inference on the trained model, check_replicas_in_sync() (which calls it)."""
+        if self.sharded and self._master_stale:
+            self.buckets.all_gather_shards(self.opt.flat_param)
+            self.buckets.all_gather_shards(self.opt.buf)
+            self._master_stale = False
 
     def check_replicas_in_sync(self):
         """Max |parameter checksum difference| across ranks (0.0 on one rank): every rank must hold bit-identical weights after
         an all-reduced step.  One small all-gather; meant for tests and bench.py, not for the hot loop."""
+        self.sync_master()
         flat = self.opt.flat_param if self.graph else torch.cat([p.detach().reshape(-1).float() for p in self.buckets.params])
         cs = torch.stack([flat.double().sum(), flat.double().abs().sum(), (flat.double() * flat.double()).sum()])
         if self.world == 1:
@@ -278,6 +306,16 @@ class Trainer:
                 self._g_opt.replay()
             else:
                 self.opt.update()
+            return
+        if self.sharded:
+            b = self.buckets
+            b.reduce_sharded()
+            s, e = b.shard_range()
+            self.opt.update(s, e, grad=b.grad_shard)                    # this rank's slice of the trunk weights
+            if b.flat.numel() > b.shard_end:
+                self.opt.update(b.shard_end, b.flat.numel())            # the replicated rest, identical on every rank
+            b.all_gather_shards(self.opt.flat_param16)                  # everyone's refreshed bf16 weights
+            self._master_stale = True
             return
         for s, e in self.buckets.reduce_chunks(self.reduce_chunks):
             self.opt.update(s, e)

@@ -66,6 +66,44 @@ def _worker(rank, world, port, out):
     both = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(both, chk)
     ok = ok and float((both[0] - both[1]).abs()) == 0.0
+    # sharded optimiser (Trainer._reduce_and_update with self.sharded): reduce-scatter of the sharded region + all-reduce of the
+    # rest, every rank updating its slice, all-gather of the bf16 copies.  The bf16 copies are complete on every rank right after
+    # the step; after the sync (all-gather of the fp32 masters) the weights equal those of the plain all-reduce + full update.
+    def make():
+        torch.manual_seed(1)
+        return torch.nn.Sequential(torch.nn.Linear(16, 40), torch.nn.ReLU(), torch.nn.Linear(40, 8), torch.nn.LayerNorm(8), torch.nn.Linear(8, 4))
+
+    def run(sharded):
+        n3 = make()
+        big = [n3[0].weight, n3[0].bias, n3[2].weight] if sharded else None
+        gb3 = GradBuckets(list(n3.parameters()), hooks=False, sharded=big)
+        opt3 = _FlatPolySGD(gb3.params, gb3.flat, gb3.offsets, lr=0.1, wt_dec=0.5, max_step=10)
+        for _ in range(3):
+            gb3.zero()
+            n3(x).pow(2).sum().backward()
+            opt3.set_lr_for_step()
+            if sharded:
+                gb3.reduce_sharded()
+                s_, e_ = gb3.shard_range()
+                opt3.update(s_, e_, grad=gb3.grad_shard)
+                opt3.update(gb3.shard_end, gb3.flat.numel())
+                gb3.all_gather_shards(opt3.flat_param16)
+                stale = {n: p.detach().clone() for n, p in n3.named_parameters()}
+                gb3.all_gather_shards(opt3.flat_param)      # (this toy net reads the fp32 masters; the bf16 trunk reads the copies)
+            else:
+                gb3.reduce_all()
+                opt3.update()
+        p16 = {n: opt3.flat_param16[gb3.offsets[p]:gb3.offsets[p] + p.numel()].clone() for n, p in n3.named_parameters()}
+        if not sharded:
+            stale = None
+        return {n: p.detach().clone() for n, p in n3.named_parameters()}, p16, stale, gb3
+
+    ref_p, ref_16, _, _ = run(False)
+    sh_p, sh_16, sh_stale, gbs = run(True)
+    ok = ok and gbs.shard_end > 0 and gbs.shard_end % (128 * world) == 0 and gbs.shard_end < gbs.flat.numel()
+    ok = ok and all(torch.allclose(ref_p[n], sh_p[n], atol=1e-6) for n in ref_p)              # fp32 masters after the sync
+    ok = ok and all(torch.equal(ref_16[n], sh_16[n]) for n in ref_16)                         # bf16 copies right after the step
+    ok = ok and not all(torch.allclose(ref_p[n], sh_stale[n], atol=1e-6) for n in ref_p)      # (the masters really were sharded)
     shards = shard_indices(11, rank, world)
     out[rank] = (ok, shards)
     dist.destroy_process_group()
