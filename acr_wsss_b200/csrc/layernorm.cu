@@ -7,7 +7,7 @@
 // d-gamma / d-beta partial sums of the columns it owns in registers; CTAs write one partial row each and a second tiny
 // kernel folds them in a fixed order (deterministic, no atomics).  Stock PyTorch spends 105 us per call in its
 // gamma/beta backward at [12560, 768]; the whole backward here is bounded by ~130 MB of traffic.
-#include "common.cuh"
+#include "attn_tc.cuh"
 #include <cuda_bf16.h>
 
 namespace {
@@ -286,11 +286,8 @@ int launch_bwd(const void* dy, int dy_bf16, const void* dres, const void* x, int
   do {                                                                                                                      \
     auto kfn = layernorm_bwd_kernel<VEC, DYB, XB, CS>;                                                                      \
     const size_t smem = (size_t)(CS ? 3 : 2) * kWarpsPerCta * E * sizeof(float);                                            \
-    static bool attr_set = false;                                                                                           \
-    if (!attr_set) {                                                                                                        \
-      ACR_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                          \
-      attr_set = true;                                                                                                      \
-    }                                                                                                                       \
+    static bool attr_set[64] = {false};       /* per device: the attribute is a per-device property of the kernel */      \
+    if (int e_ = acr_attn::set_max_smem(kfn, smem, attr_set)) return e_;                                                    \
     kfn<<<ctas, T, smem, st>>>(dy, dres, x, mean, rstd, gamma, M, rows_per_cta, dx, pg, pb, pc);                            \
   } while (0)
   if (pc != nullptr) {          // column sums of dx: bf16 stream only (the trunk's residual path)

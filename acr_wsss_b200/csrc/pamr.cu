@@ -472,11 +472,8 @@ template <int ND, int CG>
 int launch_iter_smem(const float* wgt, const float* cur, float* dst, int B, int C, int H, int W, const Dil& dil, cudaStream_t st) {
   const int groups = (C + CG - 1) / CG;
   const size_t smem = (size_t)CG * kPamrTS * kPamrTS * sizeof(float);
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    ACR_CUDA(cudaFuncSetAttribute(pamr_iter_smem_kernel<ND, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = smem;
-  }
+  static bool attr_set[64] = {false};
+  if (int e = acr_attn::set_max_smem(pamr_iter_smem_kernel<ND, CG>, smem, attr_set)) return e;
   dim3 grid((W + kPamrTile - 1) / kPamrTile, (H + kPamrTile - 1) / kPamrTile, B * groups);
   pamr_iter_smem_kernel<ND, CG><<<grid, 512, smem, st>>>(wgt, cur, dst, C, H, W, dil, groups);
   return acr::check_launch("pamr_iter_smem_kernel");

@@ -693,15 +693,14 @@ def test_densecrf_loss_k81_matches_reference_filter(dev):
     assert rel_err(t2n(seg.grad), t2n(seg2.grad)) < 1e-5
 
 
-@pytest.mark.parametrize("B,P,C", [(2, 4, 5), (1, 7, 80), (2, 3, 1)])
-def test_dense_crf_from_patch_logits_matches_composition(dev, B, P, C):
+@pytest.mark.parametrize("B,P,C,S", [(2, 4, 5, 64), (1, 7, 80, 112), (2, 3, 1, 48), (1, 5, 3, 46), (1, 9, 4, 18)])
+def test_dense_crf_from_patch_logits_matches_composition(dev, B, P, C, S):
     """The fused head of the dense-CRF term (ops.crf_head: bilinear up-sampling of the patch logits, softmax over [background,
     classes], rloss down-scaling) against the library composition the reference-shaped path uses: probabilities, the loss and its
     gradient with respect to the patch logits."""
     import torch.nn.functional as F
     from acr_wsss_b200 import ops, synth, dense_crf_loss, dense_crf_loss_from_patch_logits
-    S = 16 * P
-    g = torch.Generator().manual_seed(P * C)
+    g = torch.Generator().manual_seed(P * C)          # (S / P = 16 as in the model, and non-integer / small ratios of the general kernels)
     z = (torch.randn(B, P * P, C, generator=g) * 2.0).to(dev)
     img = synth.smooth_rgb(B, S, S, seed=1).to(dev)
 
