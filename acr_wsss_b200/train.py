@@ -142,6 +142,9 @@ class Trainer:
         # 14.07 ms per step (13.43 on one GPU): the HBM-bound optimiser kernel does not overlap the NCCL kernels in practice.
         self.reduce_chunks = int(os.environ.get("ACR_AR_CHUNKS", "1"))
         self._load_hook = model.register_load_state_dict_post_hook(lambda module, incompatible: self.refresh_bf16())
+        # sharded optimiser: the fp32 masters of the trunk weights are current on one rank each -- reading them without a sync would
+        # silently save stale weights, so state_dict() refuses until sync_master() has run on every rank (Trainer.state_dict does both)
+        self._sd_hook = model.register_state_dict_pre_hook(lambda module, prefix, keep_vars: self._guard_stale())
         self._img = None
         self._label = None
         self._g_fb = None
@@ -159,6 +162,16 @@ class Trainer:
         if self.graph and hasattr(self.opt, "flat_param16"):
             self.sync_master()
             self.opt.flat_param16.copy_(self.opt.flat_param)
+
+    def _guard_stale(self):
+        if self.sharded and self._master_stale:
+            raise RuntimeError("Trainer (sharded optimiser): the fp32 master weights are sharded across ranks; call trainer.sync_master() "
+                               "-- or trainer.state_dict() -- on EVERY rank before reading model.state_dict()")
+
+    def state_dict(self):
+        """model.state_dict() with every rank's fp32 master weights made current first (a collective: call it on all ranks)."""
+        self.sync_master()
+        return self.model.state_dict()
 
     def sync_master(self):
         """Sharded optimiser only: make every rank's fp32 master weights current again (each rank updates only its slice of the

@@ -9,8 +9,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
   python bench.py --steps 2 --warmup 3 --no-cam --no-cpu-baseline --profile-range > gpurun_out/ncu_launch_${TAG}.log 2>&1
 echo "launch list rc=$?"
 timeout 120 python scripts/bench_attn.py 16 785 12 64 > gpurun_out/bench_attn_${TAG}.json || exit 1
+# bench_attn.py runs the backward 11 times each without G, with fp32 G and with sign codes (the training step's mode): skip into the third block
 for K in attn_bwd_kernel attn_fwd_kernel attn_mean_kernel; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip 4 -c 2 -f -o gpurun_out/prof_${K}_${TAG} \
+  SKIP=4; [ $K = attn_bwd_kernel ] && SKIP=26
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip $SKIP -c 2 -f -o gpurun_out/prof_${K}_${TAG} \
     python scripts/bench_attn.py 16 785 12 64 > gpurun_out/ncu_${K}_${TAG}.log 2>&1
   echo "$K capture rc=$?"
 done
