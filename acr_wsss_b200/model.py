@@ -83,7 +83,22 @@ class Attention(nn.Module):
         return None
 
     def get_attn_gradients(self):
-        return self._state.get("attn_grad")
+        """dP [B,H,N,N] of the last backward (what the reference's hook keeps, vision_transformer.py:192-193,209).  The exact path
+        stores it; the fused path never forms it (the backward kernel keeps row 0 only, which is all getam uses), so it is
+        recomputed here on demand from what that backward saw: dP_h = dO_h V_h^T (+ G/H when an affinity gradient came with it)."""
+        st = self._state
+        if st.get("attn_grad") is not None:
+            return st["attn_grad"]
+        if st.get("d_out") is not None and st.get("qkv") is not None:
+            qkv, d_out = st["qkv"], st["d_out"]
+            B, N, _ = qkv.shape
+            H = self.num_heads
+            v = qkv.view(B, N, 3, H, -1)[:, :, 2].float()                      # [B,N,H,D]
+            dP = torch.einsum("bnhd,bmhd->bhnm", d_out.view(B, N, H, -1).float(), v)
+            if st.get("g_dense") is not None:
+                dP = dP + st["g_dense"].unsqueeze(1) / H
+            return dP
+        return None
 
     def get_attn_row0(self):
         """Per-head cls-token row of P, [B,H,N]."""
@@ -446,7 +461,8 @@ class ACR(nn.Module):
 
         attn_list[l] is the head-mean map [B,N,N] as in the reference.  cam_list[l] is c_l restricted to
         row 0, shape [1,1,N] (the only row the reference's result and its caller use, DPT/ACR.py:213 /
-        infer_cam.py:180-184); pass full=True on the fp32 path to get the reference's full [1,N,N] maps.
+        infer_cam.py:180-184); pass full=True to get the reference's full [1,N,N] maps (on the fused path P and dP are
+        recomputed on demand for that, see Attention.get_attn / get_attn_gradients).
         """
         blocks = self.pretrained.model.blocks
         skip = 1      # (2 for the distilled DeiT variant, DPT/ACR.py:210-211: a hybrid/distilled backbone is outside the hot path --

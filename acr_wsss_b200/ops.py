@@ -210,6 +210,10 @@ class _AttnCoreBF16(torch.autograd.Function):
               _p(d_qkv), _p(g_row0), _p(ws), wsb, _stream())
         if want_row0:
             ctx.state["grad_row0"] = g_row0
+            # what Attention.get_attn_gradients() needs to rebuild the full dP on demand (accessor protocol; 2 B x N x E bytes)
+            ctx.state["d_out"] = d_out
+            ctx.state["g_dense"] = (g_mean if g_mean is not None else
+                                    (decode_sign_codes(code, N, w_cls, w_aff, g_scale) if code is not None else None))
         return d_qkv, None, None, None, None
 
 

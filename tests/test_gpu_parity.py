@@ -539,6 +539,33 @@ def test_attention_bf16_backward_vs_oracle(dev, B, N, H, with_g):
     assert rel_err(t2n(st["grad_row0"]), t2n(dP_r[:, :, 0, :])) < BF16_TOL
 
 
+def test_fused_path_accessors_full_maps(dev):
+    """Accessor protocol on the fused bf16 path (vision_transformer.py:186-196, DPT/ACR.py:182-183,206): get_attn() and
+    get_attn_gradients() return the full [B,H,N,N] maps (recomputed on demand: the kernels keep row 0 only), consistent with the
+    row-0 quantities the kernels wrote, and getam(full=True) returns full [1,N,N] per-block maps whose row 0 is the default result."""
+    from acr_wsss_b200 import synth
+    orc = _orc()
+    C, S = 20, 64
+    m, _ = _build(dev, C, "vitb", "bf16", 2.0)
+    m.eval()
+    img = synth.images(1, S, seed=3).to(dev)
+    cls_pred, _, attn, _ = m.forward_cam(img)
+    m.zero_grad(set_to_none=False)
+    cls_pred[0, 7].backward(retain_graph=True)
+    blk = m.pretrained.model.blocks[-1].attn
+    N = (S // 16) ** 2 + 1
+    P, dP = blk.get_attn(), blk.get_attn_gradients()
+    assert P.shape == (1, 12, N, N) and dP is not None and dP.shape == (1, 12, N, N)
+    assert rel_err(t2n(P[:, :, 0, :]), t2n(blk.get_attn_row0())) < 1e-2
+    assert rel_err(t2n(dP[:, :, 0, :]), t2n(blk.get_attn_gradients_row0())) < 1e-2
+    assert rel_err(t2n(P.mean(1)), t2n(attn[:, -1])) < 1e-2                      # head mean of the recomputed maps = the stacked map
+    cam, _, cams = m.getam(0, start_layer=10, func="cam_grad_s")
+    cam_f, _, cams_f = m.getam(0, start_layer=10, func="cam_grad_s", full=True)
+    assert cams_f[0].shape == (1, N, N) and rel_err(t2n(cam_f), t2n(cam)) < 1e-6
+    for a, b in zip(cams, cams_f):
+        assert rel_err(t2n(b[0, 0]), t2n(a.reshape(-1))) < 2e-2
+
+
 def test_attention_bf16_scale2_tokens_vs_exact_path(dev):
     """N = 3137 (896x896 input, scale 2.0 of infer_cam.py's multi-scale list): the fused bf16 kernels, forward and backward
     with an affinity gradient, against this repo's exact fp32 CUDA path (itself pinned to the oracle at smaller N) -- the
