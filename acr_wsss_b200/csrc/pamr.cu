@@ -318,11 +318,11 @@ constexpr int kPamrStage = kPamrCh * kPamrTS * kPamrTS;            // floats per
 // the issue slots, ALU pipe 39 %, shared-memory pipe 45 %).
 __host__ __device__ constexpr int std_dil(int i) { return i == 0 ? 1 : i == 1 ? 2 : i == 2 ? 4 : i == 3 ? 8 : i == 4 ? 12 : 24; }
 
-// taps of NCH channels of one stage for this thread's two pixels
-template <int ND, int NCH, bool STD>
+// taps of NCH channels of one stage for this thread's two pixels (rows r and r + ROW2 of a tile with row stride TS and PER floats per channel)
+template <int ND, int NCH, bool STD, int PER = kPamrTS * kPamrTS, int ROW2 = 16>
 __device__ __forceinline__ void pamr_taps(const float* __restrict__ t, int base, const Dil& dil, const float (&w0)[8 * ND], const float (&w1)[8 * ND],
                                           float (&a0)[kPamrCh], float (&a1)[kPamrCh]) {
-  constexpr int TS = kPamrTS, per = TS * TS;
+  constexpr int TS = kPamrTS, per = PER;
 #pragma unroll
   for (int c = 0; c < NCH; ++c) { a0[c] = 0.f; a1[c] = 0.f; }
 #pragma unroll
@@ -336,7 +336,7 @@ __device__ __forceinline__ void pamr_taps(const float* __restrict__ t, int base,
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         a0[c] = fmaf(w0[n], t[c * per + off], a0[c]);
-        a1[c] = fmaf(w1[n], t[c * per + off + 16 * TS], a1[c]);
+        a1[c] = fmaf(w1[n], t[c * per + off + ROW2 * TS], a1[c]);
       }
     }
   }
@@ -348,7 +348,9 @@ __device__ __forceinline__ void pamr_taps(const float* __restrict__ t, int base,
 // memory cost 23 us of an 69 us iteration at cfg3: it doubles the time of the CTAs every wave waits for).
 // dst_pad = 0: the last iteration writes the caller's unpadded output.
 // (A persistent variant -- one CTA per SM walking over the work items with the TMA ring running across items -- was 40 %
-// SLOWER: the per-item state pushed the 96 weight registers into local memory, profiles/r02_ncu_pamr_persistent.txt.)
+// SLOWER: the per-item state pushed the 96 weight registers into local memory, profiles/r02_ncu_pamr_persistent.txt.  A
+// one-pixel-per-thread variant of the half-height kernel below -- 512 threads, 48 weights, two CTAs per SM at 64 registers -- spilt
+// 56 of its 48+ live values as well and was 10 % slower than the two-pixel version.)
 template <int ND, int CG, bool STD>
 __global__ void __launch_bounds__(512, 1)
 pamr_iter_tma_kernel(const __grid_constant__ CUtensorMap tmap_mask, const float* __restrict__ wgt, float* __restrict__ mout,
@@ -424,6 +426,81 @@ pamr_iter_tma_kernel(const __grid_constant__ CUtensorMap tmap_mask, const float*
   }
 }
 
+// Half-height variant, TWO CTAs per SM (the shipped one): 32 x 16 output tiles, 256 threads, a single 61 KB stage per CTA.
+// ncu on the kernel above (profiles/r02_ncu_refine_kernels.txt): half of its stall time is the un-overlapped prologue -- 96 weight
+// loads per thread -- and the per-chunk TMA waits, with all 16 warps of the SM in the same phase.  Two independent CTAs per SM put
+// one CTA's prologue / TMA round trip under the other's tap loop; registers (128 x 512 threads) and tap order are unchanged.
+constexpr int kPamrTileH2 = 16;
+constexpr int kPamrTSY2 = kPamrTileH2 + 2 * kPamrHalo;             // 64 rows
+constexpr int kPamrStage2 = kPamrCh * kPamrTSY2 * kPamrTS;         // floats per stage (61,440 B)
+template <int ND, int CG, bool STD>
+__global__ void __launch_bounds__(256, 2)
+pamr_iter_tma2_kernel(const __grid_constant__ CUtensorMap tmap_mask, const float* __restrict__ wgt, float* __restrict__ mout,
+                      int C, int H, int W, Dil dil, int groups, int dst_pad) {
+  extern __shared__ __align__(128) float tile[];                  // [kPamrCh][TSY2][TS], then the mbarrier
+  constexpr int TS = kPamrTS, R = kPamrHalo;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tile + kPamrStage2);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8 threads, two rows per thread (ty, ty + 8)
+  const int x0 = blockIdx.x * kPamrTile, y0 = blockIdx.y * kPamrTileH2;
+  const int b = blockIdx.z / groups, g = blockIdx.z % groups;
+  const int c0 = g * CG, cend = min(C, c0 + CG);
+  const int nchunks = (cend - c0 + kPamrCh - 1) / kPamrCh;
+  const long long HW = (long long)H * W;
+  auto issue = [&](int k) {
+    tc::mbar_arrive_expect_tx(full, kPamrStage2 * sizeof(float));
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     tc::smem_u32(tile)),
+                 "l"(reinterpret_cast<uint64_t>(&tmap_mask)), "r"(tc::smem_u32(full)), "r"(x0), "r"(y0), "r"(b * C + c0 + k * kPamrCh)
+                 : "memory");
+  };
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmap_mask);
+    tc::mbar_init(full, 1);
+    tc::fence_barrier_init();
+    issue(0);
+  }
+  const int px = x0 + tx, py0 = y0 + ty, py1 = y0 + ty + 8;
+  const bool ok0 = px < W && py0 < H, ok1 = px < W && py1 < H;
+  float w0[8 * ND], w1[8 * ND];
+  {
+    const float* p0 = wgt + (long long)b * (8 * ND) * HW + (long long)min(py0, H - 1) * W + min(px, W - 1);
+    const float* p1 = wgt + (long long)b * (8 * ND) * HW + (long long)min(py1, H - 1) * W + min(px, W - 1);
+#pragma unroll
+    for (int n = 0; n < 8 * ND; ++n) {
+      w0[n] = __ldg(p0);
+      w1[n] = __ldg(p1);
+      p0 += HW;
+      p1 += HW;
+    }
+  }
+  __syncthreads();                                                 // barrier initialisation visible to every waiter
+  const int base = (ty + R) * TS + tx + R;
+  const int Wd = W + 2 * dst_pad;
+  const long long HWd = (long long)(H + 2 * dst_pad) * Wd;
+  for (int k = 0; k < nchunks; ++k) {
+    tc::mbar_wait(full, k & 1);
+    float a0[kPamrCh], a1[kPamrCh];
+    const int nch = min(kPamrCh, cend - (c0 + k * kPamrCh));
+    if (nch == kPamrCh) pamr_taps<ND, kPamrCh, STD, kPamrTSY2 * kPamrTS, 8>(tile, base, dil, w0, w1, a0, a1);
+    else if (nch == 2) pamr_taps<ND, 2, STD, kPamrTSY2 * kPamrTS, 8>(tile, base, dil, w0, w1, a0, a1);
+    else pamr_taps<ND, 1, STD, kPamrTSY2 * kPamrTS, 8>(tile, base, dil, w0, w1, a0, a1);
+    __syncthreads();                                               // every thread is done with the stage
+    if (threadIdx.x == 0 && k + 1 < nchunks) {
+      tc::fence_proxy_async_smem();
+      issue(k + 1);
+    }
+    float* op = mout + ((long long)b * C + c0 + k * kPamrCh) * HWd;
+    op += (long long)dst_pad * Wd + dst_pad + px;
+#pragma unroll
+    for (int c = 0; c < kPamrCh; ++c) {
+      if (c < nch) {
+        if (ok0) op[c * HWd + (long long)py0 * Wd] = a0[c];
+        if (ok1) op[c * HWd + (long long)py1 * Wd] = a1[c];
+      }
+    }
+  }
+}
+
 // Ring of a padded mask buffer [planes, H + 2R, W + 2R]: every cell outside the image repeats the nearest image pixel
 // (pamr.py:51 pads with 'replicate').  One thread per ring cell: 4 (H + W + 2R) R cells per plane.
 __global__ void __launch_bounds__(256)
@@ -444,12 +521,12 @@ pamr_pad_kernel(float* __restrict__ buf, int planes, int H, int W) {
   plane[(long long)yp * Wp + xp] = plane[(long long)ys * Wp + xs];
 }
 
-int make_mask_tmap(CUtensorMap* m, const float* base, int planes, int H, int W) {      // H, W: PADDED extents
+int make_mask_tmap(CUtensorMap* m, const float* base, int planes, int H, int W, int box_h = kPamrTS) {      // H, W: PADDED extents
   acr_attn::EncodeTiledFn fn = acr_attn::get_encode_fn();
   ACR_REQUIRE(fn != nullptr, ACR_E_NOSM100, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
   cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kPamrTS, (cuuint32_t)kPamrTS, (cuuint32_t)kPamrCh};
+  cuuint32_t box[3] = {(cuuint32_t)kPamrTS, (cuuint32_t)box_h, (cuuint32_t)kPamrCh};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -466,6 +543,17 @@ int launch_iter_tma(const CUtensorMap& tmap, const float* wgt, float* dst, int d
   dim3 grid((W + kPamrTile - 1) / kPamrTile, (H + kPamrTile - 1) / kPamrTile, B * groups);
   pamr_iter_tma_kernel<ND, CG, STD><<<grid, 512, smem, st>>>(tmap, wgt, dst, C, H, W, dil, groups, dst_pad);
   return acr::check_launch("pamr_iter_tma_kernel");
+}
+
+template <int ND, int CG, bool STD>
+int launch_iter_tma2(const CUtensorMap& tmap, const float* wgt, float* dst, int dst_pad, int B, int C, int H, int W, const Dil& dil, cudaStream_t st) {
+  const int groups = (C + CG - 1) / CG;
+  const size_t smem = (size_t)kPamrStage2 * sizeof(float) + 64;
+  static bool attr_set[64] = {false};
+  if (int e = acr_attn::set_max_smem(pamr_iter_tma2_kernel<ND, CG, STD>, smem, attr_set)) return e;
+  dim3 grid((W + kPamrTile - 1) / kPamrTile, (H + kPamrTileH2 - 1) / kPamrTileH2, B * groups);
+  pamr_iter_tma2_kernel<ND, CG, STD><<<grid, 256, smem, st>>>(tmap, wgt, dst, C, H, W, dil, groups, dst_pad);
+  return acr::check_launch("pamr_iter_tma2_kernel");
 }
 
 template <int ND, int CG>
@@ -515,9 +603,11 @@ int pamr_iterate(const float* wgt, float* ping, float* pong, float* out, int B, 
   const bool smem_ok = (cfg == 100 || cfg == 101) && dil.n <= 6 && R <= kPamrHalo && (long long)B * ((C + kCG - 1) / kCG) <= 65535;
   const bool tma_ok = padded;
   CUtensorMap tm_ping, tm_pong;
+  static const bool full_tiles = getenv("ACR_PAMR_TILE32") != nullptr;      // A/B switch: the 32 x 32-tile, one-CTA-per-SM kernel
+  const int box_h = full_tiles ? kPamrTS : kPamrTSY2;
   if (tma_ok) {
-    if (int e = make_mask_tmap(&tm_ping, ping, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo)) return e;
-    if (int e = make_mask_tmap(&tm_pong, pong, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo)) return e;
+    if (int e = make_mask_tmap(&tm_ping, ping, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo, box_h)) return e;
+    if (int e = make_mask_tmap(&tm_pong, pong, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo, box_h)) return e;
   }
   const float* cur = ping;
   for (int it = 0; it < num_iter; ++it) {
@@ -529,8 +619,25 @@ int pamr_iterate(const float* wgt, float* ping, float* pong, float* out, int B, 
       const int dp = last ? 0 : kPamrHalo;
       bool std6 = dil.n == 6;
       for (int i = 0; i < 6 && std6; ++i) std6 = dil.d[i] == std_dil(i);
-      if (std6) {
+      // channel groups of 21: the 96 weight loads per thread at the head of a CTA cost about as much as the taps of 7 channels, so
+      // they are amortised over three times as many (measured at 448 x 448, C = 21: 693 -> 642 us for one image, 4708 -> 3651 us
+      // for eight; C = 81: 2237 -> 1737 us).  ACR_PAMR_CG21=0 restores groups of 7.
+      static const bool cg21 = !(getenv("ACR_PAMR_CG21") && getenv("ACR_PAMR_CG21")[0] == '0');
+      if (std6 && !full_tiles && cg21) {
+        e = launch_iter_tma2<6, 21, true>(tm, wgt, dst, dp, B, C, H, W, dil, st);
+      } else if (std6 && !full_tiles) {
+        e = launch_iter_tma2<6, kCG, true>(tm, wgt, dst, dp, B, C, H, W, dil, st);
+      } else if (std6) {
         e = launch_iter_tma<6, kCG, true>(tm, wgt, dst, dp, B, C, H, W, dil, st);
+      } else if (!full_tiles) {
+        switch (dil.n) {
+          case 1: e = launch_iter_tma2<1, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 2: e = launch_iter_tma2<2, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 3: e = launch_iter_tma2<3, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 4: e = launch_iter_tma2<4, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 5: e = launch_iter_tma2<5, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          default: e = launch_iter_tma2<6, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+        }
       } else {
         switch (dil.n) {
           case 1: e = launch_iter_tma<1, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
