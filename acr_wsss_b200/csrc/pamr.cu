@@ -435,17 +435,21 @@ constexpr int kPamrTSY2 = kPamrTileH2 + 2 * kPamrHalo;             // 64 rows
 constexpr int kPamrStage2 = kPamrCh * kPamrTSY2 * kPamrTS;         // floats per stage (61,440 B)
 template <int ND, int CG, bool STD>
 __global__ void __launch_bounds__(256, 2)
-pamr_iter_tma2_kernel(const __grid_constant__ CUtensorMap tmap_mask, const float* __restrict__ wgt, float* __restrict__ mout,
-                      int C, int H, int W, Dil dil, int groups, int dst_pad) {
-  extern __shared__ __align__(128) float tile[];                  // [kPamrCh][TSY2][TS], then the mbarrier
+pamr_iter_tma2_kernel(const __grid_constant__ CUtensorMap tmap_mask, const __grid_constant__ CUtensorMap tmap_wgt,
+                      float* __restrict__ mout, int C, int H, int W, Dil dil, int groups, int dst_pad) {
+  // shared: first the 8*ND weight planes of this tile ([8*ND][16][32] floats, one TMA box: 96 loads per thread through the LSU queue
+  // were the slowest part of the CTA), then -- once they sit in registers -- the mask stage [kPamrCh][TSY2][TS]; then two mbarriers
+  extern __shared__ __align__(128) float tile[];
   constexpr int TS = kPamrTS, R = kPamrHalo;
-  uint64_t* full = reinterpret_cast<uint64_t*>(tile + kPamrStage2);
+  constexpr int kWgtFloats = 8 * ND * kPamrTileH2 * kPamrTile;
+  constexpr int kBufFloats = kWgtFloats > kPamrStage2 ? kWgtFloats : kPamrStage2;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tile + kBufFloats);
+  uint64_t* wfull = full + 1;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8 threads, two rows per thread (ty, ty + 8)
   const int x0 = blockIdx.x * kPamrTile, y0 = blockIdx.y * kPamrTileH2;
   const int b = blockIdx.z / groups, g = blockIdx.z % groups;
   const int c0 = g * CG, cend = min(C, c0 + CG);
   const int nchunks = (cend - c0 + kPamrCh - 1) / kPamrCh;
-  const long long HW = (long long)H * W;
   auto issue = [&](int k) {
     tc::mbar_arrive_expect_tx(full, kPamrStage2 * sizeof(float));
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
@@ -455,25 +459,31 @@ pamr_iter_tma2_kernel(const __grid_constant__ CUtensorMap tmap_mask, const float
   };
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmap_mask);
+    tc::prefetch_tmap(&tmap_wgt);
     tc::mbar_init(full, 1);
+    tc::mbar_init(wfull, 1);
     tc::fence_barrier_init();
-    issue(0);
+    tc::mbar_arrive_expect_tx(wfull, kWgtFloats * sizeof(float));
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     tc::smem_u32(tile)),
+                 "l"(reinterpret_cast<uint64_t>(&tmap_wgt)), "r"(tc::smem_u32(wfull)), "r"(x0), "r"(y0), "r"(b * 8 * ND)
+                 : "memory");
   }
   const int px = x0 + tx, py0 = y0 + ty, py1 = y0 + ty + 8;
   const bool ok0 = px < W && py0 < H, ok1 = px < W && py1 < H;
   float w0[8 * ND], w1[8 * ND];
-  {
-    const float* p0 = wgt + (long long)b * (8 * ND) * HW + (long long)min(py0, H - 1) * W + min(px, W - 1);
-    const float* p1 = wgt + (long long)b * (8 * ND) * HW + (long long)min(py1, H - 1) * W + min(px, W - 1);
-#pragma unroll
-    for (int n = 0; n < 8 * ND; ++n) {
-      w0[n] = __ldg(p0);
-      w1[n] = __ldg(p1);
-      p0 += HW;
-      p1 += HW;
-    }
-  }
   __syncthreads();                                                 // barrier initialisation visible to every waiter
+  tc::mbar_wait(wfull, 0);
+#pragma unroll
+  for (int n = 0; n < 8 * ND; ++n) {
+    w0[n] = tile[(n * kPamrTileH2 + ty) * kPamrTile + tx];
+    w1[n] = tile[(n * kPamrTileH2 + ty + 8) * kPamrTile + tx];
+  }
+  __syncthreads();                                                 // everyone holds its weights: the buffer becomes the mask stage
+  if (threadIdx.x == 0) {
+    tc::fence_proxy_async_smem();
+    issue(0);
+  }
   const int base = (ty + R) * TS + tx + R;
   const int Wd = W + 2 * dst_pad;
   const long long HWd = (long long)(H + 2 * dst_pad) * Wd;
@@ -546,13 +556,14 @@ int launch_iter_tma(const CUtensorMap& tmap, const float* wgt, float* dst, int d
 }
 
 template <int ND, int CG, bool STD>
-int launch_iter_tma2(const CUtensorMap& tmap, const float* wgt, float* dst, int dst_pad, int B, int C, int H, int W, const Dil& dil, cudaStream_t st) {
+int launch_iter_tma2(const CUtensorMap& tmap, const CUtensorMap& tmap_wgt, float* dst, int dst_pad, int B, int C, int H, int W, const Dil& dil, cudaStream_t st) {
   const int groups = (C + CG - 1) / CG;
-  const size_t smem = (size_t)kPamrStage2 * sizeof(float) + 64;
+  constexpr size_t wfl = (size_t)8 * ND * kPamrTileH2 * kPamrTile;
+  const size_t smem = (wfl > (size_t)kPamrStage2 ? wfl : (size_t)kPamrStage2) * sizeof(float) + 64;
   static bool attr_set[64] = {false};
   if (int e = acr_attn::set_max_smem(pamr_iter_tma2_kernel<ND, CG, STD>, smem, attr_set)) return e;
   dim3 grid((W + kPamrTile - 1) / kPamrTile, (H + kPamrTileH2 - 1) / kPamrTileH2, B * groups);
-  pamr_iter_tma2_kernel<ND, CG, STD><<<grid, 256, smem, st>>>(tmap, wgt, dst, C, H, W, dil, groups, dst_pad);
+  pamr_iter_tma2_kernel<ND, CG, STD><<<grid, 256, smem, st>>>(tmap, tmap_wgt, dst, C, H, W, dil, groups, dst_pad);
   return acr::check_launch("pamr_iter_tma2_kernel");
 }
 
@@ -605,9 +616,21 @@ int pamr_iterate(const float* wgt, float* ping, float* pong, float* out, int B, 
   CUtensorMap tm_ping, tm_pong;
   static const bool full_tiles = getenv("ACR_PAMR_TILE32") != nullptr;      // A/B switch: the 32 x 32-tile, one-CTA-per-SM kernel
   const int box_h = full_tiles ? kPamrTS : kPamrTSY2;
+  CUtensorMap tm_wgt;
   if (tma_ok) {
     if (int e = make_mask_tmap(&tm_ping, ping, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo, box_h)) return e;
     if (int e = make_mask_tmap(&tm_pong, pong, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo, box_h)) return e;
+    if (!full_tiles) {      // weight planes [B * 8 * nd, H, W]: one box = the 8 * nd planes of a 32 x 16 tile
+      acr_attn::EncodeTiledFn fn = acr_attn::get_encode_fn();
+      ACR_REQUIRE(fn != nullptr, ACR_E_NOSM100, "cuTensorMapEncodeTiled unavailable");
+      cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * 8 * dil.n};
+      cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+      cuuint32_t box[3] = {(cuuint32_t)kPamrTile, (cuuint32_t)kPamrTileH2, (cuuint32_t)(8 * dil.n)};
+      cuuint32_t estr[3] = {1, 1, 1};
+      CUresult r = fn(&tm_wgt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(wgt), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ACR_REQUIRE(r == CUDA_SUCCESS, ACR_E_INVAL, "cuTensorMapEncodeTiled(weights) failed (%d)", (int)r);
+    }
   }
   const float* cur = ping;
   for (int it = 0; it < num_iter; ++it) {
@@ -624,19 +647,19 @@ int pamr_iterate(const float* wgt, float* ping, float* pong, float* out, int B, 
       // for eight; C = 81: 2237 -> 1737 us).  ACR_PAMR_CG21=0 restores groups of 7.
       static const bool cg21 = !(getenv("ACR_PAMR_CG21") && getenv("ACR_PAMR_CG21")[0] == '0');
       if (std6 && !full_tiles && cg21) {
-        e = launch_iter_tma2<6, 21, true>(tm, wgt, dst, dp, B, C, H, W, dil, st);
+        e = launch_iter_tma2<6, 21, true>(tm, tm_wgt, dst, dp, B, C, H, W, dil, st);
       } else if (std6 && !full_tiles) {
-        e = launch_iter_tma2<6, kCG, true>(tm, wgt, dst, dp, B, C, H, W, dil, st);
+        e = launch_iter_tma2<6, kCG, true>(tm, tm_wgt, dst, dp, B, C, H, W, dil, st);
       } else if (std6) {
         e = launch_iter_tma<6, kCG, true>(tm, wgt, dst, dp, B, C, H, W, dil, st);
       } else if (!full_tiles) {
         switch (dil.n) {
-          case 1: e = launch_iter_tma2<1, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
-          case 2: e = launch_iter_tma2<2, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
-          case 3: e = launch_iter_tma2<3, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
-          case 4: e = launch_iter_tma2<4, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
-          case 5: e = launch_iter_tma2<5, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
-          default: e = launch_iter_tma2<6, kCG, false>(tm, wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 1: e = launch_iter_tma2<1, kCG, false>(tm, tm_wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 2: e = launch_iter_tma2<2, kCG, false>(tm, tm_wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 3: e = launch_iter_tma2<3, kCG, false>(tm, tm_wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 4: e = launch_iter_tma2<4, kCG, false>(tm, tm_wgt, dst, dp, B, C, H, W, dil, st); break;
+          case 5: e = launch_iter_tma2<5, kCG, false>(tm, tm_wgt, dst, dp, B, C, H, W, dil, st); break;
+          default: e = launch_iter_tma2<6, kCG, false>(tm, tm_wgt, dst, dp, B, C, H, W, dil, st); break;
         }
       } else {
         switch (dil.n) {
