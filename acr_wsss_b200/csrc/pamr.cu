@@ -426,45 +426,41 @@ pamr_iter_tma_kernel(const __grid_constant__ CUtensorMap tmap_mask, const float*
   }
 }
 
-// Half-height variant, TWO CTAs per SM (the shipped one): 32 x 16 output tiles, 256 threads, two 41 KB stages per CTA.
+// Half-height variant, TWO CTAs per SM (the shipped one): 32 x 16 output tiles, 256 threads, a single 61 KB stage per CTA.
 // ncu on the kernel above (profiles/r02_ncu_refine_kernels.txt): half of its stall time is the un-overlapped prologue -- 96 weight
 // loads per thread -- and the per-chunk TMA waits, with all 16 warps of the SM in the same phase.  Two independent CTAs per SM put
 // one CTA's prologue / TMA round trip under the other's tap loop; registers (128 x 512 threads) and tap order are unchanged.
 constexpr int kPamrTileH2 = 16;
 constexpr int kPamrTSY2 = kPamrTileH2 + 2 * kPamrHalo;             // 64 rows
-constexpr int kPamrCh2 = 2;                                        // channels per stage: two 41 KB stages fit the 98 KB weights buffer
-constexpr int kPamrStage2 = kPamrCh2 * kPamrTSY2 * kPamrTS;        // floats per stage (40,960 B)
+constexpr int kPamrStage2 = kPamrCh * kPamrTSY2 * kPamrTS;         // floats per stage (61,440 B)
 template <int ND, int CG, bool STD>
 __global__ void __launch_bounds__(256, 2)
 pamr_iter_tma2_kernel(const __grid_constant__ CUtensorMap tmap_mask, const __grid_constant__ CUtensorMap tmap_wgt,
                       float* __restrict__ mout, int C, int H, int W, Dil dil, int groups, int dst_pad) {
   // shared: first the 8*ND weight planes of this tile ([8*ND][16][32] floats, one TMA box: 96 loads per thread through the LSU queue
-  // were the slowest part of the CTA), then -- once they sit in registers -- TWO mask stages [kPamrCh2][TSY2][TS] (with a single
-  // stage a quarter of the warp samples sat in the TMA wait of every chunk); then three mbarriers
+  // were the slowest part of the CTA), then -- once they sit in registers -- the mask stage [kPamrCh][TSY2][TS]; then two mbarriers
   extern __shared__ __align__(128) float tile[];
   constexpr int TS = kPamrTS, R = kPamrHalo;
   constexpr int kWgtFloats = 8 * ND * kPamrTileH2 * kPamrTile;
-  constexpr int kBufFloats = kWgtFloats > 2 * kPamrStage2 ? kWgtFloats : 2 * kPamrStage2;
-  uint64_t* full = reinterpret_cast<uint64_t*>(tile + kBufFloats);      // full[0], full[1]
-  uint64_t* wfull = full + 2;
+  constexpr int kBufFloats = kWgtFloats > kPamrStage2 ? kWgtFloats : kPamrStage2;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tile + kBufFloats);
+  uint64_t* wfull = full + 1;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8 threads, two rows per thread (ty, ty + 8)
   const int x0 = blockIdx.x * kPamrTile, y0 = blockIdx.y * kPamrTileH2;
   const int b = blockIdx.z / groups, g = blockIdx.z % groups;
   const int c0 = g * CG, cend = min(C, c0 + CG);
-  const int nchunks = (cend - c0 + kPamrCh2 - 1) / kPamrCh2;
-  auto issue = [&](int k) {                                        // chunk k -> stage k & 1
-    const int st = k & 1;
-    tc::mbar_arrive_expect_tx(&full[st], kPamrStage2 * sizeof(float));
+  const int nchunks = (cend - c0 + kPamrCh - 1) / kPamrCh;
+  auto issue = [&](int k) {
+    tc::mbar_arrive_expect_tx(full, kPamrStage2 * sizeof(float));
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                     tc::smem_u32(tile + st * kPamrStage2)),
-                 "l"(reinterpret_cast<uint64_t>(&tmap_mask)), "r"(tc::smem_u32(&full[st])), "r"(x0), "r"(y0), "r"(b * C + c0 + k * kPamrCh2)
+                     tc::smem_u32(tile)),
+                 "l"(reinterpret_cast<uint64_t>(&tmap_mask)), "r"(tc::smem_u32(full)), "r"(x0), "r"(y0), "r"(b * C + c0 + k * kPamrCh)
                  : "memory");
   };
   if (threadIdx.x == 0) {
     tc::prefetch_tmap(&tmap_mask);
     tc::prefetch_tmap(&tmap_wgt);
-    tc::mbar_init(&full[0], 1);
-    tc::mbar_init(&full[1], 1);
+    tc::mbar_init(full, 1);
     tc::mbar_init(wfull, 1);
     tc::fence_barrier_init();
     tc::mbar_arrive_expect_tx(wfull, kWgtFloats * sizeof(float));
@@ -487,28 +483,26 @@ pamr_iter_tma2_kernel(const __grid_constant__ CUtensorMap tmap_mask, const __gri
   if (threadIdx.x == 0) {
     tc::fence_proxy_async_smem();
     issue(0);
-    if (nchunks > 1) issue(1);
   }
   const int base = (ty + R) * TS + tx + R;
   const int Wd = W + 2 * dst_pad;
   const long long HWd = (long long)(H + 2 * dst_pad) * Wd;
   for (int k = 0; k < nchunks; ++k) {
-    const int st = k & 1;
-    const float* t = tile + st * kPamrStage2;
-    tc::mbar_wait(&full[st], (k >> 1) & 1);
+    tc::mbar_wait(full, k & 1);
     float a0[kPamrCh], a1[kPamrCh];
-    const int nch = min(kPamrCh2, cend - (c0 + k * kPamrCh2));
-    if (nch == 2) pamr_taps<ND, 2, STD, kPamrTSY2 * kPamrTS, 8>(t, base, dil, w0, w1, a0, a1);
-    else pamr_taps<ND, 1, STD, kPamrTSY2 * kPamrTS, 8>(t, base, dil, w0, w1, a0, a1);
-    __syncthreads();                                               // every thread is done with stage st
-    if (threadIdx.x == 0 && k + 2 < nchunks) {
+    const int nch = min(kPamrCh, cend - (c0 + k * kPamrCh));
+    if (nch == kPamrCh) pamr_taps<ND, kPamrCh, STD, kPamrTSY2 * kPamrTS, 8>(tile, base, dil, w0, w1, a0, a1);
+    else if (nch == 2) pamr_taps<ND, 2, STD, kPamrTSY2 * kPamrTS, 8>(tile, base, dil, w0, w1, a0, a1);
+    else pamr_taps<ND, 1, STD, kPamrTSY2 * kPamrTS, 8>(tile, base, dil, w0, w1, a0, a1);
+    __syncthreads();                                               // every thread is done with the stage
+    if (threadIdx.x == 0 && k + 1 < nchunks) {
       tc::fence_proxy_async_smem();
-      issue(k + 2);
+      issue(k + 1);
     }
-    float* op = mout + ((long long)b * C + c0 + k * kPamrCh2) * HWd;
+    float* op = mout + ((long long)b * C + c0 + k * kPamrCh) * HWd;
     op += (long long)dst_pad * Wd + dst_pad + px;
 #pragma unroll
-    for (int c = 0; c < kPamrCh2; ++c) {
+    for (int c = 0; c < kPamrCh; ++c) {
       if (c < nch) {
         if (ok0) op[c * HWd + (long long)py0 * Wd] = a0[c];
         if (ok1) op[c * HWd + (long long)py1 * Wd] = a1[c];
@@ -537,12 +531,12 @@ pamr_pad_kernel(float* __restrict__ buf, int planes, int H, int W) {
   plane[(long long)yp * Wp + xp] = plane[(long long)ys * Wp + xs];
 }
 
-int make_mask_tmap(CUtensorMap* m, const float* base, int planes, int H, int W, int box_h = kPamrTS, int box_c = kPamrCh) {      // H, W: PADDED extents
+int make_mask_tmap(CUtensorMap* m, const float* base, int planes, int H, int W, int box_h = kPamrTS) {      // H, W: PADDED extents
   acr_attn::EncodeTiledFn fn = acr_attn::get_encode_fn();
   ACR_REQUIRE(fn != nullptr, ACR_E_NOSM100, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
   cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kPamrTS, (cuuint32_t)box_h, (cuuint32_t)box_c};
+  cuuint32_t box[3] = {(cuuint32_t)kPamrTS, (cuuint32_t)box_h, (cuuint32_t)kPamrCh};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -565,7 +559,7 @@ template <int ND, int CG, bool STD>
 int launch_iter_tma2(const CUtensorMap& tmap, const CUtensorMap& tmap_wgt, float* dst, int dst_pad, int B, int C, int H, int W, const Dil& dil, cudaStream_t st) {
   const int groups = (C + CG - 1) / CG;
   constexpr size_t wfl = (size_t)8 * ND * kPamrTileH2 * kPamrTile;
-  const size_t smem = (wfl > (size_t)2 * kPamrStage2 ? wfl : (size_t)2 * kPamrStage2) * sizeof(float) + 64;
+  const size_t smem = (wfl > (size_t)kPamrStage2 ? wfl : (size_t)kPamrStage2) * sizeof(float) + 64;
   static bool attr_set[64] = {false};
   if (int e = acr_attn::set_max_smem(pamr_iter_tma2_kernel<ND, CG, STD>, smem, attr_set)) return e;
   dim3 grid((W + kPamrTile - 1) / kPamrTile, (H + kPamrTileH2 - 1) / kPamrTileH2, B * groups);
@@ -624,8 +618,8 @@ int pamr_iterate(const float* wgt, float* ping, float* pong, float* out, int B, 
   const int box_h = full_tiles ? kPamrTS : kPamrTSY2;
   CUtensorMap tm_wgt;
   if (tma_ok) {
-    if (int e = make_mask_tmap(&tm_ping, ping, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo, box_h, full_tiles ? kPamrCh : kPamrCh2)) return e;
-    if (int e = make_mask_tmap(&tm_pong, pong, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo, box_h, full_tiles ? kPamrCh : kPamrCh2)) return e;
+    if (int e = make_mask_tmap(&tm_ping, ping, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo, box_h)) return e;
+    if (int e = make_mask_tmap(&tm_pong, pong, B * C, H + 2 * kPamrHalo, W + 2 * kPamrHalo, box_h)) return e;
     if (!full_tiles) {      // weight planes [B * 8 * nd, H, W]: one box = the 8 * nd planes of a 32 x 16 tile
       acr_attn::EncodeTiledFn fn = acr_attn::get_encode_fn();
       ACR_REQUIRE(fn != nullptr, ACR_E_NOSM100, "cuTensorMapEncodeTiled unavailable");
