@@ -184,16 +184,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
         }
       }
       const float ms = m * scale_log2;
-      float rowsum = 0.f;
+      // fp32x2: one FFMA2 + one FADD2 per pair of keys instead of two FFMA + two FADD
+      const uint64_t sc2 = tc::f2_pack(scale_log2, scale_log2), nms2 = tc::f2_pack(-ms, -ms);
+      uint64_t rs2 = tc::f2_pack(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
         if (c < nch) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = tc::fast_exp2(fmaf(__uint_as_float(r[c * 32 + 2 * i]), scale_log2, -ms));
-            const float p1 = tc::fast_exp2(fmaf(__uint_as_float(r[c * 32 + 2 * i + 1]), scale_log2, -ms));
-            rowsum += p0 + p1;
+            float x0, x1;
+            tc::f2_unpack(tc::f2_fma(tc::f2_pack(__uint_as_float(r[c * 32 + 2 * i]), __uint_as_float(r[c * 32 + 2 * i + 1])), sc2, nms2), x0, x1);
+            const float p0 = tc::fast_exp2(x0), p1 = tc::fast_exp2(x1);
+            rs2 = tc::f2_add(rs2, tc::f2_pack(p0, p1));
             pk[i] = tc::pack_bf16(p0, p1);
           }
         } else {                                     // keys past N: P = 0 (V rows there are zero-filled, 0 * garbage must stay finite)
@@ -205,7 +208,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
       tc::tmem_st_wait();
       tc::tc_fence_before();
       tc::mbar_arrive(&s.p_full);
-      l += rowsum;
+      float rs_lo, rs_hi;
+      tc::f2_unpack(rs2, rs_lo, rs_hi);
+      l += rs_lo + rs_hi;
     }
     if (rows_live) {
       tc::mbar_wait(&s.o_full, (ntiles - 1) & 1);
@@ -375,12 +380,23 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
         if (!live || (tail && colbase >= N)) break;
         tc::tmem_ld32(tmem + ab * 128 + lane_off + slice * MEAN_COLS + c * 32, r);
         tc::tmem_ld_wait();
-        if (!tail) {
+        if (!tail) {               // fp32x2: 16 FFMA2 + 32 MUFU.EX2 + 16 FADD2 (or FFMA2) per head and thread
+          const uint64_t sc2 = tc::f2_pack(scale_log2, scale_log2), nl2 = tc::f2_pack(-lse2, -lse2);
+          uint64_t part2 = tc::f2_pack(0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float p = tc::fast_exp2(fmaf(__uint_as_float(r[i]), scale_log2, -lse2));
-            if (MODE == 0) { acc[c * 32 + i] += p; r[i] = __float_as_uint(p); } else part = fmaf(p, acc[c * 32 + i], part);
+          for (int i = 0; i < 32; i += 2) {
+            float x0, x1;
+            tc::f2_unpack(tc::f2_fma(tc::f2_pack(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), sc2, nl2), x0, x1);
+            const float p0 = tc::fast_exp2(x0), p1 = tc::fast_exp2(x1);
+            const uint64_t pp = tc::f2_pack(p0, p1), aa = tc::f2_pack(acc[c * 32 + i], acc[c * 32 + i + 1]);
+            if (MODE == 0) {
+              tc::f2_unpack(tc::f2_add(aa, pp), acc[c * 32 + i], acc[c * 32 + i + 1]);
+              r[i] = __float_as_uint(p0); r[i + 1] = __float_as_uint(p1);
+            } else {
+              part2 = tc::f2_fma(pp, aa, part2);
+            }
           }
+          if (MODE == 1) { float a0, a1; tc::f2_unpack(part2, a0, a1); part += a0 + a1; }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {

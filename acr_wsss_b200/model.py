@@ -240,12 +240,14 @@ class VisionTransformer(nn.Module):
         posemb_grid = posemb_grid.permute(0, 2, 3, 1).reshape(1, gs_h * gs_w, -1)
         return torch.cat([posemb_tok, posemb_grid], dim=1)
 
-    def forward_flex(self, x, last_block_out=None, replicate_at=None, replicas=1):
+    def forward_flex(self, x, last_block_out=None, replicate_at=None, replicas=1, need_norm=True):
         """vision_transformer.py:449-486.  Returns (norm(x), None); `last_block_out`, if a list, receives the
         un-normalised output of the last block (what the reference reads through its forward hook, Q4).
         replicate_at / replicas: batched GETAM -- the input of block `replicate_at` is detached and
         repeated `replicas` times along the batch, so ONE backward with one one-hot cotangent per replica yields the
-        per-class attention gradients of blocks >= replicate_at; the replicated leaf is kept in self._rep_in."""
+        per-class attention gradients of blocks >= replicate_at; the replicated leaf is kept in self._rep_in.
+        need_norm=False skips the final LayerNorm (returns (None, None)): the ACR heads read the un-normalised output of
+        the last block (DPT/ACR.py:95-96 discards the return value and reads activations["4"]), so on that path the reference computes norm(x) and drops it."""
         b, c, h, w = x.shape
         pos_embed = self._resize_pos_embed(self.pos_embed, h // self.patch_size[1], w // self.patch_size[0])
         # patch_embed.proj is a stride-16 16x16 convolution (vision_transformer.py:463-464) == one GEMM over
@@ -289,7 +291,7 @@ class VisionTransformer(nn.Module):
                 x = blk(x)
         if last_block_out is not None:
             last_block_out.append(x)
-        return self.norm(x), None
+        return (self.norm(x) if need_norm else None), None
 
 
 class _Pretrained(nn.Module):
@@ -360,9 +362,9 @@ class ACR(nn.Module):
         last = []
         if self.precision == "bf16":
             with torch.autocast("cuda", dtype=torch.bfloat16):
-                vit.forward_flex(x, last)
+                vit.forward_flex(x, last, need_norm=False)
         else:
-            vit.forward_flex(x, last)
+            vit.forward_flex(x, last, need_norm=False)
         layer_4 = last[0].float()
         self.pretrained.activations["4"] = layer_4
         for blk in vit.blocks:
@@ -420,9 +422,9 @@ class ACR(nn.Module):
         with torch.enable_grad():
             if self.precision == "bf16":
                 with torch.autocast("cuda", dtype=torch.bfloat16):
-                    vit.forward_flex(x, last, replicate_at=start_layer, replicas=replicas)
+                    vit.forward_flex(x, last, replicate_at=start_layer, replicas=replicas, need_norm=False)
             else:
-                vit.forward_flex(x, last, replicate_at=start_layer, replicas=replicas)
+                vit.forward_flex(x, last, replicate_at=start_layer, replicas=replicas, need_norm=False)
             layer_4 = last[0].float()
             x_cls = self.cls_head(layer_4[:, 0, :])
         for blk in vit.blocks:

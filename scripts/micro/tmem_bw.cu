@@ -1,8 +1,23 @@
-// Microbenchmark: TMEM -> register read bandwidth of tcgen05.ld.32x32b.x32 with 4 / 8 / 16 reading warps per SM.
+// Microbenchmark: TMEM -> register read bandwidth of tcgen05.ld with 4 / 8 / 16 reading warps per SM.
+//   mode 0: 32x32b.x32 + wait per 32 columns;  mode 1: four 32x32b.x32 in flight, one wait;  mode 2: 16x256b.x8 (same 32 registers)
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tmem_bw tmem_bw.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 #include "../../acr_wsss_b200/csrc/tc_common.cuh"
 
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(640) tmem_read_kernel(int iters, int nread_warps, unsigned long long* cycles, float* sink) {
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5;
@@ -11,43 +26,63 @@ __global__ void __launch_bounds__(640) tmem_read_kernel(int iters, int nread_war
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = tmem_base;
-  float acc = 0.f;
+  uint32_t acc = 0;
   unsigned long long t0 = 0, t1 = 0;
   if (warp >= 4 && warp < 4 + nread_warps) {
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const int grp = (warp - 4) >> 2;                 // column group of 128
-    uint32_t r[32];
     asm volatile("bar.sync 1, %0;" ::"r"(nread_warps * 32) : "memory");
     t0 = clock64();
     for (int it = 0; it < iters; ++it) {
+      if (MODE == 0) {
+        uint32_t r[32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tc::tmem_ld32(tmem + lane_off + ((grp * 128 + c * 32) & 511), r);
+        for (int c = 0; c < 4; ++c) {
+          tc::tmem_ld32(tmem + lane_off + ((grp * 128 + c * 32) & 511), r);
+          tc::tmem_ld_wait();
+          acc ^= r[0] ^ r[31];
+        }
+      } else if (MODE == 1) {
+        uint32_t r[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tc::tmem_ld32(tmem + lane_off + ((grp * 128 + c * 32) & 511), r + c * 32);
         tc::tmem_ld_wait();
+        acc ^= r[0] ^ r[127] ^ r[40] ^ r[70];
+      } else {
+        uint32_t r[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc += __uint_as_float(r[i]);
+        for (int c = 0; c < 4; ++c) {          // 16 lanes x 64 columns per instruction: two per 32-lane x 32-column block
+          tmem_ld_16x256b_x8(tmem + lane_off + grp * 128 + (c & 1) * 64, r);
+          tc::tmem_ld_wait();
+          acc ^= r[0] ^ r[31];
+        }
       }
     }
     t1 = clock64();
     if (threadIdx.x == 128) cycles[blockIdx.x] = t1 - t0;
   }
-  if (acc == 123.456f) sink[0] = acc;
+  if (acc == 0x12345678u) sink[0] = 1.f;
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc::tc_fence_after(); tc::tmem_dealloc<512>(tmem); }
 }
 
+template <int MODE>
+void run(unsigned long long* d_c, float* d_s) {
+  for (int nw : {4, 8, 16}) {
+    const int iters = 2000;
+    tmem_read_kernel<MODE><<<148, 640>>>(iters, nw, d_c, d_s);
+    cudaDeviceSynchronize();
+    unsigned long long c[148]; cudaMemcpy(c, d_c, sizeof(c), cudaMemcpyDeviceToHost);
+    // bytes read per SM: each reading warp reads 32 lanes x 128 cols x 4 B per iteration (mode 2: 16 lanes x 64 cols x 4 per instruction)
+    double bytes = (double)nw * 32 * 128 * 4 * iters;
+    printf("mode %d read warps %2d: %llu cycles, %.1f B/clk/SM  (err=%s)\n", MODE, nw, c[0], bytes / (double)c[0], cudaGetErrorString(cudaGetLastError()));
+  }
+}
+
 int main() {
   unsigned long long* d_c; float* d_s;
   cudaMalloc(&d_c, 148 * 8); cudaMalloc(&d_s, 4);
-  for (int nw : {4, 8, 16}) {
-    const int iters = 2000;
-    tmem_read_kernel<<<148, 640>>>(iters, nw, d_c, d_s);
-    cudaDeviceSynchronize();
-    unsigned long long c[148]; cudaMemcpy(c, d_c, sizeof(c), cudaMemcpyDeviceToHost);
-    // bytes read per SM: each reading warp reads 32 lanes x 128 cols x 4 B per iteration
-    double bytes = (double)nw * 32 * 128 * 4 * iters;
-    printf("read warps %2d: %llu cycles, %.1f B/clk/SM  (err=%s)\n", nw, c[0], bytes / (double)c[0], cudaGetErrorString(cudaGetLastError()));
-  }
+  run<0>(d_c, d_s); run<1>(d_c, d_s); run<2>(d_c, d_s);
   return 0;
 }
