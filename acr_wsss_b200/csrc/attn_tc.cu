@@ -22,22 +22,41 @@ struct FwdSmem {
   uint8_t q[TILE_BYTES];
   uint8_t k[2][TILE_BYTES];
   uint8_t v[2][TILE_BYTES];
+  float mx[2][2][BM];                // row maxima of the two column halves, double-buffered over key tiles
+  float lsum[2][BM];                 // row sums of the two column halves (epilogue)
   uint64_t q_full, kv_full[2], kv_empty[2], s_full, s_free, p_full, o_full;
   uint32_t tmem_base;
 };
 
-// 2 CTAs per SM: 256 threads x 128 registers at launch; the control warpgroup (TMA / MMA issue / TMEM alloc) hands
-// its registers to the softmax warpgroup (setmaxnreg), so one CTA's softmax overlaps the other's MMAs.
+// 2 CTAs per SM, 384 threads: a control warpgroup (TMA / MMA issue / TMEM alloc) that hands its registers to EIGHT softmax
+// warps (setmaxnreg 40 / 96).  A softmax thread owns one query row and 64 of the 128 key columns of a tile (warps 4-7: columns
+// 0-63, warps 8-11: columns 64-127; warp % 4 = TMEM lane quadrant), so every scheduler holds four softmax warps (two per
+// resident CTA).  Knock-out builds of the previous version (4 softmax warps per CTA, a row x 128 columns per thread: 96 us per
+// launch at 16 images) ran in 74 us with BOTH MMAs and all exponentials removed: three quarters of the kernel were the
+// ~850-instruction per-tile stream of a warp and its barrier waits with two warps per scheduler to hide them.
 //
-// Per key tile the softmax warps read S out of TMEM ONCE (128 columns into registers) and hand tS back at once (s_free),
-// so the MMA warp issues S(j+1) under the exponentials of tile j.  O never leaves TMEM during the loop: the P.V MMAs
-// accumulate in place, and a row is rescaled (tcgen05.ld / multiply / tcgen05.st, warp-uniform decision) only when its
-// running maximum grew by more than 2^8 since the last rescale -- P stays <= 2^8, far inside bf16 / fp32 range, and the
-// final O / l is exact whatever stabiliser was used.  (clock64 timeline of the previous version, which re-read S for a
-// separate max pass and pulled O into registers every tile: 4100 cycles per tile, of which 700 max pass, 1000 waiting
-// for the P.V round trip, 230 O update.)
+// Per key tile a thread reads its S columns out of TMEM twice (reads cost ~70 cycles per 64 KB tile): pass 1 for the row
+// maximum, exchanged with the partner warp through shared memory, pass 2 for the exponentials; tS is handed back (s_free)
+// after the last load of pass 2, so the MMA warp issues S(j+1) under the second half of the exponentials and the P.V MMA.
+// (Running the exponentials of tile j ahead of the wait for the P.V MMA of tile j-1, with P(j) held as 32 packed registers and
+// only its TMEM stores behind o_full, measured 3 % slower: that chain is not what bounds the tile.)
+// O never leaves TMEM during the loop: the P.V MMAs accumulate in place, and a row is rescaled (each warp of a pair takes
+// 32 of the 64 columns; warp-uniform decision, identical in both warps) only when its running maximum grew by more than 2^8
+// since the last rescale -- P stays <= 2^8, far inside bf16 / fp32 range, and the final O / l is exact whatever stabiliser
+// was used.
 constexpr float kRescaleThreshold = 8.f;          // log2 units
-__global__ void __launch_bounds__(256, 2)
+constexpr int FWD_THREADS = 384;
+// named barrier of the two softmax warps that share a lane quadrant (immediate ids: a register id makes ptxas reserve all 16
+// barriers of the SM for one CTA)
+__device__ __forceinline__ void fwd_pair_sync(int quad) {
+  switch (quad) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+__global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse,
                 int N, int H, float scale_log2) {
   extern __shared__ uint8_t smem_raw[];
@@ -51,8 +70,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
     tc::mbar_init(&s.q_full, 1);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&s.kv_full[i], 1); tc::mbar_init(&s.kv_empty[i], 1); }
     tc::mbar_init(&s.s_full, 1);
-    tc::mbar_init(&s.s_free, 128);
-    tc::mbar_init(&s.p_full, 128);
+    tc::mbar_init(&s.s_free, 256);
+    tc::mbar_init(&s.p_full, 256);
     tc::mbar_init(&s.o_full, 1);
     tc::fence_barrier_init();
   }
@@ -99,7 +118,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
     issue_s(0);
     for (int j = 0; j < ntiles; ++j) {
       const int st = j & 1;
-      if (j + 1 < ntiles) {                      // S(j+1) as soon as the softmax warps hold S(j) in registers
+      if (j + 1 < ntiles) {                      // S(j+1) as soon as the softmax warps have read S(j) for the last time
         tc::mbar_wait(&s.kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
         tc::mbar_wait(&s.s_free, j & 1);
         tc::tc_fence_after();
@@ -119,14 +138,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
   } else if (warp < 4) {
     tc::reg_dealloc<40>();
   } else {
-    tc::reg_alloc<216>();
-    const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    float m = -INFINITY, l = 0.f;      // m: the stabiliser in use = row max of the RAW scores at the last rescale
-    uint32_t r[BN];
+    tc::reg_alloc<96>();
+    const int half = (warp - 4) >> 2;              // key columns half*64 .. half*64+63 of every tile
+    const int quad = warp & 3;                     // TMEM lane quadrant = warp % 4
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const int cb = half * 64;
+    float m = -INFINITY, l = 0.f;      // m: the stabiliser in use = row max of the RAW scores at the last rescale; l: this half's row sum
+    uint32_t r[32];
     // N = p*p+1 leaves a thin last tile: warps whose 32 query rows all lie past N only keep the barrier protocol going
-    // (their TMEM lanes hold garbage that is never stored).
-    const bool rows_live = q0 + (warp & 3) * 32 < N;
+    // (their TMEM lanes hold garbage that is never stored).  Both warps of a pair share their rows, so they agree.
+    const bool rows_live = q0 + quad * 32 < N;
     for (int j = 0; j < ntiles; ++j) {
       tc::mbar_wait(&s.s_full, j & 1);
       tc::tc_fence_after();
@@ -139,26 +161,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
         tc::mbar_wait(&s.p_full, j & 1);
         continue;
       }
-      const int col0 = j * BN;
-      const int ncols = min(BN, N - col0);           // valid key columns of this tile
-      const int nch = (ncols + 31) >> 5;             // 32-column chunks that hold any (warp-uniform)
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < nch) tc::tmem_ld32(tS + lane_off + c * 32, r + c * 32);
-      tc::tmem_ld_wait();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&s.s_free);                    // tS may be overwritten by S(j+1)
+      const int ncols = min(BN, N - j * BN);         // valid key columns of this tile
+      const bool full = (ncols == BN);
+      // ---- pass 1: row maximum of this thread's 64 columns
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < nch) {
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = cb + c * 32;
+        if (c0 < ncols) {                              // warp-uniform
+          tc::tmem_ld32(tS + lane_off + c0, r);
+          tc::tmem_ld_wait();
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            if (c * 32 + i >= ncols) r[c * 32 + i] = 0xff800000u;      // -inf: keys past N
-            mx = fmaxf(mx, __uint_as_float(r[c * 32 + i]));
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c0 + i < ncols) ? __uint_as_float(r[i]) : -INFINITY);
           }
         }
       }
+      s.mx[j & 1][half][row] = mx;
+      fwd_pair_sync(quad);       // the two warps that share these 32 rows
+      mx = fmaxf(mx, s.mx[j & 1][half ^ 1][row]);
       // the previous P.V MMA must have retired before tP is rewritten (and before O may be rescaled)
       if (j > 0) {
         tc::mbar_wait(&s.o_full, (j - 1) & 1);
@@ -171,39 +195,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
         if (__any_sync(0xffffffffu, need)) {         // rare after the first tiles; warp-collective TMEM access
           const float alpha = need ? tc::fast_exp2((m - mx) * scale_log2) : 1.f;
           if (need) { m = mx; l *= alpha; }
-          uint32_t o[32];
+          tc::tmem_ld32(tO + lane_off + half * 32, r);         // this warp's 32 of the 64 columns of O
+          tc::tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            tc::tmem_ld32(tO + lane_off + c * 32, o);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tc::tmem_st16(tO + lane_off + c * 32, o);
-            tc::tmem_st16(tO + lane_off + c * 32 + 16, o + 16);
-          }
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tc::tmem_st16(tO + lane_off + half * 32, r);
+          tc::tmem_st16(tO + lane_off + half * 32 + 16, r + 16);
         }
       }
+      // ---- pass 2: P = exp2(S * scale - m * scale) as bf16 into TMEM, row sum (fp32x2: one FFMA2 + one FADD2 per pair of keys)
       const float ms = m * scale_log2;
-      // fp32x2: one FFMA2 + one FADD2 per pair of keys instead of two FFMA + two FADD
       const uint64_t sc2 = tc::f2_pack(scale_log2, scale_log2), nms2 = tc::f2_pack(-ms, -ms);
       uint64_t rs2 = tc::f2_pack(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
+        const int c0 = cb + c * 32;
+        const bool any = c0 < ncols;                   // warp-uniform
+        if (any) {
+          tc::tmem_ld32(tS + lane_off + c0, r);
+          tc::tmem_ld_wait();
+        }
+        if (c == 1) {                                  // last read of S(j): tS may be overwritten by S(j+1)
+          tc::tc_fence_before();
+          tc::mbar_arrive(&s.s_free);
+        }
         uint32_t pk[16];
-        if (c < nch) {
+        if (any) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float x0, x1;
-            tc::f2_unpack(tc::f2_fma(tc::f2_pack(__uint_as_float(r[c * 32 + 2 * i]), __uint_as_float(r[c * 32 + 2 * i + 1])), sc2, nms2), x0, x1);
-            const float p0 = tc::fast_exp2(x0), p1 = tc::fast_exp2(x1);
+            tc::f2_unpack(tc::f2_fma(tc::f2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), sc2, nms2), x0, x1);
+            float p0 = tc::fast_exp2(x0), p1 = tc::fast_exp2(x1);
+            if (!full) {                               // keys past N
+              if (c0 + 2 * i >= ncols) p0 = 0.f;
+              if (c0 + 2 * i + 1 >= ncols) p1 = 0.f;
+            }
             rs2 = tc::f2_add(rs2, tc::f2_pack(p0, p1));
             pk[i] = tc::pack_bf16(p0, p1);
           }
-        } else {                                     // keys past N: P = 0 (V rows there are zero-filled, 0 * garbage must stay finite)
+        } else {                                       // keys past N: P = 0 (V rows there are zero-filled, 0 * garbage must stay finite)
 #pragma unroll
           for (int i = 0; i < 16; ++i) pk[i] = 0u;
         }
-        tc::tmem_st16(tP + lane_off + c * 16, pk);
+        tc::tmem_st16(tP + lane_off + half * 32 + c * 16, pk);
       }
       tc::tmem_st_wait();
       tc::tc_fence_before();
@@ -213,25 +247,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
       l += rs_lo + rs_hi;
     }
     if (rows_live) {
+      s.lsum[half][row] = l;
+      fwd_pair_sync(quad);
+      l += s.lsum[half ^ 1][row];
       tc::mbar_wait(&s.o_full, (ntiles - 1) & 1);
       tc::tc_fence_after();
-      uint32_t o[HD];
-      tc::tmem_ld32(tO + lane_off, o);
-      tc::tmem_ld32(tO + lane_off + 32, o + 32);
+      tc::tmem_ld32(tO + lane_off + half * 32, r);
       tc::tmem_ld_wait();
       if (q0 + row < N) {
         const float inv = 1.f / l;
-        __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * ((size_t)H * HD) + (size_t)h * HD;
+        __nv_bfloat16* dst = out + ((size_t)b * N + q0 + row) * ((size_t)H * HD) + (size_t)h * HD + half * 32;
 #pragma unroll
-        for (int c = 0; c < HD / 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint4 v;
-          v.x = tc::pack_bf16(__uint_as_float(o[c * 8 + 0]) * inv, __uint_as_float(o[c * 8 + 1]) * inv);
-          v.y = tc::pack_bf16(__uint_as_float(o[c * 8 + 2]) * inv, __uint_as_float(o[c * 8 + 3]) * inv);
-          v.z = tc::pack_bf16(__uint_as_float(o[c * 8 + 4]) * inv, __uint_as_float(o[c * 8 + 5]) * inv);
-          v.w = tc::pack_bf16(__uint_as_float(o[c * 8 + 6]) * inv, __uint_as_float(o[c * 8 + 7]) * inv);
+          v.x = tc::pack_bf16(__uint_as_float(r[c * 8 + 0]) * inv, __uint_as_float(r[c * 8 + 1]) * inv);
+          v.y = tc::pack_bf16(__uint_as_float(r[c * 8 + 2]) * inv, __uint_as_float(r[c * 8 + 3]) * inv);
+          v.z = tc::pack_bf16(__uint_as_float(r[c * 8 + 4]) * inv, __uint_as_float(r[c * 8 + 5]) * inv);
+          v.w = tc::pack_bf16(__uint_as_float(r[c * 8 + 6]) * inv, __uint_as_float(r[c * 8 + 7]) * inv);
           reinterpret_cast<uint4*>(dst)[c] = v;
         }
-        lse[((size_t)b * H + h) * N + q0 + row] = (m * scale_log2 + log2f(l)) * kLn2;
+        if (half == 0) lse[((size_t)b * H + h) * N + q0 + row] = (m * scale_log2 + log2f(l)) * kLn2;
       }
     }
   }
@@ -507,7 +542,7 @@ extern "C" int acr_attn_fwd_bf16(const void* qkv, int B, int N, int H, int D, fl
     if (int e = set_max_smem(attn_fwd_kernel, smem, attr_set)) return e;
     dim3 grid(qt, H, B);
     acr::KernelTimer kt_("attn_fwd_kernel", st);
-    attn_fwd_kernel<<<grid, 256, smem, st>>>(tmap, (__nv_bfloat16*)out, lse, N, H, scale_log2);
+    attn_fwd_kernel<<<grid, FWD_THREADS, smem, st>>>(tmap, (__nv_bfloat16*)out, lse, N, H, scale_log2);
     if (int e = acr::check_launch("attn_fwd_kernel")) return e;
   }
   if (attn_mean) {
