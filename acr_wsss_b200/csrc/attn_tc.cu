@@ -280,9 +280,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, __nv_bfloat16* __r
 
 // ---------------------------------------------------------------------------------------------
 constexpr int MEAN_STAGES = 3;
+constexpr int MEAN_SW_SLICES = 4;              // = MEAN_SW / 4 column slices of a tile (declared further down)
 struct MeanSmem {
   uint8_t qk[MEAN_STAGES][2][TILE_BYTES];      // [stage][0=Q,1=K]; reused as the fp32 staging tile at the end
   float lse2[MEAN_MAX_H][BM];
+  float part[MEAN_SW_SLICES][MEAN_MAX_H][BM];  // MODE 1: per-head row sums of the four column slices (one global atomic per row, head and CTA)
   uint64_t full[MEAN_STAGES], empty[MEAN_STAGES], t_full[2], t_empty[2];
   uint32_t tmem_base;
 };
@@ -296,6 +298,7 @@ static_assert(sizeof(float) * BM * STAGE_LD <= sizeof(uint8_t) * MEAN_STAGES * 2
 // wait -> tcgen05.ld -> wait -> 32 exponentials of a warp is latency bound (clock64 timeline: 1500 cycles per head against
 // ~600 cycles of SFU work with 2 warps per scheduler), more resident warps hide it.
 constexpr int MEAN_SW = 16;
+static_assert(MEAN_SW == 4 * MEAN_SW_SLICES, "slices of the softmax warps");
 constexpr int MEAN_COLS = BN / (MEAN_SW / 4);      // 32
 constexpr int MEAN_THREADS = 128 + MEAN_SW * 32;   // 640
 
@@ -449,7 +452,21 @@ attn_mean_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const float* __re
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&s.t_empty[ab]);
-      if (MODE == 1 && row_ok && live) atomicAdd(p_row0 + ((size_t)b * H + h) * N + q0 + row, part);
+      if (MODE == 1) s.part[slice][h][row] = part;
+    }
+    if (MODE == 1) {
+      // delta[b,h,q] += the four slices' sums: ONE atomic per (row, head) of the CTA, issued after the head loop (one per thread
+      // and head inside the loop was 4x the atomics -- 4.8 M per launch -- in the loop's way)
+      asm volatile("bar.sync 1, %0;" ::"n"(MEAN_SW * 32) : "memory");
+      for (int idx = sidx; idx < H * BM; idx += MEAN_SW * 32) {
+        const int hh = idx / BM, rr = idx % BM;
+        if (q0 + rr < N) {
+          float v = 0.f;
+#pragma unroll
+          for (int sl = 0; sl < MEAN_SW_SLICES; ++sl) v += s.part[sl][hh][rr];
+          atomicAdd(p_row0 + ((size_t)b * H + hh) * N + q0 + rr, v);
+        }
+      }
     }
     if (MODE == 0) {
     // All MMAs have completed (the last t_full was observed) and every TMA load was consumed: the pipeline
