@@ -514,6 +514,40 @@ def test_attention_bf16_forward_vs_oracle(dev, B, N, H):
     assert float((mean.sum(-1) - 1).abs().max()) < 1e-3         # rows of a head-mean of softmaxes sum to 1
 
 
+@pytest.mark.parametrize("N", [300, 785])
+def test_attention_bf16_forward_lazy_rescale_path(dev, N):
+    """The forward kernel rescales O only when a row maximum grew by more than 2^8 since the last rescale; N(0, 1.5) inputs
+    never get there (the maximum of a later key tile exceeds the first tile's by ~2 log2 units).  Keys whose norm grows with
+    the tile index make every row with a positive projection raise its stabiliser at (almost) every tile, the rows with a
+    negative one never -- both kinds inside every warp -- and the kernel must still match the fp32 softmax of the oracle."""
+    from acr_wsss_b200 import ops
+    orc = _orc()
+    assert _sm100(), "the fused path needs sm_100a; there is no fallback"
+    B, H, D = 1, 2, 64
+    g = torch.Generator().manual_seed(7 * N)
+    qkv = torch.randn(B, N, 3, H, D, generator=g) * 1.5
+    u = torch.randn(H, D, generator=g)
+    u = u / u.norm(dim=-1, keepdim=True)
+    tile = (torch.arange(N) // 128).float().view(1, N, 1, 1)
+    qkv[:, :, 0] = qkv[:, :, 0] + 6.0 * torch.sign(torch.randn(B, N, H, 1, generator=g)) * u          # q = noise +- 6 u
+    qkv[:, :, 1] = qkv[:, :, 1] + (4.0 + 14.0 * tile) * u                                            # k = noise + (4 + 14 t) u
+    qkv = qkv.reshape(B, N, 3 * H * D).to(torch.bfloat16)
+    out_r, P_r = orc.attention_core(qkv.float(), H, D ** -0.5)
+    # the construction does what it says: raw row maxima of consecutive key tiles differ by more than 8 / (scale * log2 e) = 44
+    q = qkv.float().view(B, N, 3, H, D)[:, :, 0].permute(0, 2, 1, 3)
+    k = qkv.float().view(B, N, 3, H, D)[:, :, 1].permute(0, 2, 1, 3)
+    S = q @ k.transpose(-1, -2)
+    m0, m1 = S[..., :128].amax(-1), S[..., 128:256].amax(-1)
+    assert float((m1 - m0).max()) > 60 and float((m1 - m0).min()) < 0
+    st = {}
+    with torch.no_grad():
+        out, mean = ops.attention_core(qkv.to(dev), H, D ** -0.5, None, st, "bf16")
+    assert torch.isfinite(out.float()).all() and torch.isfinite(mean).all()
+    assert rel_err(t2n(out), t2n(out_r)) < BF16_TOL
+    assert rel_err(t2n(mean), t2n(P_r.mean(1))) < 2e-3
+    assert float((mean.sum(-1) - 1).abs().max()) < 1e-3
+
+
 @pytest.mark.parametrize("B,N,H,with_g", [(1, 1, 1, True), (2, 17, 3, True), (1, 128, 2, False), (1, 197, 12, True),
                                           (2, 785, 12, True), (1, 1025, 16, True)])
 def test_attention_bf16_backward_vs_oracle(dev, B, N, H, with_g):
